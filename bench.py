@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json: "image-encode ms + decode tokens/s, 7B q4_1").
+
+A *step* = one pass of the hot path over one synthetic batch: encode one 224x224 image (ViT-g + Q-Former + projection),
+feed the 32 embedding rows as the image prefix, then generate 128 tokens greedily (BASELINE configs[1]: "Vicuna-7B q4_1
+decode-only, 32-token image prefix + 128 generated tokens").  Reported per JSON line:
+  value      decode tokens/s with everything resident in HBM (device-chained greedy loop, CUDA-event timed)
+  e2e        the same metric through the reference-facing C ABI (minigpt4_encode_image / minigpt4_begin_chat_image /
+             128 x minigpt4_end_chat_image) with HOST buffers; host<->device copies and per-token sync inside the timing
+  encode_ms  image-encode latency (device, CUDA events) and encode_e2e_ms (wall clock through the ABI)
+  roofline   decode dequant-matvec family: algorithmic weight bytes / CUDA-event time per launch vs MEASURED_PEAKS hbm_gbs
+  cpu_baseline  the CPU oracle (a restatement of the reference's ggml path) on this box's host cores, bounded sample
+`--impl reference` times that CPU path alone (the reference itself cannot be built here: DESIGN.md "Oracle").
+N > 1 (torchrun): the LLaMA step is tensor-parallel over N GPUs (one NCCL sum per row-split matmul); "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_PREFIX, N_GEN = 32, 128
+PROMPT = "what is in this picture?"
+
+
+def model_dir() -> Path:
+    for cand in ("/dev/shm", "/tmp"):
+        try:
+            if shutil.disk_usage(cand).free > 12 << 30:
+                d = Path(cand) / "minigpt4_b200_models"
+                d.mkdir(parents=True, exist_ok=True)
+                return d
+        except OSError:
+            pass
+    d = Path("/tmp/minigpt4_b200_models")
+    d.mkdir(parents=True, exist_ok=True)
+    return d
+
+
+def ensure_models(size: str, wtype: str, blocks: int):
+    from minigpt4_cpp_b200 import modelgen as mg
+    d = model_dir()
+    dims = mg.LLAMA_7B if size == "7b" else mg.LLAMA_13B
+    llm = d / f"llama-{size}-{wtype}.bin"
+    vis = d / f"minigpt4-{size}-f16-b{blocks}.bin"
+    info = d / f"llama-{size}-{wtype}.json"
+    if not (llm.exists() and info.exists()):
+        st = mg.write_llama_ggjt(llm, mg.LlamaSpec(wtype=wtype, **dims))
+        info.write_text(json.dumps(st))
+    if not vis.exists():
+        mg.write_minigpt4(vis, mg.VisionSpec(n_blocks=blocks, n_embd_llm=dims["n_embd"], fast=True))
+    return str(vis), str(llm), json.loads(info.read_text())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_leg(vis: str, llm: str, n_tokens: int, do_encode: bool, threads: int):
+    """Time the CPU oracle (restated reference ggml path) on a bounded sample; returns dict + generated ids."""
+    from oracle import oracle as orc
+    from minigpt4_cpp_b200 import modelgen as mg
+    e = orc.OracleEngine(vis if do_encode else None, llm, n_ctx=512, n_threads=threads)
+    out = {"cores": threads, "kind": "port"}
+    if do_encode:
+        img = mg.synth_image()
+        t0 = time.perf_counter(); emb = e.encode_image(img); out["encode_ms"] = (time.perf_counter() - t0) * 1e3
+    else:
+        emb = np.random.default_rng(0).standard_normal((N_PREFIX, e.n_embd)).astype(np.float32)
+    t0 = time.perf_counter(); e.eval_embd(emb); out["prefix_ms"] = (time.perf_counter() - t0) * 1e3
+    ids = []
+    t0 = time.perf_counter()
+    for _ in range(n_tokens):
+        ids.append(e.end_chat_greedy()[0])
+    dt = time.perf_counter() - t0
+    out["value"] = n_tokens / dt
+    out["unit"] = "tokens/s"
+    out["sample"] = f"{n_tokens} greedy decode tokens after the {N_PREFIX}-row image prefix" + (", 1 image encode" if do_encode else "") + ", same synthetic weights"
+    return out, ids, emb
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vis, llm, _ = ensure_models(args.size, args.wtype, args.blocks)
+    threads = os.cpu_count() or 1
+    from oracle import oracle as orc
+    from minigpt4_cpp_b200 import modelgen as mg
+    e = orc.OracleEngine(vis, llm, n_ctx=512, n_threads=threads)
+    img = mg.synth_image()
+    n_tok = args.cpu_tokens
+    enc_ms, dec_s, step_s = [], [], []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        e.reset_chat()
+        emb = e.encode_image(img) if (it == 0 or args.cpu_encode_every_step) else emb
+        t1 = time.perf_counter()
+        e.eval_embd(emb)
+        t2 = time.perf_counter()
+        for _ in range(n_tok):
+            e.end_chat_greedy()
+        t3 = time.perf_counter()
+        if it >= args.warmup:
+            enc_ms.append((t1 - t0) * 1e3); dec_s.append(t3 - t2); step_s.append(t3 - t0)
+    v = n_tok * len(dec_s) / sum(dec_s)
+    line = {"impl": "reference", "metric": "decode tokens/s (Vicuna-7B q4_1) + image-encode ms", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(step_s) / len(step_s), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int8 x int4 dot (Q8_1 x Q4_1), f32 accumulate", "data": "synthetic",
+            "config": {"workload": f"Vicuna-{args.size} {args.wtype} decode, {N_PREFIX}-row image prefix + {n_tok} generated tokens per step (bounded CPU sample of the 128-token workload)"},
+            "encode_ms": max(enc_ms) if enc_ms else None,
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
+                             "sample": f"{len(dec_s)} steps x {n_tok} decode tokens; CPU oracle = restatement of ggml@master-31cfbb1 semantics (reference unbuildable offline)"},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="7b", choices=["7b", "13b"])
+    ap.add_argument("--wtype", default="q4_1")
+    ap.add_argument("--blocks", type=int, default=39)
+    ap.add_argument("--cpu-tokens", type=int, default=8)
+    ap.add_argument("--cpu-encode-every-step", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    import minigpt4_cpp_b200 as m
+    from minigpt4_cpp_b200 import modelgen as mg
+    lib = m.load_library()
+    ext = m.B200(lib)
+    assert ext.L.minigpt4_b200_device_count() > 0, "bench.py needs a CUDA device: the engine has no CPU path"
+    ext.L.minigpt4_b200_set_device(local)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = np.zeros(128, np.uint8)
+        if rank == 0:
+            ext.L.minigpt4_b200_tp_unique_id(uid.ctypes.data_as(ctypes.c_void_p))
+        t = torch.from_numpy(uid).cuda(); dist.broadcast(t, 0); uid = t.cpu().numpy()
+        ext.L.minigpt4_b200_tp_configure(rank, world, uid.ctypes.data_as(ctypes.c_void_p))
+    if rank == 0:
+        paths = ensure_models(args.size, args.wtype, args.blocks)
+    if dist:
+        dist.barrier()
+    vis, llm, info = ensure_models(args.size, args.wtype, args.blocks)
+
+    ctx = lib.minigpt4_model_load(vis, llm, 1, 1337, 2048, 512, 0)
+    assert ctx.ptr, "model load failed"
+    img = mg.synth_image()
+    mi = m.MiniGPT4Image(img.ctypes.data_as(ctypes.c_void_p), 224, 224, 3, m.ImageFormat.F32)
+
+    def barrier():
+        if dist:
+            import torch
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    def step(timed: bool):
+        """returns (encode_dev_ms, encode_wall_ms, chain_ms, e2e_decode_s, chain_ids, e2e_tokens)"""
+        # -- e2e leg: everything through the reference ABI with host buffers
+        lib.minigpt4_reset_chat(ctx)
+        t0 = time.perf_counter()
+        emb = lib.minigpt4_encode_image(ctx, mi)
+        enc_wall = (time.perf_counter() - t0) * 1e3
+        enc_dev = ext.stats(ctx).last_encode_ms
+        lib.minigpt4_system_prompt(ctx)
+        lib.minigpt4_begin_chat_image(ctx, emb, PROMPT)
+        t0 = time.perf_counter()
+        toks = [lib.minigpt4_end_chat_image(ctx, temp=0.0) for _ in range(N_GEN)]
+        e2e_s = time.perf_counter() - t0
+        # -- device-resident leg: 32-row prefix, then 128 greedy steps chained on the device (no host round trip)
+        lib.minigpt4_reset_chat(ctx)
+        rows = np.ctypeslib.as_array(emb.data, shape=(emb.n_embeddings,)).reshape(32, -1)
+        ext.eval_embd(ctx, rows)
+        ids, chain_ms = ext.decode_chain(ctx, N_GEN)
+        lib.minigpt4_free_embedding(emb)
+        return enc_dev, enc_wall, chain_ms, e2e_s, ids, toks
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local)
+    launches0 = ext.stats(ctx).kernel_launches
+    barrier()
+    sampler.start()
+    t_begin = time.perf_counter()
+    res = [step(True) for _ in range(args.steps)]
+    barrier()
+    wall = time.perf_counter() - t_begin
+    clocks = sampler.stop()
+    launches = ext.stats(ctx).kernel_launches - launches0
+
+    chain_ms = sum(r[2] for r in res); e2e_s = sum(r[3] for r in res)
+    enc_dev = float(np.mean([r[0] for r in res])); enc_wall = float(np.mean([r[1] for r in res]))
+    if dist:
+        import torch
+        t = torch.tensor([chain_ms, e2e_s, wall, enc_dev, enc_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        chain_ms, e2e_s, wall, enc_dev, enc_wall = t.tolist()
+    value = args.steps * N_GEN / (chain_ms * 1e-3)
+    e2e = args.steps * N_GEN / e2e_s
+
+    # roofline of the decode dequant-matvec family (CUDA events, cold weights: each launch streams a different layer)
+    st = ext.stats(ctx)
+    peak, peak_src = measured_peaks()
+    kinds = ["qkv", "wo", "gate_up", "down", "output"]
+    per_kind, tot_bytes, tot_ms = {}, 0.0, 0.0
+    for k, name in enumerate(kinds):
+        ms, nb = ext.time_matvec(ctx, k, 3)
+        n_launch = 1 if k == 4 else st.n_layer
+        per_kind[name] = {"bytes": nb, "us": ms * 1e3, "gbs": nb / ms * 1e-6, "frac": nb / ms * 1e-6 / peak}
+        tot_bytes += nb * n_launch; tot_ms += ms * n_launch
+    roofline = {"bound": "hbm", "kernel": f"matvec_kernel<{args.wtype},NT=1> (qkv/wo/gate_up/down x{st.n_layer} + output per token)",
+                "achieved": tot_bytes / tot_ms * 1e-6, "peak": peak, "unit": "GB/s", "frac": tot_bytes / tot_ms * 1e-6 / peak,
+                "traffic": None, "peak_source": peak_src, "bytes_per_token": st.llm_weight_bytes_per_token, "per_kernel": per_kind,
+                "step_effective_gbs": st.llm_weight_bytes_per_token * value * 1e-9}
+
+    line = {"metric": "decode tokens/s (Vicuna-7B q4_1, 32-row image prefix + 128 generated) + image-encode ms", "value": value, "unit": "tokens/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int4 dot (Q8_1 x Q4_1) f32-accumulate decode; f16 x f16 -> f32 tcgen05 encode", "data": "synthetic",
+            "config": {"workload": f"configs[1]: Vicuna-{args.size} {args.wtype} decode-only, {N_PREFIX}-row image prefix + {N_GEN} generated tokens; plus ViT-g f16 224x224 encode ({args.blocks} blocks) per step",
+                       "parallelism": f"tp{world}" if world > 1 else "single-gpu", "l2": "inputs larger than L2 (4.1 GB of weights streamed per token vs 126 MB L2)",
+                       "value_region": "CUDA-event time of the 128-step device-chained greedy decode loop", "n_ctx": 2048},
+            "encode_ms": enc_dev, "encode_e2e_ms": enc_wall,
+            "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": int(img.nbytes + 32 * st.n_embd * 4 + 4 * 64), "d2h_bytes_per_step": int(32 * st.n_embd * 4 + 4 * N_GEN),
+                    "path": "minigpt4_encode_image + minigpt4_begin_chat_image + 128 x minigpt4_end_chat_image(temp=0) through ctypes"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+
+    if rank == 0 and not args.no_cpu:
+        cpu, cpu_ids, _ = cpu_leg(vis, llm, args.cpu_tokens, True, os.cpu_count() or 1)
+        line["cpu_baseline"] = cpu
+        # parity spot check at full size: the oracle, fed the GPU's own embedding, must pick the same greedy ids
+        from oracle import oracle as orc
+        e = orc.OracleEngine(None, llm, n_ctx=512)
+        lib.minigpt4_reset_chat(ctx)
+        emb = ext.encode_array(ctx, img)
+        ext.eval_embd(ctx, emb); e.eval_embd(emb)
+        lg, lc = ext.logits(ctx), e.logits
+        g_ids, c_ids = [], []
+        for _ in range(args.cpu_tokens):
+            t = ext.greedy_id(ctx); g_ids.append(t); ext.eval_tokens(ctx, [t]); c_ids.append(e.end_chat_greedy()[0])
+        line["parity"] = {"logits_rel_err_after_prefix": float(np.abs(lg - lc).max() / np.abs(lc).max()), "greedy_ids_gpu": g_ids, "greedy_ids_cpu": c_ids,
+                          "match": g_ids == c_ids}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    lib.minigpt4_free(ctx)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,465 @@
+// llama.cu — host side of the device-resident LLaMA step (see llama.h, llama_kernels.cuh).
+#include "llama_kernels.cuh"
+#include "tp.h"
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+
+namespace mg4 {
+using namespace k;
+
+static size_t g_max_dyn_smem = 0;
+
+template <int WT, int NT>
+static void launch_mv(const MatvecArgs &a, int grid, size_t smem, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(matvec_kernel<WT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_dyn_smem));
+        configured = true;
+    }
+    matvec_kernel<WT, NT><<<grid, kThreads, smem, s>>>(a);
+}
+template <int WT>
+static void launch_mv_nt(int nt, const MatvecArgs &a, int grid, size_t smem, cudaStream_t s) {
+    switch (nt) {
+        case 1: launch_mv<WT, 1>(a, grid, smem, s); break;
+        case 2: launch_mv<WT, 2>(a, grid, smem, s); break;
+        case 4: launch_mv<WT, 4>(a, grid, smem, s); break;
+        default: launch_mv<WT, 8>(a, grid, smem, s); break;
+    }
+}
+static int nt_for(int ntok) { return ntok <= 1 ? 1 : ntok <= 2 ? 2 : ntok <= 4 ? 4 : 8; }
+
+static void launch_matvec(MatvecArgs a, int nt, int sm_count, cudaStream_t s, unsigned long long *counter) {
+    const int rows = a.w.rows;
+    const int target = 2 * sm_count * kWarps;
+    int rpw = (rows + target - 1) / target;
+    rpw = std::max(2, (rpw + 1) & ~1);
+    a.rows_per_warp = rpw;
+    const int grid = (rows + kWarps * rpw - 1) / (kWarps * rpw);
+    const size_t smem = (size_t)nt * act_bytes(act_of(a.w.type), a.w.cols);
+    if (smem > g_max_dyn_smem) MG4_PANIC("activation staging needs %zu B of shared memory (> %zu)", smem, g_max_dyn_smem);
+    switch (a.w.type) {
+        case GG_Q4_0: launch_mv_nt<GG_Q4_0>(nt, a, grid, smem, s); break;
+        case GG_Q4_1: launch_mv_nt<GG_Q4_1>(nt, a, grid, smem, s); break;
+        case GG_Q5_K: launch_mv_nt<GG_Q5_K>(nt, a, grid, smem, s); break;
+        case GG_Q6_K: launch_mv_nt<GG_Q6_K>(nt, a, grid, smem, s); break;
+        case GG_F16: launch_mv_nt<GG_F16>(nt, a, grid, smem, s); break;
+        default: MG4_PANIC("no matvec kernel for ggml type %d", a.w.type);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    if (counter) ++*counter;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight upload + repack
+// ------------------------------------------------------------------------------------------------
+static bool type_supported(int t) { return t == GG_Q4_0 || t == GG_Q4_1 || t == GG_Q5_K || t == GG_Q6_K || t == GG_F16; }
+
+static void qmat_alloc(QMat &m, int type, int rows, int cols) {
+    m.type = type; m.rows = (rows + 1) & ~1; m.cols = cols;
+    const size_t R = (size_t)m.rows;
+    auto zalloc = [](void **p, size_t n) { CUDA_CHECK(cudaMalloc(p, n)); CUDA_CHECK(cudaMemset(*p, 0, n)); };
+    switch (type) {
+        case GG_Q4_0: zalloc(&m.p0, R * cols / 32 * 16); zalloc(&m.p1, R * cols / 32 * 2); break;
+        case GG_Q4_1: zalloc(&m.p0, R * cols / 32 * 16); zalloc(&m.p1, R * cols / 32 * 4); break;
+        case GG_Q5_K: zalloc(&m.p0, R * cols / 256 * 128); zalloc(&m.p1, R * cols / 256 * 32); zalloc(&m.p2, R * cols / 256 * 16); break;
+        case GG_Q6_K: zalloc(&m.p0, R * cols / 256 * 128); zalloc(&m.p1, R * cols / 256 * 64); zalloc(&m.p2, R * cols / 256 * 16); zalloc(&m.p3, R * cols / 256 * 2); break;
+        case GG_F16: zalloc(&m.p0, R * cols * 2); break;
+        default: MG4_PANIC("unsupported weight type %d", type);
+    }
+    m.bytes = (size_t)rows * gg_row_bytes(type, (size_t)cols);
+}
+static void qmat_free(QMat &m) {
+    for (void **p : {&m.p0, &m.p1, &m.p2, &m.p3}) if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+struct Stager {  // raw tensor bytes -> device scratch
+    unsigned char *dev = nullptr; size_t cap = 0;
+    unsigned char *put(const void *host, size_t n) {
+        if (n > cap) { if (dev) cudaFree(dev); cap = n + (n >> 2); CUDA_CHECK(cudaMalloc((void **)&dev, cap)); }
+        CUDA_CHECK(cudaMemcpy(dev, host, n, cudaMemcpyHostToDevice));
+        return dev;
+    }
+    ~Stager() { if (dev) cudaFree(dev); }
+};
+
+// copy rows [row0,row0+nrows) x column range [col0,col0+ncols) of src into dst at dst_row = r*row_mul + row_off, dst_col0
+static void repack_into(QMat &dst, const HostTensor &src, Stager &st, int row0, int nrows, int col0, int ncols, int row_mul, int row_off, int dst_col0) {
+    const int src_cols = (int)src.ne[0];
+    const size_t rb = gg_row_bytes(src.gg, (size_t)src_cols);
+    const unsigned char *raw = st.put(src.data + (size_t)row0 * rb, (size_t)nrows * rb);
+    const int be = (int)gg_block_elems(src.gg);
+    const int src_nb = src_cols / be, blk0 = col0 / be, nblk = ncols / be, dst_nb = dst.cols / be, dblk0 = dst_col0 / be;
+    const size_t n = (size_t)nrows * nblk;
+    const int th = 256; const unsigned gr = (unsigned)((n + th - 1) / th);
+    switch (src.gg) {
+        case GG_Q4_0: repack_q4<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, false, (uint4 *)dst.p0, dst.p1, dst_nb, row_mul, row_off, dblk0); break;
+        case GG_Q4_1: repack_q4<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, true, (uint4 *)dst.p0, dst.p1, dst_nb, row_mul, row_off, dblk0); break;
+        case GG_Q5_K: repack_q5k<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, (unsigned char *)dst.p0, (unsigned char *)dst.p1, (unsigned char *)dst.p2, dst_nb, row_mul, row_off, dblk0); break;
+        case GG_Q6_K: repack_q6k<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, (unsigned char *)dst.p0, (unsigned char *)dst.p1, (unsigned char *)dst.p2, (unsigned short *)dst.p3, dst_nb, row_mul, row_off, dblk0); break;
+        case GG_F16: repack_f16<<<gr, th>>>((const unsigned short *)raw, src_cols, col0, ncols, nrows, (unsigned short *)dst.p0, dst.cols, row_mul, row_off, dst_col0); break;
+        default: MG4_PANIC("unsupported weight type %d", src.gg);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());  // the stager is reused by the next tensor
+}
+
+static float *upload_f32(const HostTensor &t) {
+    if (t.gg != GG_F32) MG4_PANIC("tensor %s must be F32", t.name.c_str());
+    float *d; CUDA_CHECK(cudaMalloc((void **)&d, t.nbytes)); CUDA_CHECK(cudaMemcpy(d, t.data, t.nbytes, cudaMemcpyHostToDevice));
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+LlamaDevice::LlamaDevice() {}
+LlamaDevice::~LlamaDevice() {
+    if (graph_) cudaGraphExecDestroy(graph_);
+    for (auto &L : layers_) { qmat_free(L.qkv); qmat_free(L.wq); qmat_free(L.wk); qmat_free(L.wv); qmat_free(L.wo); qmat_free(L.w13); qmat_free(L.w2); cudaFree(L.attn_norm); cudaFree(L.ffn_norm); }
+    qmat_free(output_);
+    for (void *p : {(void *)final_norm_, tok_raw_, (void *)kcache_, (void *)vcache_, (void *)rope_, (void *)tab_exp_, (void *)tab_silu_, (void *)x_, (void *)q_, (void *)att_,
+                    (void *)act_, (void *)logits_, (void *)partial_, (void *)embd_in_, (void *)state_}) if (p) cudaFree(p);
+    if (h_state_) cudaFreeHost(h_state_);
+    if (h_argmax_) cudaFreeHost(h_argmax_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+static inline unsigned short f2h_bits(float f) { __half h = __float2half_rn(f); unsigned short u; memcpy(&u, &h, 2); return u; }
+static inline float h2f_bits(unsigned short u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
+
+bool LlamaDevice::load(const LlamaFile &f, int n_ctx, TPLink *tp) {
+    tp_ = tp;
+    const int world = tp ? tp->world : 1, rank = tp ? tp->rank : 0;
+    d_.n_vocab = (int)f.n_vocab; d_.n_embd = (int)f.n_embd; d_.n_head = (int)f.n_head; d_.n_layer = (int)f.n_layer;
+    d_.n_ff = (int)f.n_ff(); d_.n_ctx = n_ctx; d_.head_dim = d_.n_embd / d_.n_head;
+    if (d_.head_dim != 128 || (int)f.n_rot != 128) { MG4_ERR("only head_dim 128 LLaMA models are supported (got %d)", d_.head_dim); return false; }
+    if (d_.n_head % world || d_.n_ff % (32 * world)) { MG4_ERR("tensor-parallel degree %d does not divide the model", world); return false; }
+    n_head_local_ = d_.n_head / world; n_embd_local_ = n_head_local_ * 128; n_ff_local_ = d_.n_ff / world;
+    const int E = d_.n_embd, El = n_embd_local_, FF = d_.n_ff, FFl = n_ff_local_;
+
+    int dev = 0; CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    sm_count_ = prop.multiProcessorCount;
+    g_max_dyn_smem = std::min<size_t>(prop.sharedMemPerBlockOptin, 220 * 1024) - 1024;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&ev0_)); CUDA_CHECK(cudaEventCreate(&ev1_));
+
+    Stager st;
+    bytes_per_token_ = 0;
+    layers_.resize((size_t)d_.n_layer);
+    for (int il = 0; il < d_.n_layer; ++il) {
+        Layer &L = layers_[(size_t)il];
+        const std::string p = "layers." + std::to_string(il) + ".";
+        const HostTensor &wq = f.get(p + "attention.wq.weight"), &wk = f.get(p + "attention.wk.weight"), &wv = f.get(p + "attention.wv.weight");
+        const HostTensor &wo = f.get(p + "attention.wo.weight");
+        const HostTensor &w1 = f.get(p + "feed_forward.w1.weight"), &w2 = f.get(p + "feed_forward.w2.weight"), &w3 = f.get(p + "feed_forward.w3.weight");
+        for (const HostTensor *t : {&wq, &wk, &wv, &wo, &w1, &w2, &w3}) {
+            if (!type_supported(t->gg)) { MG4_ERR("tensor %s has unsupported type %d", t->name.c_str(), t->gg); return false; }
+            const int be = (int)gg_block_elems(t->gg);
+            if (world > 1 && be > 1 && ((El % be) || (FFl % be))) { MG4_ERR("tensor-parallel split of %s is not aligned to its %d-element quant blocks", t->name.c_str(), be); return false; }
+        }
+        if (wq.ne[0] != E || wq.ne[1] != E || w1.ne[1] != FF || w2.ne[0] != FF) { MG4_ERR("unexpected tensor shapes in layer %d", il); return false; }
+        if (w1.gg != w3.gg) { MG4_ERR("w1/w3 of layer %d differ in type", il); return false; }
+        L.fused_qkv = wq.gg == wk.gg && wk.gg == wv.gg;
+        if (L.fused_qkv) {
+            qmat_alloc(L.qkv, wq.gg, 3 * El, E);
+            repack_into(L.qkv, wq, st, rank * El, El, 0, E, 1, 0, 0);
+            repack_into(L.qkv, wk, st, rank * El, El, 0, E, 1, El, 0);
+            repack_into(L.qkv, wv, st, rank * El, El, 0, E, 1, 2 * El, 0);
+            bytes_per_token_ += L.qkv.bytes;
+        } else {
+            qmat_alloc(L.wq, wq.gg, El, E); repack_into(L.wq, wq, st, rank * El, El, 0, E, 1, 0, 0);
+            qmat_alloc(L.wk, wk.gg, El, E); repack_into(L.wk, wk, st, rank * El, El, 0, E, 1, 0, 0);
+            qmat_alloc(L.wv, wv.gg, El, E); repack_into(L.wv, wv, st, rank * El, El, 0, E, 1, 0, 0);
+            bytes_per_token_ += L.wq.bytes + L.wk.bytes + L.wv.bytes;
+        }
+        qmat_alloc(L.wo, wo.gg, E, El); repack_into(L.wo, wo, st, 0, E, rank * El, El, 1, 0, 0);
+        qmat_alloc(L.w13, w1.gg, 2 * FFl, E);
+        repack_into(L.w13, w1, st, rank * FFl, FFl, 0, E, 2, 0, 0);
+        repack_into(L.w13, w3, st, rank * FFl, FFl, 0, E, 2, 1, 0);
+        qmat_alloc(L.w2, w2.gg, E, FFl); repack_into(L.w2, w2, st, 0, E, rank * FFl, FFl, 1, 0, 0);
+        bytes_per_token_ += L.wo.bytes + L.w13.bytes + L.w2.bytes;
+        L.attn_norm = upload_f32(f.get(p + "attention_norm.weight"));
+        L.ffn_norm = upload_f32(f.get(p + "ffn_norm.weight"));
+    }
+    {
+        const HostTensor &out = f.get("output.weight");
+        if (!type_supported(out.gg)) { MG4_ERR("output.weight has unsupported type %d", out.gg); return false; }
+        qmat_alloc(output_, out.gg, d_.n_vocab, E);
+        repack_into(output_, out, st, 0, d_.n_vocab, 0, E, 1, 0, 0);
+        bytes_per_token_ += output_.bytes;
+        final_norm_ = upload_f32(f.get("norm.weight"));
+        const HostTensor &tok = f.get("tok_embeddings.weight");
+        tok_type_ = tok.gg;
+        if (!(type_supported(tok.gg) || tok.gg == GG_F32)) { MG4_ERR("tok_embeddings has unsupported type %d", tok.gg); return false; }
+        CUDA_CHECK(cudaMalloc(&tok_raw_, tok.nbytes));
+        CUDA_CHECK(cudaMemcpy(tok_raw_, tok.data, tok.nbytes, cudaMemcpyHostToDevice));
+    }
+    // ggml's fp16 lookup tables (ggml_init): exp and silu, computed with the host libm exactly as ggml does
+    {
+        std::vector<unsigned short> te(65536), ts(65536);
+        for (int i = 0; i < 65536; ++i) { const float x = h2f_bits((unsigned short)i); te[(size_t)i] = f2h_bits(expf(x)); ts[(size_t)i] = f2h_bits(x / (1.0f + expf(-x))); }
+        CUDA_CHECK(cudaMalloc((void **)&tab_exp_, 131072)); CUDA_CHECK(cudaMemcpy(tab_exp_, te.data(), 131072, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMalloc((void **)&tab_silu_, 131072)); CUDA_CHECK(cudaMemcpy(tab_silu_, ts.data(), 131072, cudaMemcpyHostToDevice));
+    }
+    // RoPE table, mode 0: theta_i = pos * 10000^(-2i/n_rot) formed by repeated multiplication, cosf/sinf from libm (ggml_rope_f32)
+    {
+        const int hd2 = 64;
+        std::vector<float2> tab((size_t)n_ctx * hd2);
+        const float theta_scale = powf(10000.0f, -2.0f / 128.0f);
+        for (int p = 0; p < n_ctx; ++p) { float theta = (float)p; for (int i = 0; i < hd2; ++i) { tab[(size_t)p * hd2 + i] = make_float2(cosf(theta), sinf(theta)); theta *= theta_scale; } }
+        CUDA_CHECK(cudaMalloc((void **)&rope_, tab.size() * sizeof(float2)));
+        CUDA_CHECK(cudaMemcpy(rope_, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    const size_t kv = (size_t)d_.n_layer * n_ctx * El;
+    CUDA_CHECK(cudaMalloc((void **)&kcache_, kv * 2)); CUDA_CHECK(cudaMemset(kcache_, 0, kv * 2));
+    CUDA_CHECK(cudaMalloc((void **)&vcache_, kv * 2)); CUDA_CHECK(cudaMemset(vcache_, 0, kv * 2));
+    CUDA_CHECK(cudaMalloc((void **)&x_, (size_t)8 * E * 4));
+    CUDA_CHECK(cudaMalloc((void **)&q_, (size_t)8 * El * 4));
+    CUDA_CHECK(cudaMalloc((void **)&att_, (size_t)8 * El * 4));
+    CUDA_CHECK(cudaMalloc((void **)&act_, (size_t)8 * FFl * 4));
+    CUDA_CHECK(cudaMalloc((void **)&partial_, (size_t)8 * E * 4));
+    CUDA_CHECK(cudaMalloc((void **)&logits_, (size_t)(d_.n_vocab + 1) * 4));
+    CUDA_CHECK(cudaMalloc((void **)&embd_in_, (size_t)512 * E * 4));
+    CUDA_CHECK(cudaMalloc((void **)&state_, sizeof(DeviceState))); CUDA_CHECK(cudaMemset(state_, 0, sizeof(DeviceState)));
+    CUDA_CHECK(cudaHostAlloc((void **)&h_state_, sizeof(DeviceState), cudaHostAllocDefault)); memset(h_state_, 0, sizeof(DeviceState));
+    CUDA_CHECK(cudaHostAlloc((void **)&h_argmax_, 64, cudaHostAllocDefault)); *h_argmax_ = 0;
+    CUDA_CHECK(cudaDeviceSynchronize());
+    build_graph();
+    MG4_INFO("LLaMA on device: %d layers, n_embd %d, n_ff %d, vocab %d, %.1f MB streamed per token, tp %d/%d", d_.n_layer, E, FF, d_.n_vocab,
+             bytes_per_token_ / 1048576.0, rank, world);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one pass of all layers over `ntok` (<= nt) rows that sit in x_; positions/tokens come from *state_
+// ------------------------------------------------------------------------------------------------
+void LlamaDevice::launch_layers(int nt, int ntok, bool want_logits) {
+    const int E = d_.n_embd, El = n_embd_local_, FFl = n_ff_local_, C = d_.n_ctx;
+    const bool tp = tp_ && tp_->world > 1;
+    const float kq_scale = 1.0f / sqrtf((float)d_.n_embd / (float)d_.n_head);
+    const size_t attn_smem = (size_t)C * 6;
+    for (int il = 0; il < d_.n_layer; ++il) {
+        Layer &L = layers_[(size_t)il];
+        __half *kc = kcache_ + (size_t)il * C * El, *vc = vcache_ + (size_t)il * C * El;
+        MatvecArgs a{};
+        a.x = x_; a.x_stride = E; a.norm_w = L.attn_norm; a.ntok = ntok; a.epi = EPI_QKV;
+        a.q_out = q_; a.kcache = kc; a.vcache = vc; a.rope = rope_; a.e_local = El; a.half_dim = 64; a.state = state_; a.tab_silu = tab_silu_;
+        if (L.fused_qkv) { a.w = L.qkv; a.part = -1; a.n_valid = a.w.rows; launch_matvec(a, nt, sm_count_, stream_, &launches_); }
+        else {
+            const QMat *ms[3] = {&L.wq, &L.wk, &L.wv};
+            for (int part = 0; part < 3; ++part) { a.w = *ms[part]; a.part = part; a.n_valid = a.w.rows; launch_matvec(a, nt, sm_count_, stream_, &launches_); }
+        }
+        attn_kernel<<<dim3((unsigned)n_head_local_, (unsigned)ntok), 256, attn_smem, stream_>>>(q_, kc, vc, att_, state_, El, C, kq_scale, tab_exp_);
+        CUDA_CHECK(cudaGetLastError()); ++launches_;
+
+        MatvecArgs b{};
+        b.w = L.wo; b.x = att_; b.x_stride = El; b.norm_w = nullptr; b.ntok = ntok; b.n_valid = b.w.rows; b.state = state_; b.tab_silu = tab_silu_;
+        if (!tp) { b.epi = EPI_RESID; b.out = x_; b.out_stride = E; b.resid = x_; launch_matvec(b, nt, sm_count_, stream_, &launches_); }
+        else {
+            b.epi = EPI_PLAIN; b.out = partial_; b.out_stride = E; launch_matvec(b, nt, sm_count_, stream_, &launches_);
+            tp_->all_reduce_sum(partial_, (size_t)ntok * E, stream_);
+            add_kernel<<<(ntok * E + 255) / 256, 256, 0, stream_>>>(x_, partial_, ntok * E); ++launches_;
+        }
+        MatvecArgs c{};
+        c.w = L.w13; c.x = x_; c.x_stride = E; c.norm_w = L.ffn_norm; c.ntok = ntok; c.epi = EPI_SWIGLU; c.out = act_; c.out_stride = FFl; c.n_valid = c.w.rows;
+        c.state = state_; c.tab_silu = tab_silu_;
+        launch_matvec(c, nt, sm_count_, stream_, &launches_);
+        MatvecArgs e{};
+        e.w = L.w2; e.x = act_; e.x_stride = FFl; e.norm_w = nullptr; e.ntok = ntok; e.n_valid = e.w.rows; e.state = state_; e.tab_silu = tab_silu_;
+        if (!tp) { e.epi = EPI_RESID; e.out = x_; e.out_stride = E; e.resid = x_; launch_matvec(e, nt, sm_count_, stream_, &launches_); }
+        else {
+            e.epi = EPI_PLAIN; e.out = partial_; e.out_stride = E; launch_matvec(e, nt, sm_count_, stream_, &launches_);
+            tp_->all_reduce_sum(partial_, (size_t)ntok * E, stream_);
+            add_kernel<<<(ntok * E + 255) / 256, 256, 0, stream_>>>(x_, partial_, ntok * E); ++launches_;
+        }
+    }
+    if (want_logits) {
+        MatvecArgs o{};
+        o.w = output_; o.x = x_ + (size_t)(ntok - 1) * E; o.x_stride = E; o.norm_w = final_norm_; o.ntok = 1; o.epi = EPI_LOGITS; o.out = logits_; o.n_valid = d_.n_vocab;
+        o.state = state_; o.tab_silu = tab_silu_;
+        launch_matvec(o, 1, sm_count_, stream_, &launches_);
+    }
+    finalize_kernel<<<1, 32, 0, stream_>>>(state_, want_logits ? 1 : 0, nullptr); ++launches_;
+    CUDA_CHECK(cudaGetLastError());
+    // 4-byte result of the step for the greedy fast path (pinned; valid after the next stream sync)
+    if (want_logits) CUDA_CHECK(cudaMemcpyAsync(h_argmax_, &state_->argmax_id, 4, cudaMemcpyDeviceToHost, stream_));
+}
+
+void LlamaDevice::run_chunk(int n, bool want_logits, bool from_tokens) {
+    // h_state_ already holds n_past / n_tok / tokens for this chunk
+    CUDA_CHECK(cudaMemcpyAsync(state_, h_state_, offsetof(DeviceState, argmax_key), cudaMemcpyHostToDevice, stream_));
+    if (from_tokens) {
+        embed_kernel<<<n, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, state_, x_);
+        ++launches_;
+    }
+    launch_layers(nt_for(n), n, want_logits);
+    CUDA_CHECK(cudaStreamSynchronize(stream_));  // h_state_ is rewritten by the next chunk
+}
+
+bool LlamaDevice::eval_tokens(const int32_t *ids, int n, int n_past) {
+    if (n <= 0) return true;
+    if (n_past + n > d_.n_ctx) { MG4_ERR("context overflow: %d + %d > n_ctx %d", n_past, n, d_.n_ctx); return false; }
+    for (int i = 0; i < n; ++i) if (ids[i] < 0 || ids[i] >= d_.n_vocab) { MG4_ERR("token id %d out of range", ids[i]); return false; }
+    for (int i = 0; i < n; i += 8) {
+        const int c = std::min(8, n - i);
+        h_state_->n_past = n_past + i; h_state_->n_tok = c;
+        for (int j = 0; j < c; ++j) h_state_->tokens[j] = ids[i + j];
+        run_chunk(c, i + c == n, true);
+    }
+    return true;
+}
+bool LlamaDevice::eval_embd_device(const float *rows_dev, int n, int n_past) {
+    if (n <= 0) return true;
+    if (n_past + n > d_.n_ctx) { MG4_ERR("context overflow: %d + %d > n_ctx %d", n_past, n, d_.n_ctx); return false; }
+    for (int i = 0; i < n; i += 8) {
+        const int c = std::min(8, n - i);
+        h_state_->n_past = n_past + i; h_state_->n_tok = c;
+        CUDA_CHECK(cudaMemcpyAsync(x_, rows_dev + (size_t)i * d_.n_embd, (size_t)c * d_.n_embd * 4, cudaMemcpyDeviceToDevice, stream_));
+        run_chunk(c, i + c == n, false);
+    }
+    return true;
+}
+bool LlamaDevice::eval_embd(const float *rows_host, int n, int n_past) {
+    if (n <= 0) return true;
+    if (n > 512) { MG4_ERR("eval_embd: at most 512 rows per call"); return false; }
+    CUDA_CHECK(cudaMemcpyAsync(embd_in_, rows_host, (size_t)n * d_.n_embd * 4, cudaMemcpyHostToDevice, stream_));
+    return eval_embd_device(embd_in_, n, n_past);
+}
+void LlamaDevice::logits_to_host(float *dst) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, logits_, (size_t)d_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+int32_t LlamaDevice::argmax() {
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return *h_argmax_;
+}
+void LlamaDevice::sync() { CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+void LlamaDevice::hidden_to_host(float *dst, int n) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, x_, (size_t)n * d_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode step as a CUDA graph: embed(tokens[0]) -> layers -> logits/arg-max -> finalize (n_past++, tokens[0] = arg-max)
+// positions and the token come from *state_, so the same graph serves every step
+// ------------------------------------------------------------------------------------------------
+void LlamaDevice::build_graph() {
+    cudaGraph_t g = nullptr;
+    const unsigned long long before = launches_;
+    CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    embed_kernel<<<1, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, state_, x_);
+    launch_layers(1, 1, true);
+    CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
+    CUDA_CHECK(cudaGraphInstantiate(&graph_, g, 0));
+    CUDA_CHECK(cudaGraphDestroy(g));
+    graph_kernels_ = (int)(launches_ - before) + 1;
+    launches_ = before;
+}
+bool LlamaDevice::decode_step(int32_t id, int n_past) {
+    if (n_past + 1 > d_.n_ctx) { MG4_ERR("context overflow at %d", n_past); return false; }
+    if (id >= 0) {
+        h_state_->n_past = n_past; h_state_->n_tok = 1; h_state_->tokens[0] = id;
+        CUDA_CHECK(cudaMemcpyAsync(state_, h_state_, offsetof(DeviceState, argmax_key), cudaMemcpyHostToDevice, stream_));
+    }
+    CUDA_CHECK(cudaGraphLaunch(graph_, stream_));
+    launches_ += (unsigned long long)graph_kernels_;
+    return true;
+}
+float LlamaDevice::decode_chain(int steps, int n_past, int32_t *ids_out) {
+    if (n_past + steps > d_.n_ctx) { MG4_ERR("context overflow"); return -1.f; }
+    // the chain starts from the device state left by the previous eval: tokens[0] = arg-max, n_past up to date
+    int32_t *ids_dev = nullptr;
+    CUDA_CHECK(cudaMalloc((void **)&ids_dev, (size_t)steps * 4));
+    CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    for (int i = 0; i < steps; ++i) {
+        CUDA_CHECK(cudaMemcpyAsync(ids_dev + i, &state_->tokens[0], 4, cudaMemcpyDeviceToDevice, stream_));  // the id being fed
+        CUDA_CHECK(cudaGraphLaunch(graph_, stream_));
+    }
+    CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    launches_ += (unsigned long long)graph_kernels_ * steps;
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    if (ids_out) CUDA_CHECK(cudaMemcpy(ids_out, ids_dev, (size_t)steps * 4, cudaMemcpyDeviceToHost));
+    cudaFree(ids_dev);
+    return ms;
+}
+
+float LlamaDevice::time_matvec(int kind, int reps, double *bytes_per_launch) {
+    const int E = d_.n_embd, El = n_embd_local_, FFl = n_ff_local_, C = d_.n_ctx;
+    void *flush = nullptr; const size_t flush_bytes = 256u << 20;
+    if (kind == 4) CUDA_CHECK(cudaMalloc(&flush, flush_bytes));
+    h_state_->n_past = 0; h_state_->n_tok = 1; h_state_->tokens[0] = 1;
+    CUDA_CHECK(cudaMemcpyAsync(state_, h_state_, offsetof(DeviceState, argmax_key), cudaMemcpyHostToDevice, stream_));
+    double total_ms = 0.0, bytes = 0.0; long launches = 0;
+    auto one = [&](int il) {
+        Layer &L = layers_[(size_t)(kind == 4 ? 0 : il)];
+        MatvecArgs a{};
+        a.ntok = 1; a.state = state_; a.tab_silu = tab_silu_;
+        switch (kind) {
+            case 0: a.w = L.fused_qkv ? L.qkv : L.wq; a.x = x_; a.x_stride = E; a.norm_w = L.attn_norm; a.epi = EPI_QKV; a.q_out = q_;
+                    a.kcache = kcache_ + (size_t)il * C * El; a.vcache = vcache_ + (size_t)il * C * El; a.rope = rope_; a.e_local = El; a.half_dim = 64; a.part = L.fused_qkv ? -1 : 0; break;
+            case 1: a.w = L.wo; a.x = att_; a.x_stride = El; a.epi = EPI_PLAIN; a.out = partial_; a.out_stride = E; break;
+            case 2: a.w = L.w13; a.x = x_; a.x_stride = E; a.norm_w = L.ffn_norm; a.epi = EPI_SWIGLU; a.out = act_; a.out_stride = FFl; break;
+            case 3: a.w = L.w2; a.x = act_; a.x_stride = FFl; a.epi = EPI_PLAIN; a.out = partial_; a.out_stride = E; break;
+            default: a.w = output_; a.x = x_; a.x_stride = E; a.norm_w = final_norm_; a.epi = EPI_LOGITS; a.out = logits_; a.n_valid = d_.n_vocab; break;
+        }
+        if (kind != 4) a.n_valid = a.w.rows;
+        bytes = (double)a.w.bytes;
+        launch_matvec(a, 1, sm_count_, stream_, &launches_);
+    };
+    for (int il = 0; il < d_.n_layer; ++il) one(il);  // warm-up pass (instruction cache, smem attributes)
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (int r = 0; r < reps; ++r) {
+        if (kind == 4) {
+            for (int i = 0; i < 8; ++i) {
+                CUDA_CHECK(cudaMemsetAsync(flush, i, flush_bytes, stream_));  // evict the 126 MB L2
+                CUDA_CHECK(cudaEventRecord(ev0_, stream_)); one(0); CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+                CUDA_CHECK(cudaStreamSynchronize(stream_));
+                float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_)); total_ms += ms; ++launches;
+            }
+        } else {
+            CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+            for (int il = 0; il < d_.n_layer; ++il) one(il);
+            CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_)); total_ms += ms; launches += d_.n_layer;
+        }
+    }
+    if (flush) cudaFree(flush);
+    CUDA_CHECK(cudaMemsetAsync(&state_->argmax_key, 0, 8, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (bytes_per_launch) *bytes_per_launch = bytes;
+    return (float)(total_ms / (double)launches);
+}
+
+// ------------------------------------------------------------------------------------------------
+void LlamaDevice::test_matvec(int gg, int rows, int cols, const void *w_host, const float *x_host, int n, float *y_host) {
+    if (!type_supported(gg)) MG4_PANIC("test_matvec: unsupported type %d", gg);
+    int dev = 0; CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (!g_max_dyn_smem) g_max_dyn_smem = std::min<size_t>(prop.sharedMemPerBlockOptin, 220 * 1024) - 1024;
+    HostTensor t; t.gg = gg; t.n_dims = 2; t.ne[0] = cols; t.ne[1] = rows; t.data = (const uint8_t *)w_host; t.nbytes = (size_t)rows * gg_row_bytes(gg, (size_t)cols);
+    QMat m; Stager st;
+    qmat_alloc(m, gg, rows, cols);
+    repack_into(m, t, st, 0, rows, 0, cols, 1, 0, 0);
+    float *x, *y; DeviceState *stt;
+    CUDA_CHECK(cudaMalloc((void **)&x, (size_t)n * cols * 4)); CUDA_CHECK(cudaMalloc((void **)&y, (size_t)n * m.rows * 4));
+    CUDA_CHECK(cudaMalloc((void **)&stt, sizeof(DeviceState))); CUDA_CHECK(cudaMemset(stt, 0, sizeof(DeviceState)));
+    CUDA_CHECK(cudaMemcpy(x, x_host, (size_t)n * cols * 4, cudaMemcpyHostToDevice));
+    for (int i = 0; i < n; i += 8) {
+        const int c = std::min(8, n - i);
+        MatvecArgs a{};
+        a.w = m; a.x = x + (size_t)i * cols; a.x_stride = cols; a.ntok = c; a.epi = EPI_PLAIN; a.out = y + (size_t)i * m.rows; a.out_stride = m.rows; a.n_valid = rows; a.state = stt;
+        launch_matvec(a, nt_for(c), prop.multiProcessorCount, 0, nullptr);
+    }
+    CUDA_CHECK(cudaDeviceSynchronize());
+    std::vector<float> tmp((size_t)n * m.rows);
+    CUDA_CHECK(cudaMemcpy(tmp.data(), y, tmp.size() * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) memcpy(y_host + (size_t)i * rows, tmp.data() + (size_t)i * m.rows, (size_t)rows * 4);
+    cudaFree(x); cudaFree(y); cudaFree(stt); qmat_free(m);
+}
+
+}  // namespace mg4

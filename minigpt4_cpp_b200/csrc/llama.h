@@ -1,0 +1,99 @@
+// llama.h — device-resident LLaMA/Vicuna step (the path behind llama_eval / llama_eval_embd,
+// called by the reference at minigpt4.cpp:2373 and :2412).
+//
+// Data layout in HBM (owned by this engine; algorithmic bytes == file bytes):
+//   * every quantised matrix is repacked at load into SoA planes so that each warp-level access is a
+//     128-bit aligned vector (Q4_1: 16 B nibble plane + half2{d,m} plane; Q4_0: nibbles + half d;
+//     Q5_K: qs 128 B + qh 32 B + {scales[12],d,dmin} 16 B; Q6_K: ql 128 B + qh 64 B + scales 16 B + half d)
+//   * wq|wk|wv are concatenated row-wise (one launch), w1/w3 are row-interleaved (gate r, up r adjacent)
+//   * KV cache: F16 [layer][n_ctx][n_embd_local] for K and V (token-major; values as in ggml's cache)
+//   * activations between kernels are F32 vectors; each consumer re-quantises them to the weight type's
+//     vec_dot type (Q8_0/Q8_1/Q8_K/F16) in its prologue — the integer-dot formulation ggml uses
+#pragma once
+#include "formats.h"
+
+namespace mg4 {
+
+struct TPLink;  // tensor-parallel communicator (tp.h)
+
+struct QMat {          // one repacked weight matrix (or a fused group of matrices of one type)
+    int type = -1;     // GGType
+    int rows = 0, cols = 0;
+    void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
+    size_t bytes = 0;  // algorithmic bytes (rows * row_bytes)
+};
+
+struct LlamaDims { int n_vocab, n_embd, n_head, n_layer, n_ff, n_ctx, head_dim; };
+
+struct DeviceState {   // lives in device memory; kernels read positions/tokens from here so graphs are position independent
+    int n_past;
+    int n_tok;
+    int tokens[8];
+    unsigned long long argmax_key;
+    int argmax_id;
+    int pad[3];
+};
+
+class LlamaDevice {
+public:
+    LlamaDevice();
+    ~LlamaDevice();
+    bool load(const LlamaFile &f, int n_ctx, TPLink *tp);
+    const LlamaDims &dims() const { return d_; }
+    // Evaluate `n` tokens / embedding rows starting at position n_past. Afterwards logits of the last row are
+    // on device and the arg-max id is known.  Returns false if the context would overflow.
+    bool eval_tokens(const int32_t *ids, int n, int n_past);
+    bool eval_embd(const float *rows_host, int n, int n_past);
+    bool eval_embd_device(const float *rows_dev, int n, int n_past);
+    void logits_to_host(float *dst);   // n_vocab floats, synchronous
+    int32_t argmax();                  // greedy id of the current logits (already in pinned host memory after a sync)
+    void sync();
+    int sm_count() const { return sm_count_; }
+    // one decode step through the captured CUDA graph: feeds `id` (or, if id < 0, the on-device arg-max of the
+    // previous step), leaves new logits/arg-max on device.
+    bool decode_step(int32_t id, int n_past);
+    // bench leg: `steps` chained greedy steps with no host round trip; returns device ms for the loop.
+    float decode_chain(int steps, int n_past, int32_t *ids_out);
+    // measurement seam: average CUDA-event duration (ms) of one launch of the decode matvec of `kind`
+    // (0 qkv, 1 wo, 2 gate/up, 3 down, 4 output) cycling through all layers so every launch streams cold weights.
+    float time_matvec(int kind, int reps, double *bytes_per_launch);
+    // test taps
+    void hidden_to_host(float *dst, int n);  // residual stream after the last evaluated chunk (n rows)
+    size_t weight_bytes_per_token() const { return bytes_per_token_; }
+    unsigned long long kernel_launches() const { return launches_; }
+    cudaStream_t stream() const { return stream_; }
+
+    // kernel-level test hook: y[n][rows] = W x (W given as raw ggml blocks on host), through the same
+    // repack + matvec kernels the engine uses.
+    static void test_matvec(int gg, int rows, int cols, const void *w_host, const float *x_host, int n, float *y_host);
+
+private:
+    struct Layer { QMat qkv, wq, wk, wv, wo, w13, w2; bool fused_qkv; float *attn_norm, *ffn_norm; };
+    void run_chunk(int n, bool want_logits, bool from_tokens);
+    void launch_layers(int nt, int ntok, bool want_logits);
+    void build_graph();
+    LlamaDims d_{};
+    int n_head_local_ = 0, n_embd_local_ = 0, n_ff_local_ = 0;
+    TPLink *tp_ = nullptr;
+    std::vector<Layer> layers_;
+    QMat output_;
+    float *final_norm_ = nullptr;
+    void *tok_raw_ = nullptr; int tok_type_ = -1;  // tok_embeddings kept as raw ggml blocks (row gather only)
+    __half *kcache_ = nullptr, *vcache_ = nullptr;
+    float2 *rope_ = nullptr;                        // [n_ctx][head_dim/2] {cos, sin}, host-computed with libm like ggml
+    __half *tab_exp_ = nullptr, *tab_silu_ = nullptr;  // ggml's fp16 LUTs
+    float *x_ = nullptr, *q_ = nullptr, *att_ = nullptr, *act_ = nullptr, *logits_ = nullptr, *partial_ = nullptr;
+    float *embd_in_ = nullptr;
+    DeviceState *state_ = nullptr;
+    DeviceState *h_state_ = nullptr;  // pinned
+    int32_t *h_argmax_ = nullptr;     // pinned
+    cudaStream_t stream_ = nullptr;
+    cudaGraphExec_t graph_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    size_t bytes_per_token_ = 0;
+    unsigned long long launches_ = 0;
+    int graph_kernels_ = 0;
+    int sm_count_ = 148;
+};
+
+}  // namespace mg4

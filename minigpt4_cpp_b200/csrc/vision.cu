@@ -1,0 +1,374 @@
+// vision.cu — host side of the vision graph (see vision.h, vision_kernels.cuh).
+#include "vision.h"
+#include "vision_kernels.cuh"
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+
+namespace mg4 {
+using namespace vk;
+
+struct GemmPlan { CUtensorMap tmW, tmX; GemmArgs a; size_t smem; int grid; };
+
+// ---- TMA descriptor encoding through the driver entry point (no libcuda link dependency) ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr; cudaDriverEntryPointQueryResult qr;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+        if (!p || qr != cudaDriverEntryPointSuccess) MG4_PANIC("cuTensorMapEncodeTiled is not available from this driver");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+static void make_map_f16(CUtensorMap *m, const void *ptr, int rows, int cols, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) MG4_PANIC("cuTensorMapEncodeTiled failed (%d) for [%d x %d] box %d", (int)r, rows, cols, box_rows);
+}
+
+static int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
+
+static GemmPlan *make_plan(const __half *W, int M, int K, const __half *X, int T, int epi) {
+    if (M % 128 || K % 64 || T < 1 || T > 272) MG4_PANIC("gemm plan: unsupported shape M=%d K=%d T=%d", M, K, T);
+    GemmPlan *p = new GemmPlan();
+    memset(p, 0, sizeof(*p));
+    GemmArgs &a = p->a;
+    a.M_out = M; a.T = T; a.K = K; a.epi = epi;
+    a.t_pad = (T + 15) & ~15;
+    a.n1 = std::min(256, a.t_pad); a.n2 = a.t_pad - a.n1;
+    if (a.t_pad > 256) { a.box_rows = a.t_pad / 2; a.n_box = 2; } else { a.box_rows = a.t_pad; a.n_box = 1; }
+    a.stage_bytes = 16384 + a.t_pad * 128;
+    a.stages = std::min(8, (200 * 1024) / a.stage_bytes);
+    a.tmem_cols = next_pow2_cols(a.t_pad);
+    p->smem = (size_t)a.stages * a.stage_bytes + 1024 + 256;
+    p->grid = M / 128;
+    make_map_f16(&p->tmW, W, M, K, 128);
+    make_map_f16(&p->tmX, X, T, K, a.box_rows);
+    return p;
+}
+static void launch_plan(const GemmPlan *p, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) { CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024)); configured = true; }
+    gemm_f16_tcgen05<<<p->grid, 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+static inline unsigned short f2h_bits(float f) { __half h = __float2half_rn(f); unsigned short u; memcpy(&u, &h, 2); return u; }
+static inline float h2f_bits(unsigned short u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
+static __half *upload_table(int which) {  // ggml's fp16 LUTs (ggml_init): 0 = gelu (tanh form), 1 = exp
+    std::vector<unsigned short> t(65536);
+    for (int i = 0; i < 65536; ++i) {
+        const float x = h2f_bits((unsigned short)i);
+        const float y = which == 0 ? 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x))) : expf(x);
+        t[(size_t)i] = f2h_bits(y);
+    }
+    __half *d; CUDA_CHECK(cudaMalloc((void **)&d, 131072)); CUDA_CHECK(cudaMemcpy(d, t.data(), 131072, cudaMemcpyHostToDevice));
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+VisionDevice::VisionDevice() {}
+VisionDevice::~VisionDevice() {
+    if (graph_) cudaGraphExecDestroy(graph_);
+    for (GemmPlan *p : plans_) delete p;
+    for (void *p : allocs_) cudaFree(p);
+    if (tab_gelu_) cudaFree(tab_gelu_);
+    if (tab_exp_) cudaFree(tab_exp_);
+    if (h_out_) cudaFreeHost(h_out_);
+    if (h_img_) cudaFreeHost(h_img_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+void *VisionDevice::dalloc(size_t n) {
+    void *p; CUDA_CHECK(cudaMalloc(&p, n)); CUDA_CHECK(cudaMemset(p, 0, n)); allocs_.push_back(p); return p;
+}
+const __half *VisionDevice::w16(const VisionFile &f, const std::string &model, const std::string &name, int rows, int cols) {
+    const HostTensor &t = f.get(model, name);
+    if (t.gg != GG_F16) MG4_PANIC("tensor %s.%s: only F16 matrices are supported by the tensor-core path (type %d)", model.c_str(), name.c_str(), t.gg);
+    if (t.nelements() != (int64_t)rows * cols) MG4_PANIC("tensor %s.%s: expected %d x %d", model.c_str(), name.c_str(), rows, cols);
+    void *d = dalloc(t.nbytes);
+    CUDA_CHECK(cudaMemcpy(d, t.data, t.nbytes, cudaMemcpyHostToDevice));
+    weight_bytes_ += t.nbytes;
+    return (const __half *)d;
+}
+const float *VisionDevice::w32(const VisionFile &f, const std::string &model, const std::string &name, int n) {
+    const HostTensor &t = f.get(model, name);
+    if (t.gg != GG_F32 || t.nelements() != n) MG4_PANIC("tensor %s.%s: expected %d F32 values", model.c_str(), name.c_str(), n);
+    void *d = dalloc(t.nbytes);
+    CUDA_CHECK(cudaMemcpy(d, t.data, t.nbytes, cudaMemcpyHostToDevice));
+    weight_bytes_ += t.nbytes;
+    return (const float *)d;
+}
+
+Error VisionDevice::load(const VisionFile &f) {
+    long v = 0;
+    if (json_find_int(f.config_json, "Qformer", "encoder_width", &v)) d_.D = (int)v;
+    if (json_find_int(f.config_json, "Qformer", "query_length", &v)) d_.n_q = (int)v;
+    const HostTensor &pos = f.get("visual_encoder", "pos_embed");
+    d_.T = (int)pos.ne[1];
+    d_.H = d_.D / 88; d_.dh = 88;
+    if (d_.D != (int)pos.ne[0] || d_.D % 128 || d_.T != 257 || d_.n_q != 32) { MG4_ERR("unsupported vision geometry D=%d T=%d queries=%d", d_.D, d_.T, d_.n_q); return ErrLoadModelFileHeader; }
+    d_.n_blocks = 0; while (f.find("visual_encoder", "blocks." + std::to_string(d_.n_blocks) + ".norm1.weight")) ++d_.n_blocks;
+    d_.q_layers = 0; while (f.find("Qformer", "bert.encoder.layer." + std::to_string(d_.q_layers) + ".attention.self.query.weight")) ++d_.q_layers;
+    if (json_find_int(f.config_json, "Qformer", "num_hidden_layers", &v) && (int)v < d_.q_layers) d_.q_layers = (int)v;  // reference loops num_hidden_layers (:2293)
+    const HostTensor &lp = f.get("llama_proj", "weight");
+    d_.n_embd_llm = (int)lp.ne[1];
+    if (d_.n_embd_llm != 4096 && d_.n_embd_llm != 5120) { MG4_ERR("llama_proj width %d is neither 7B nor 13B", d_.n_embd_llm); return ErrLoadModelFileHeader; }
+    d_.FF = (int)f.get("visual_encoder", "blocks.0.mlp.fc1.weight").ne[1];
+    const int D = d_.D, T = d_.T, FF = d_.FF, QH = 768, NQ = 32;
+
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&ev0_)); CUDA_CHECK(cudaEventCreate(&ev1_));
+    tab_gelu_ = upload_table(0); tab_exp_ = upload_table(1);
+
+    // activations
+    img_ = (float *)dalloc((size_t)3 * 224 * 224 * 4);
+    patches_ = (__half *)dalloc((size_t)256 * 640 * 2);
+    x_ = (float *)dalloc((size_t)T * D * 4);
+    ln16_ = (__half *)dalloc((size_t)T * D * 2);
+    qkv_ = (float *)dalloc((size_t)T * 3 * D * 4);
+    ctx16_ = (__half *)dalloc((size_t)T * D * 2);
+    h16_ = (__half *)dalloc((size_t)T * FF * 2);
+    img_emb16_ = (__half *)dalloc((size_t)T * D * 2);
+    hs_ = (float *)dalloc((size_t)NQ * QH * 4); hs16_ = (__half *)dalloc((size_t)NQ * QH * 2);
+    qa_ = (float *)dalloc((size_t)NQ * QH * 4); qa16_ = (__half *)dalloc((size_t)NQ * QH * 2);
+    qc_ = (float *)dalloc((size_t)NQ * QH * 4); qc16_ = (__half *)dalloc((size_t)NQ * QH * 2);
+    qqkv_ = (float *)dalloc((size_t)NQ * 3 * QH * 4);
+    qq_ = (float *)dalloc((size_t)NQ * QH * 4);
+    qkv_cross_ = (float *)dalloc((size_t)T * 2 * QH * 4);
+    qctx16_ = (__half *)dalloc((size_t)NQ * QH * 2);
+    qh16_ = (__half *)dalloc((size_t)NQ * 3072 * 2);
+    proj_out_ = (float *)dalloc((size_t)NQ * d_.n_embd_llm * 4);
+    float *qtmp = (float *)dalloc((size_t)NQ * QH * 4);
+    CUDA_CHECK(cudaHostAlloc((void **)&h_out_, (size_t)NQ * d_.n_embd_llm * 4, cudaHostAllocDefault));
+    CUDA_CHECK(cudaHostAlloc((void **)&h_img_, (size_t)3 * 224 * 224 * 4, cudaHostAllocDefault));
+
+    auto add_plan = [&](GemmPlan *p) { plans_.push_back(p); flops_ += 2.0 * p->a.M_out * p->a.T * p->a.K; return p; };
+    const std::string VE = "visual_encoder";
+    cls_ = w32(f, VE, "cls_token", D);
+    pos_ = w32(f, VE, "pos_embed", T * D);
+    {   // patch embedding: [D][3*14*14] -> [D][640]
+        const HostTensor &pw = f.get(VE, "patch_embed.proj.weight");
+        if (pw.gg != GG_F16 || pw.nelements() != (int64_t)D * 588) MG4_PANIC("patch_embed.proj.weight must be F16 [14,14,3,%d]", D);
+        __half *raw = (__half *)dalloc(pw.nbytes); CUDA_CHECK(cudaMemcpy(raw, pw.data, pw.nbytes, cudaMemcpyHostToDevice));
+        __half *padded = (__half *)dalloc((size_t)D * 640 * 2);
+        pad_rows_f16_kernel<<<(unsigned)(((size_t)D * 640 + 255) / 256), 256>>>(raw, D, 588, padded, 640);
+        CUDA_CHECK(cudaDeviceSynchronize());
+        weight_bytes_ += pw.nbytes;
+        patch_ = add_plan(make_plan(padded, D, 640, patches_, 256, GE_PATCH));
+        patch_->a.bias = w32(f, VE, "patch_embed.proj.bias", D); patch_->a.out_f32 = x_; patch_->a.ld_out = D; patch_->a.pos = pos_;
+    }
+    blocks_.resize((size_t)d_.n_blocks);
+    for (int i = 0; i < d_.n_blocks; ++i) {
+        Block &b = blocks_[(size_t)i];
+        const std::string p = "blocks." + std::to_string(i) + ".";
+        b.n1w = w32(f, VE, p + "norm1.weight", D); b.n1b = w32(f, VE, p + "norm1.bias", D);
+        b.n2w = w32(f, VE, p + "norm2.weight", D); b.n2b = w32(f, VE, p + "norm2.bias", D);
+        {   // qkv_bias = [q_bias, 0, v_bias] (reference minigpt4.cpp:1259-1262)
+            float *qb = (float *)dalloc((size_t)3 * D * 4);
+            const HostTensor &q = f.get(VE, p + "attn.q_bias"), &vb = f.get(VE, p + "attn.v_bias");
+            CUDA_CHECK(cudaMemcpy(qb, q.data, (size_t)D * 4, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(qb + 2 * D, vb.data, (size_t)D * 4, cudaMemcpyHostToDevice));
+            b.qkv_bias = qb;
+        }
+        b.qkv = add_plan(make_plan(w16(f, VE, p + "attn.qkv.weight", 3 * D, D), 3 * D, D, ln16_, T, GE_QSCALE));
+        b.qkv->a.bias = b.qkv_bias; b.qkv->a.qscale = 1.0f / sqrtf((float)d_.dh); b.qkv->a.qscale_rows = D; b.qkv->a.out_f32 = qkv_; b.qkv->a.ld_out = 3 * D;
+        b.proj = add_plan(make_plan(w16(f, VE, p + "attn.proj.weight", D, D), D, D, ctx16_, T, GE_RESID));
+        b.proj->a.bias = w32(f, VE, p + "attn.proj.bias", D); b.proj->a.out_f32 = x_; b.proj->a.resid = x_; b.proj->a.ld_out = D;
+        b.fc1 = add_plan(make_plan(w16(f, VE, p + "mlp.fc1.weight", FF, D), FF, D, ln16_, T, GE_GELU_F16));
+        b.fc1->a.bias = w32(f, VE, p + "mlp.fc1.bias", FF); b.fc1->a.out_f16 = h16_; b.fc1->a.ld_out = FF; b.fc1->a.tab_gelu = tab_gelu_;
+        b.fc2 = add_plan(make_plan(w16(f, VE, p + "mlp.fc2.weight", D, FF), D, FF, h16_, T, GE_RESID));
+        b.fc2->a.bias = w32(f, VE, p + "mlp.fc2.bias", D); b.fc2->a.out_f32 = x_; b.fc2->a.resid = x_; b.fc2->a.ld_out = D;
+        flops_ += 4.0 * d_.H * (double)T * T * d_.dh;
+    }
+    lnv_w_ = w32(f, "ln_vision", "weight", D); lnv_b_ = w32(f, "ln_vision", "bias", D);
+    qtok_ = w32(f, "query_tokens", "weight", NQ * QH);
+    const std::string QF = "Qformer";
+    qln_w_ = w32(f, QF, "bert.embeddings.LayerNorm.weight", QH); qln_b_ = w32(f, QF, "bert.embeddings.LayerNorm.bias", QH);
+    auto cat16 = [&](std::initializer_list<const HostTensor *> ts, int cols) {  // row-concatenate F16 matrices
+        size_t total = 0; for (auto t : ts) { if (t->gg != GG_F16 || t->ne[0] != cols) MG4_PANIC("Q-Former matrix %s must be F16 with %d columns", t->name.c_str(), cols); total += t->nbytes; }
+        unsigned char *d = (unsigned char *)dalloc(total); size_t off = 0;
+        for (auto t : ts) { CUDA_CHECK(cudaMemcpy(d + off, t->data, t->nbytes, cudaMemcpyHostToDevice)); off += t->nbytes; }
+        weight_bytes_ += total;
+        return (const __half *)d;
+    };
+    auto cat32 = [&](std::initializer_list<const HostTensor *> ts) {
+        size_t total = 0; for (auto t : ts) total += t->nbytes;
+        unsigned char *d = (unsigned char *)dalloc(total); size_t off = 0;
+        for (auto t : ts) { CUDA_CHECK(cudaMemcpy(d + off, t->data, t->nbytes, cudaMemcpyHostToDevice)); off += t->nbytes; }
+        return (const float *)d;
+    };
+    qlayers_.resize((size_t)d_.q_layers);
+    for (int i = 0; i < d_.q_layers; ++i) {
+        QLayer &L = qlayers_[(size_t)i];
+        const std::string p = "bert.encoder.layer." + std::to_string(i) + ".";
+        L.sa_qkv = add_plan(make_plan(cat16({&f.get(QF, p + "attention.self.query.weight"), &f.get(QF, p + "attention.self.key.weight"), &f.get(QF, p + "attention.self.value.weight")}, QH),
+                                      3 * QH, QH, hs16_, NQ, GE_BIAS));
+        L.sa_qkv_b = cat32({&f.get(QF, p + "attention.self.query.bias"), &f.get(QF, p + "attention.self.key.bias"), &f.get(QF, p + "attention.self.value.bias")});
+        L.sa_qkv->a.bias = L.sa_qkv_b; L.sa_qkv->a.out_f32 = qqkv_; L.sa_qkv->a.ld_out = 3 * QH;
+        L.sa_o = add_plan(make_plan(w16(f, QF, p + "attention.output.dense.weight", QH, QH), QH, QH, qctx16_, NQ, GE_RESID));
+        L.sa_o->a.bias = w32(f, QF, p + "attention.output.dense.bias", QH); L.sa_o->a.out_f32 = qtmp; L.sa_o->a.resid = hs_; L.sa_o->a.ld_out = QH;
+        L.sa_ln_w = w32(f, QF, p + "attention.output.LayerNorm.weight", QH); L.sa_ln_b = w32(f, QF, p + "attention.output.LayerNorm.bias", QH);
+        flops_ += 4.0 * 12 * NQ * NQ * 64;
+        L.cross = f.find(QF, p + "crossattention.self.query.weight") != nullptr;
+        if (L.cross) {
+            L.ca_q = add_plan(make_plan(w16(f, QF, p + "crossattention.self.query.weight", QH, QH), QH, QH, qa16_, NQ, GE_BIAS));
+            L.ca_q->a.bias = w32(f, QF, p + "crossattention.self.query.bias", QH); L.ca_q->a.out_f32 = qq_; L.ca_q->a.ld_out = QH;
+            L.ca_kv = add_plan(make_plan(cat16({&f.get(QF, p + "crossattention.self.key.weight"), &f.get(QF, p + "crossattention.self.value.weight")}, D), 2 * QH, D, img_emb16_, T, GE_BIAS));
+            L.ca_kv_b = cat32({&f.get(QF, p + "crossattention.self.key.bias"), &f.get(QF, p + "crossattention.self.value.bias")});
+            L.ca_kv->a.bias = L.ca_kv_b; L.ca_kv->a.out_f32 = qkv_cross_; L.ca_kv->a.ld_out = 2 * QH;
+            L.ca_o = add_plan(make_plan(w16(f, QF, p + "crossattention.output.dense.weight", QH, QH), QH, QH, qctx16_, NQ, GE_RESID));
+            L.ca_o->a.bias = w32(f, QF, p + "crossattention.output.dense.bias", QH); L.ca_o->a.out_f32 = qtmp; L.ca_o->a.resid = qa_; L.ca_o->a.ld_out = QH;
+            L.ca_ln_w = w32(f, QF, p + "crossattention.output.LayerNorm.weight", QH); L.ca_ln_b = w32(f, QF, p + "crossattention.output.LayerNorm.bias", QH);
+            flops_ += 4.0 * 12 * NQ * T * 64;
+        }
+        const int QFF = (int)f.get(QF, p + "intermediate_query.dense.weight").ne[1];
+        if (QFF != 3072) MG4_PANIC("Q-Former intermediate size %d unsupported", QFF);
+        L.ff1 = add_plan(make_plan(w16(f, QF, p + "intermediate_query.dense.weight", QFF, QH), QFF, QH, L.cross ? qc16_ : qa16_, NQ, GE_GELU_F16));
+        L.ff1->a.bias = w32(f, QF, p + "intermediate_query.dense.bias", QFF); L.ff1->a.out_f16 = qh16_; L.ff1->a.ld_out = QFF; L.ff1->a.tab_gelu = tab_gelu_;
+        L.ff2 = add_plan(make_plan(w16(f, QF, p + "output_query.dense.weight", QH, QFF), QH, QFF, qh16_, NQ, GE_RESID));
+        L.ff2->a.bias = w32(f, QF, p + "output_query.dense.bias", QH); L.ff2->a.out_f32 = qtmp; L.ff2->a.resid = L.cross ? qc_ : qa_; L.ff2->a.ld_out = QH;
+        L.ff_ln_w = w32(f, QF, p + "output_query.LayerNorm.weight", QH); L.ff_ln_b = w32(f, QF, p + "output_query.LayerNorm.bias", QH);
+    }
+    proj_ = add_plan(make_plan(w16(f, "llama_proj", "weight", d_.n_embd_llm, QH), d_.n_embd_llm, QH, hs16_, NQ, GE_BIAS));
+    proj_->a.bias = w32(f, "llama_proj", "bias", d_.n_embd_llm); proj_->a.out_f32 = proj_out_; proj_->a.ld_out = d_.n_embd_llm;
+    qtmp_ = qtmp;
+
+    // capture the forward as one graph
+    CUDA_CHECK(cudaDeviceSynchronize());
+    cudaGraph_t g = nullptr;
+    launches_ = 0;
+    CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    record();
+    CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
+    CUDA_CHECK(cudaGraphInstantiate(&graph_, g, 0));
+    CUDA_CHECK(cudaGraphDestroy(g));
+    graph_kernels_ = (int)launches_; launches_ = 0;
+    MG4_INFO("vision graph on device: %d ViT blocks, %d Q-Former layers, %.1f GFLOP/image, %.1f MB weights, %d kernels/encode", d_.n_blocks, d_.q_layers,
+             flops_ * 1e-9, weight_bytes_ / 1048576.0, graph_kernels_);
+    return ErrNone;
+}
+
+static size_t attn_smem(int nk, int dh) { return ((size_t)nk * (dh + 1) + (size_t)nk * dh + 8 * dh + 8 * (size_t)((nk + 31) & ~31)) * 4; }
+
+void VisionDevice::record() {
+    const int D = d_.D, T = d_.T, QH = 768, NQ = 32;
+    cudaStream_t s = stream_;
+    auto ln = [&](const float *x, int rows, int n, const float *w, const float *b, __half *o16, float *o32) {
+        layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, rows, n, w, b, o16, o32, nullptr); ++launches_;
+    };
+    auto gemm = [&](GemmPlan *p) { launch_plan(p, s); ++launches_; };
+    static bool attn_cfg = false;
+    if (!attn_cfg) { CUDA_CHECK(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attn_cfg = true; }
+
+    im2col_patch_kernel<<<256, 128, 0, s>>>(img_, patches_, 640); ++launches_;
+    gemm(patch_);
+    cls_row_kernel<<<(D + 255) / 256, 256, 0, s>>>(cls_, pos_, x_, D); ++launches_;
+    const int qpc = (T + 7) / 8;  // 8 query chunks per head -> 128 CTAs
+    for (Block &b : blocks_) {
+        ln(x_, T, D, b.n1w, b.n1b, ln16_, nullptr);
+        gemm(b.qkv);
+        attention_f32_kernel<<<dim3((unsigned)d_.H, (unsigned)((T + qpc - 1) / qpc)), 256, attn_smem(T, d_.dh), s>>>(qkv_, 3 * D, qkv_ + D, qkv_ + 2 * D, 3 * D, T, T, d_.dh, 1.0f, qpc,
+                                                                                                                  ctx16_, D, tab_exp_); ++launches_;
+        gemm(b.proj);
+        ln(x_, T, D, b.n2w, b.n2b, ln16_, nullptr);
+        gemm(b.fc1);
+        gemm(b.fc2);
+    }
+    ln(x_, T, D, lnv_w_, lnv_b_, img_emb16_, nullptr);
+    ln(qtok_, NQ, QH, qln_w_, qln_b_, hs16_, hs_);
+    for (QLayer &L : qlayers_) {
+        gemm(L.sa_qkv);
+        attention_f32_kernel<<<dim3(12, 1), 256, attn_smem(NQ, 64), s>>>(qqkv_, 3 * QH, qqkv_ + QH, qqkv_ + 2 * QH, 3 * QH, NQ, NQ, 64, 8.0f, NQ, qctx16_, QH, tab_exp_); ++launches_;
+        gemm(L.sa_o);
+        ln(qtmp_, NQ, QH, L.sa_ln_w, L.sa_ln_b, qa16_, qa_);
+        if (L.cross) {
+            gemm(L.ca_q);
+            gemm(L.ca_kv);
+            attention_f32_kernel<<<dim3(12, 4), 256, attn_smem(T, 64), s>>>(qq_, QH, qkv_cross_, qkv_cross_ + QH, 2 * QH, NQ, T, 64, 8.0f, 8, qctx16_, QH, tab_exp_); ++launches_;
+            gemm(L.ca_o);
+            ln(qtmp_, NQ, QH, L.ca_ln_w, L.ca_ln_b, qc16_, qc_);
+        }
+        gemm(L.ff1);
+        gemm(L.ff2);
+        ln(qtmp_, NQ, QH, L.ff_ln_w, L.ff_ln_b, hs16_, hs_);
+    }
+    gemm(proj_);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+float VisionDevice::encode(const float *image_host, float *out_host) {
+    const size_t ib = (size_t)3 * 224 * 224 * 4, ob = (size_t)32 * d_.n_embd_llm * 4;
+    memcpy(h_img_, image_host, ib);
+    CUDA_CHECK(cudaMemcpyAsync(img_, h_img_, ib, cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    CUDA_CHECK(cudaGraphLaunch(graph_, stream_));
+    CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(h_out_, proj_out_, ob, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    launches_ += (unsigned long long)graph_kernels_;
+    memcpy(out_host, h_out_, ob);
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    return ms;
+}
+void VisionDevice::tap_residual(float *dst) { CUDA_CHECK(cudaMemcpy(dst, x_, (size_t)d_.T * d_.D * 4, cudaMemcpyDeviceToHost)); }
+void VisionDevice::tap_ln_vision(float *dst) {
+    std::vector<__half> h((size_t)d_.T * d_.D);
+    CUDA_CHECK(cudaMemcpy(h.data(), img_emb16_, h.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); ++i) dst[i] = __half2float(h[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel-level test hooks
+// ------------------------------------------------------------------------------------------------
+void VisionDevice::test_gemm(int M, int T, int K, const void *w_f16, const void *x_f16, const float *bias, int epi, float *out_f32) {
+    __half *W, *X; float *B = nullptr, *O; __half *O16 = nullptr, *tab = nullptr;
+    CUDA_CHECK(cudaMalloc((void **)&W, (size_t)M * K * 2)); CUDA_CHECK(cudaMalloc((void **)&X, (size_t)T * K * 2));
+    CUDA_CHECK(cudaMalloc((void **)&O, (size_t)(T + 1) * M * 4)); CUDA_CHECK(cudaMemset(O, 0, (size_t)(T + 1) * M * 4));
+    CUDA_CHECK(cudaMemcpy(W, w_f16, (size_t)M * K * 2, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(X, x_f16, (size_t)T * K * 2, cudaMemcpyHostToDevice));
+    if (bias) { CUDA_CHECK(cudaMalloc((void **)&B, (size_t)M * 4)); CUDA_CHECK(cudaMemcpy(B, bias, (size_t)M * 4, cudaMemcpyHostToDevice)); }
+    GemmPlan *p = make_plan(W, M, K, X, T, epi);
+    p->a.bias = B; p->a.out_f32 = O; p->a.ld_out = M;
+    if (epi == GE_GELU_F16) { CUDA_CHECK(cudaMalloc((void **)&O16, (size_t)T * M * 2)); tab = upload_table(0); p->a.out_f16 = O16; p->a.tab_gelu = tab; }
+    launch_plan(p, 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (epi == GE_GELU_F16) {
+        std::vector<__half> h((size_t)T * M); CUDA_CHECK(cudaMemcpy(h.data(), O16, h.size() * 2, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < h.size(); ++i) out_f32[i] = __half2float(h[i]);
+    } else CUDA_CHECK(cudaMemcpy(out_f32, O, (size_t)T * M * 4, cudaMemcpyDeviceToHost));
+    delete p; cudaFree(W); cudaFree(X); cudaFree(O); if (B) cudaFree(B); if (O16) cudaFree(O16); if (tab) cudaFree(tab);
+}
+void VisionDevice::test_layernorm(const float *x, int rows, int n, const float *w, const float *b, float *out) {
+    float *X, *W, *B, *O;
+    CUDA_CHECK(cudaMalloc((void **)&X, (size_t)rows * n * 4)); CUDA_CHECK(cudaMalloc((void **)&O, (size_t)rows * n * 4));
+    CUDA_CHECK(cudaMalloc((void **)&W, (size_t)n * 4)); CUDA_CHECK(cudaMalloc((void **)&B, (size_t)n * 4));
+    CUDA_CHECK(cudaMemcpy(X, x, (size_t)rows * n * 4, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(W, w, (size_t)n * 4, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(B, b, (size_t)n * 4, cudaMemcpyHostToDevice));
+    layernorm_kernel<<<(rows + 7) / 8, 256>>>(X, rows, n, W, B, nullptr, O, nullptr);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(out, O, (size_t)rows * n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(X); cudaFree(W); cudaFree(B); cudaFree(O);
+}
+void VisionDevice::test_attention(const float *q, const float *k, const float *v, int nq, int nk, int heads, int dh, float div, float *out) {
+    const int ld = heads * dh;
+    float *Q, *K, *V; __half *O, *tab = upload_table(1);
+    CUDA_CHECK(cudaMalloc((void **)&Q, (size_t)nq * ld * 4)); CUDA_CHECK(cudaMalloc((void **)&K, (size_t)nk * ld * 4)); CUDA_CHECK(cudaMalloc((void **)&V, (size_t)nk * ld * 4));
+    CUDA_CHECK(cudaMalloc((void **)&O, (size_t)nq * ld * 2));
+    CUDA_CHECK(cudaMemcpy(Q, q, (size_t)nq * ld * 4, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(K, k, (size_t)nk * ld * 4, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(V, v, (size_t)nk * ld * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    const int qpc = (nq + 3) / 4;
+    attention_f32_kernel<<<dim3((unsigned)heads, (unsigned)((nq + qpc - 1) / qpc)), 256, attn_smem(nk, dh)>>>(Q, ld, K, V, ld, nq, nk, dh, div, qpc, O, ld, tab);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    std::vector<__half> h((size_t)nq * ld); CUDA_CHECK(cudaMemcpy(h.data(), O, h.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); ++i) out[i] = __half2float(h[i]);
+    cudaFree(Q); cudaFree(K); cudaFree(V); cudaFree(O); cudaFree(tab);
+}
+
+}  // namespace mg4

@@ -1,0 +1,280 @@
+// vision_kernels.cuh — sm_100a kernels of the vision graph (EVA ViT-g/14 + Q-Former + llama_proj), the path
+// behind minigpt4_encode_image (reference minigpt4.cpp:2094-2363).
+//
+// Dense contractions run on the 5th-gen tensor cores: TMA (cp.async.bulk.tensor, 128B swizzle) stages F16 operand
+// tiles in shared memory, one elected thread issues tcgen05.mma kind::f16 with the F32 accumulator in TMEM, and four
+// epilogue warps read it back with tcgen05.ld and fuse bias / GELU / residual / positional-embedding work.
+// ggml numerics: F16 weights x activations rounded to F16, F32 accumulation — exactly kind::f16.
+//
+// "Swap-AB" tiling: UMMA M (128) runs over OUTPUT FEATURES (always a multiple of 128 here), UMMA N over TOKENS
+// (257 = one N=256 MMA + one N=16 MMA into 272 TMEM columns), so each CTA streams its weight slab exactly once.
+#pragma once
+#include "common.h"
+#include <cuda.h>
+
+namespace mg4 {
+namespace vk {
+
+enum GemmEpi : int { GE_BIAS = 0, GE_QSCALE = 1, GE_GELU_F16 = 2, GE_RESID = 3, GE_PATCH = 4 };
+
+struct GemmArgs {
+    int M_out, T, K;          // output features (multiple of 128), valid tokens, contraction (multiple of 64)
+    int t_pad, n1, n2;        // t_pad = round16(T) <= 272; MMA N split
+    int box_rows, n_box;      // TMA copies per stage for the token operand
+    int stages, stage_bytes, tmem_cols;
+    int epi;
+    const float *bias;        // [M_out] or null
+    float qscale; int qscale_rows;  // GE_QSCALE: rows < qscale_rows are multiplied by qscale after the bias
+    float *out_f32; __half *out_f16; int ld_out;
+    const float *resid;       // GE_RESID: out = resid + (acc + bias)   (may alias out_f32)
+    const float *pos;         // GE_PATCH: out[t+1] = acc + bias + pos[t+1]
+    const __half *tab_gelu;
+};
+
+// ---- raw PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1, layout type 2, SBO = 8 rows * 128 B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=F32, A=B=F16, both K-major, M=128
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                   "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[t][m] = epi( sum_k W[m][k] * X[t][k] )      W: F16 [M_out][K] (TMA map tmW), X: F16 [T][K] (TMA map tmX)
+// grid = M_out/128 CTAs of 192 threads: warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmArgs g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + (size_t)g.stages * g.stage_bytes);
+    uint64_t *empty = full + 8;
+    uint64_t *tmem_full = empty + 8;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x;
+    const int num_k = g.K / 64;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        for (int i = 0; i < g.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx = 16384u + (uint32_t)g.t_pad * 128u;
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % g.stages; const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                unsigned char *sa = smem + (size_t)s * g.stage_bytes, *sb = sa + 16384;
+                mbar_expect_tx(&full[s], tx);
+                tma_load_2d(sa, &tmW, kb * 64, m_tile * 128, &full[s]);
+                for (int b = 0; b < g.n_box; ++b) tma_load_2d(sb + (size_t)b * g.box_rows * 128, &tmX, kb * 64, b * g.box_rows, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t id1 = umma_idesc_f16(g.n1), id2 = umma_idesc_f16(g.n2 ? g.n2 : 16);
+        for (int kb = 0; kb < num_k; ++kb) {
+            const int s = kb % g.stages; const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * g.stage_bytes), sb = sa + 16384u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = umma_desc_sw128(sa + k * 32), bd = umma_desc_sw128(sb + k * 32);
+                    tc_mma_f16(tmem_base, ad, bd, id1, (uint32_t)((kb | k) != 0));
+                    if (g.n2) tc_mma_f16(tmem_base + 256u, ad, umma_desc_sw128(sb + 256u * 128u + k * 32), id2, (uint32_t)((kb | k) != 0));
+                }
+                tc_commit(&empty[s]);
+                if (kb == num_k - 1) tc_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;
+        const int m = m_tile * 128 + quarter * 32 + lane;
+        const float bias = g.bias ? g.bias[m] : 0.f;
+        const float qs = (g.epi == GE_QSCALE && m < g.qscale_rows) ? g.qscale : 1.0f;
+        for (int c0 = 0; c0 < g.t_pad; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int t = c0 + j;
+                if (t >= g.T) break;
+                float r = bias + v[j];
+                switch (g.epi) {
+                    case GE_QSCALE: r *= qs; g.out_f32[(size_t)t * g.ld_out + m] = r; break;
+                    case GE_GELU_F16: g.out_f16[(size_t)t * g.ld_out + m] = g.tab_gelu[__half_as_ushort(__float2half_rn(r))]; break;
+                    case GE_RESID: { const size_t o = (size_t)t * g.ld_out + m; g.out_f32[o] = g.resid[o] + r; } break;
+                    case GE_PATCH: { const size_t o = (size_t)(t + 1) * g.ld_out + m; g.out_f32[o] = (0.0f + r) + g.pos[o]; } break;
+                    default: g.out_f32[(size_t)t * g.ld_out + m] = r; if (g.out_f16) g.out_f16[(size_t)t * g.ld_out + m] = __float2half_rn(r); break;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (ggml_norm eps 1e-5 with double accumulation, then w*x+b): F32 rows -> F16 (GEMM operand) and/or F32
+// one warp per row
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__global__ void layernorm_kernel(const float *__restrict__ x, int rows, int n, const float *__restrict__ w, const float *__restrict__ b,
+                                 __half *__restrict__ out16, float *__restrict__ out32, const float *__restrict__ add_in /* optional: x + add_in before the norm */) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float *xr = x + (size_t)row * n;
+    const float *ar = add_in ? add_in + (size_t)row * n : nullptr;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += (double)(ar ? xr[i] + ar[i] : xr[i]);
+    s = warp_sum_d(s);
+    const float mean = (float)(s / (double)n);
+    double s2 = 0.0;
+    for (int i = lane; i < n; i += 32) { const float v = (ar ? xr[i] + ar[i] : xr[i]) - mean; s2 += (double)(v * v); }
+    s2 = warp_sum_d(s2);
+    const float variance = (float)(s2 / (double)n);
+    const float scale = 1.0f / sqrtf(variance + 1e-5f);
+    for (int i = lane; i < n; i += 32) {
+        const float v = ((ar ? xr[i] + ar[i] : xr[i]) - mean) * scale;
+        float y = w[i] * v;
+        if (b) y = y + b[i];
+        if (out16) out16[(size_t)row * n + i] = __float2half_rn(y);
+        if (out32) out32[(size_t)row * n + i] = y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F32 multi-head attention (ViT MHSA and Q-Former self/cross attention; ggml F32xF32 mul_mat + soft_max with fp16 exp LUT)
+// q: [nq][ldq] (+ head*dh), k,v: [nk][ldkv] (+ head*dh).  grid (heads, ceil(nq / q_per_cta)), block 256.
+// shared: K [nk][dh+1], V [nk][dh], per-warp q [dh] and p [nk_pad]
+// out: F16 [nq][ld_out] (operand of the following projection GEMM)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attention_f32_kernel(const float *__restrict__ q, int ldq, const float *__restrict__ k, const float *__restrict__ v, int ldkv,
+                                                            int nq, int nk, int dh, float score_div, int q_per_cta, __half *__restrict__ out, int ld_out,
+                                                            const __half *__restrict__ tab_exp) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int nk_pad = (nk + 31) & ~31;
+    float *Ks = (float *)smem; float *Vs = Ks + (size_t)nk * (dh + 1); float *Qs = Vs + (size_t)nk * dh; float *Ps = Qs + 8 * dh;
+    const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < nk * dh; i += blockDim.x) {
+        const int t = i / dh, d = i % dh;
+        Ks[(size_t)t * (dh + 1) + d] = k[(size_t)t * ldkv + h * dh + d];
+        Vs[(size_t)t * dh + d] = v[(size_t)t * ldkv + h * dh + d];
+    }
+    __syncthreads();
+    const int q0 = blockIdx.y * q_per_cta, q1 = min(nq, q0 + q_per_cta);
+    float *qw = Qs + warp * dh, *pw = Ps + (size_t)warp * nk_pad;
+    for (int tq = q0 + warp; tq < q1; tq += 8) {
+        for (int d = lane; d < dh; d += 32) qw[d] = q[(size_t)tq * ldq + h * dh + d];
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j < nk; j += 32) {
+            const float *kr = Ks + (size_t)j * (dh + 1);
+            float s = 0.f;
+            for (int d = 0; d < dh; ++d) s = fmaf(kr[d], qw[d], s);
+            s = s / score_div;
+            pw[j] = s; mx = fmaxf(mx, s);
+        }
+        mx = warp_max_f(mx);
+        double sum = 0.0;
+        for (int j = lane; j < nk; j += 32) { const float e = __half2float(tab_exp[__half_as_ushort(__float2half_rn(pw[j] - mx))]); pw[j] = e; sum += (double)e; }
+        sum = warp_sum_d(sum);
+        const float inv = (float)(1.0 / sum);
+        __syncwarp();
+        for (int d = lane; d < dh; d += 32) {
+            float acc = 0.f;
+            for (int j = 0; j < nk; ++j) acc = fmaf(Vs[(size_t)j * dh + d], pw[j] * inv, acc);
+            out[(size_t)tq * ld_out + h * dh + d] = __float2half_rn(acc);
+        }
+        __syncwarp();
+    }
+}
+
+// im2col for the 14x14/stride-14 patch embedding: image F32 CHW [3][224][224] -> F16 [256][kpad] with
+// column = ic*196 + ky*14 + kx (ggml_conv_2d_sk_p0 order), zero padded to kpad
+__global__ void im2col_patch_kernel(const float *__restrict__ img, __half *__restrict__ out, int kpad) {
+    const int p = blockIdx.x, oy = p / 16, ox = p % 16;
+    for (int c = threadIdx.x; c < kpad; c += blockDim.x) {
+        float v = 0.f;
+        if (c < 588) { const int ic = c / 196, ky = (c % 196) / 14, kx = c % 14; v = img[(size_t)ic * 224 * 224 + (size_t)(oy * 14 + ky) * 224 + ox * 14 + kx]; }
+        out[(size_t)p * kpad + c] = __float2half_rn(v);
+    }
+}
+__global__ void cls_row_kernel(const float *__restrict__ cls, const float *__restrict__ pos, float *__restrict__ x, int D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < D) x[i] = (0.0f + cls[i]) + pos[i];
+}
+__global__ void f32_to_f16_kernel(const float *__restrict__ in, __half *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2half_rn(in[i]);
+}
+__global__ void pad_rows_f16_kernel(const __half *__restrict__ src, int rows, int cols, __half *__restrict__ dst, int dst_cols) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * dst_cols) return;
+    const int r = (int)(i / dst_cols), c = (int)(i % dst_cols);
+    dst[i] = c < cols ? src[(size_t)r * cols + c] : __float2half_rn(0.f);
+}
+
+}  // namespace vk
+}  // namespace mg4

@@ -300,6 +300,7 @@ class VisionSpec:
     mlp_dim: int = 6144
     seed: int = 1
     extra_unused: bool = True     # also write tensors the reference never reads (text-branch FFN), like convert.py does
+    fast: bool = False            # bench-size files: synthesise F16 matrices from random bit patterns (10x faster than Gaussian)
 
 
 def _wstr(f, s: str | bytes):
@@ -313,6 +314,12 @@ def write_minigpt4(path: str | Path, spec: VisionSpec) -> None:
     D, FF, HID = spec.embed_dim, spec.mlp_dim, 768
 
     def w16(rows, cols, sigma=0.02):
+        if spec.fast:
+            # sign | exponent in {2^-8, 2^-7, 2^-6} (x sigma/0.02 via exponent shift is not needed: |w| ~ 0.004..0.03) | 10 random mantissa bits
+            bits = rng.integers(0, 1 << 16, size=(rows, cols), dtype=np.uint16)
+            expo = (np.uint16(7) + (bits >> np.uint16(13)) % np.uint16(3)).astype(np.uint16)  # biased exponents 7..9
+            out = (bits & np.uint16(0x83FF)) | (expo << np.uint16(10))
+            return out.view(np.float16)
         return (rng.standard_normal((rows, cols), dtype=np.float32) * sigma).astype(np.float16)
 
     def v32(n, mean=0.0, sigma=0.02):

@@ -1,0 +1,87 @@
+"""C-ABI surface: the library loads and exports every symbol include/*.h declares; GPU-free entry points behave like
+the reference (error strings minigpt4.cpp:97-119, EOS helpers :2764-2782, OpenCV stubs :2592-2594)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+ERRORS = ["None", "LoadModelFileHeader", "LoadModelFileVersion", "LoadModelMiniGPT4DataType", "LoadLanguageModel", "OpenImage", "ImageSize",
+          "MmapSupport", "FailedToAddString", "LLamaProjectionEmbeddingInvalidSize", "FailedToAddEmbedding", "EosToken", "Eos", "ImageNot224_244_3",
+          "ImageNotF32", "ImageChannelsExpectedRGB", "ImageFormatExpectedU8", "PathDoesNotExist", "DumpModelFileOpen", "OpenCVNotLinked"]
+
+
+def declared_symbols():
+    names = []
+    for h in (ROOT / "include").glob("*.h"):
+        names += re.findall(r"MINIGPT4_API[^;]*?\b(minigpt4_\w+)\s*\(", h.read_text())
+    return sorted(set(names))
+
+
+def test_header_declares_the_18_reference_symbols():
+    import minigpt4_cpp_b200.minigpt4_library as ml
+    base = [s for s in declared_symbols() if not s.startswith("minigpt4_b200_")]
+    assert sorted(base) == sorted(ml.ABI_SYMBOLS) and len(base) == 18
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_symbols():
+        assert hasattr(lib.library, name), name
+
+
+def test_extension_table_matches_header():
+    import minigpt4_cpp_b200.minigpt4_library as ml
+    ext = [s for s in declared_symbols() if s.startswith("minigpt4_b200_")]
+    assert sorted(ext) == sorted(ml.EXT_SYMBOLS)
+
+
+def test_error_strings(lib):
+    for code, name in enumerate(ERRORS):
+        assert lib.minigpt4_error_code_to_string(code) == name
+
+
+def test_eos_helpers(lib):
+    assert lib.library.minigpt4_contains_eos_token(b"##") == 11
+    assert lib.library.minigpt4_contains_eos_token(b"###") == 0
+    assert lib.library.minigpt4_is_eos(b"hello###") == 12
+    assert lib.library.minigpt4_is_eos(b"##") == 0
+    assert lib.minigpt4_is_eos("a ###") and not lib.minigpt4_is_eos("### a")
+
+
+def test_opencv_entry_points_report_not_linked(lib):
+    import minigpt4_cpp_b200 as m
+    with pytest.raises(RuntimeError, match="OpenCVNotLinked"):
+        lib.minigpt4_image_load_from_file(m.MiniGPT4Context(None), "x.png", 0)
+    with pytest.raises(RuntimeError, match="OpenCVNotLinked"):
+        lib.minigpt4_preprocess_image(m.MiniGPT4Context(None), m.MiniGPT4Image())
+
+
+def test_struct_layouts_match_header():
+    import minigpt4_cpp_b200 as m
+    assert ctypes.sizeof(m.MiniGPT4Image) == 24 and m.MiniGPT4Image.width.offset == 8 and m.MiniGPT4Image.format.offset == 20
+    assert ctypes.sizeof(m.MiniGPT4Embedding) == 16 and m.MiniGPT4Embedding.n_embeddings.offset == 8
+
+
+def test_model_load_missing_path_returns_null(lib):
+    ctx = lib.library.minigpt4_model_load(b"/nonexistent/a.bin", b"/nonexistent/b.bin", 0, 1, 128, 8, False)
+    assert ctx is None
+
+
+def test_quantize_missing_input(lib):
+    with pytest.raises(RuntimeError, match="PathDoesNotExist"):
+        lib.minigpt4_quantize_model("/nonexistent/in.bin", "/tmp/out.bin", 5)
+
+
+def test_reference_binding_binds_unmodified(lib):
+    """The reference's own ctypes file (when mounted) must bind to the new .so without edits."""
+    ref = Path("/root/reference/minigpt4/minigpt4_library.py")
+    if not ref.exists():
+        pytest.skip("reference tree not mounted on this box")
+    import importlib.util
+    from minigpt4_cpp_b200.build import OUT
+    spec = importlib.util.spec_from_file_location("ref_minigpt4_library", ref)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rlib = mod.MiniGPT4SharedLibrary(str(OUT))
+    assert rlib.minigpt4_is_eos("x###") and rlib.minigpt4_contains_eos_token("##")

@@ -1,0 +1,136 @@
+"""End-to-end parity (GPU) on seeded tiny models: vision graph, LLaMA step, chat flow through the reference ABI.
+Bars (north_star): logits within 1e-2 relative of the CPU path; greedy ids bit-identical for 32 tokens."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(lib, tiny):
+    c = lib.minigpt4_model_load(tiny["vision"], tiny["q4_1"].replace("tiny-q4_1", "tiny-q4_1"), 1, 1337, 512, 8, 0)
+    assert c.ptr
+    yield c
+    lib.minigpt4_free(c)
+
+
+@pytest.fixture(scope="module")
+def big_llm(tmp_path_factory, mg):
+    """LLaMA with n_embd 4096 (so the 4096-wide projected embedding can be fed), 2 layers."""
+    p = str(tmp_path_factory.mktemp("m4096") / "llama-4096.bin")
+    mg.write_llama_ggjt(p, mg.LlamaSpec(n_vocab=2048, n_embd=4096, n_head=32, n_layer=2, wtype="q4_1"))
+    return p
+
+
+def test_encode_image_matches_oracle(lib, ext, orc, mg, tiny, big_llm):
+    c = lib.minigpt4_model_load(tiny["vision"], big_llm, 1, 1, 256, 8, 0)
+    img = mg.synth_image()
+    got = ext.encode_array(c, img)
+    e = orc.OracleEngine(tiny["vision"], None)
+    want = e.encode_image(img)
+    assert got.shape == want.shape == (32, 4096)
+    assert rel_err(got, want) < 1e-2, rel_err(got, want)
+    # validation errors (reference minigpt4.cpp:2130-2138)
+    import minigpt4_cpp_b200 as m
+    bad = m.MiniGPT4Image(img.ctypes.data_as(ctypes.c_void_p), 224, 224, 4, m.ImageFormat.F32)
+    with pytest.raises(RuntimeError, match="ImageNot224_244_3"):
+        lib.minigpt4_encode_image(c, bad)
+    bad = m.MiniGPT4Image(img.ctypes.data_as(ctypes.c_void_p), 224, 224, 3, m.ImageFormat.U8)
+    with pytest.raises(RuntimeError, match="ImageNotF32"):
+        lib.minigpt4_encode_image(c, bad)
+    lib.minigpt4_free(c)
+
+
+@pytest.mark.parametrize("wt", ["q4_1", "q4_0", "q5_k", "q6_k", "f16", "mixed"])
+def test_llama_eval_matches_oracle(ext, orc, tiny, wt):
+    c = ext.llm_load(tiny[wt], n_ctx=256)
+    e = orc.OracleEngine(None, tiny[wt], n_ctx=256)
+    rng = np.random.default_rng(11)
+    ids = rng.integers(3, e.n_vocab, size=21).tolist()
+    ext.eval_tokens(c, ids)
+    want = e.eval_tokens(ids).copy()
+    got = ext.logits(c)
+    assert rel_err(got, want) < 1e-2 and int(np.argmax(got)) == int(np.argmax(want))
+    assert rel_err(got, want) < 2e-4, rel_err(got, want)  # integer-dot formulation: far tighter than the bar
+    # embedding rows (llama_eval_embd) continue the same context
+    rows = rng.standard_normal((5, e.n_embd)).astype(np.float32)
+    ext.eval_embd(c, rows)
+    want = e.eval_embd(rows).copy()
+    assert rel_err(ext.logits(c), want) < 2e-4
+    assert ext.n_past(c) == e.n_past == 26
+    # greedy continuation: 32 ids bit-identical
+    a, b = [], []
+    for _ in range(32):
+        tid = ext.greedy_id(c); a.append(tid); ext.eval_tokens(c, [tid])
+        b.append(e.end_chat_greedy()[0])
+    assert a == b
+    ext.base.minigpt4_free(c)
+
+
+def test_batch_invariance_and_chain(ext, tiny):
+    """size-independent properties: chunked prefill == token-by-token; device-chained greedy == host-driven greedy."""
+    ids = list(range(5, 30))
+    c1 = ext.llm_load(tiny["q4_1"], n_ctx=256); ext.eval_tokens(c1, ids); l1 = ext.logits(c1)
+    c2 = ext.llm_load(tiny["q4_1"], n_ctx=256)
+    for t in ids:
+        ext.eval_tokens(c2, [t])
+    l2 = ext.logits(c2)
+    assert np.array_equal(l1, l2)
+    chain, ms = ext.decode_chain(c1, 16)
+    host = []
+    for _ in range(16):
+        tid = ext.greedy_id(c2); host.append(tid); ext.eval_tokens(c2, [tid])
+    assert chain.tolist() == host and ms > 0
+    assert ext.n_past(c1) == ext.n_past(c2)
+    assert np.array_equal(ext.logits(c1), ext.logits(c2))
+    ext.base.minigpt4_free(c1); ext.base.minigpt4_free(c2)
+
+
+def test_context_overflow_is_an_error(ext, tiny):
+    c = ext.llm_load(tiny["q4_1"], n_ctx=16)
+    with pytest.raises(RuntimeError, match="FailedToAddString"):
+        ext.eval_tokens(c, list(range(3, 3 + 17)))
+    ext.base.minigpt4_free(c)
+
+
+def test_chat_flow_through_reference_abi(lib, ext, orc, mg, tiny, big_llm):
+    """system prompt -> begin_chat_image -> 32 x end_chat_image (greedy) == oracle engine, token for token."""
+    c = lib.minigpt4_model_load(tiny["vision"], big_llm, 1, 1337, 512, 8, 0)
+    e = orc.OracleEngine(tiny["vision"], big_llm, n_ctx=512)
+    img = mg.synth_image(7)
+    import minigpt4_cpp_b200 as m
+    mi = m.MiniGPT4Image(img.ctypes.data_as(ctypes.c_void_p), 224, 224, 3, m.ImageFormat.F32)
+    emb = lib.minigpt4_encode_image(c, mi)
+    assert emb.n_embeddings == 32 * 4096
+    lib.minigpt4_system_prompt(c)
+    lib.minigpt4_begin_chat_image(c, emb, "what is this?")
+    # the oracle consumes the embedding the GPU produced, so this isolates the language path + chat flow
+    gemb = np.ctypeslib.as_array(emb.data, shape=(32 * 4096,)).copy().reshape(32, 4096)
+    e.system_prompt(); e.begin_chat_image(gemb, "what is this?")
+    assert ext.n_past(c) == e.n_past
+    assert rel_err(ext.logits(c), e.logits) < 2e-4
+    got = [lib.minigpt4_end_chat_image(c, temp=0.0) for _ in range(32)]
+    want = [e.end_chat_greedy()[1].decode("utf-8", errors="ignore") for _ in range(32)]
+    assert got == want
+    # text-only turn + reset
+    lib.minigpt4_begin_chat(c, "and the color?"); e.begin_chat("and the color?")
+    assert lib.minigpt4_end_chat(c, temp=0.0) == e.end_chat_greedy()[1].decode("utf-8", errors="ignore")
+    lib.minigpt4_reset_chat(c)
+    assert ext.n_past(c) == 0
+    # wrong embedding size (reference minigpt4.cpp:2682-2686)
+    bad = m.MiniGPT4Embedding(emb.data, 100)
+    with pytest.raises(RuntimeError, match="LLamaProjectionEmbeddingInvalidSize"):
+        lib.minigpt4_begin_chat_image(c, bad, "x")
+    lib.minigpt4_free_embedding(emb)
+    assert not emb.data
+    # sampling path (temp > 0) returns valid tokens
+    lib.minigpt4_reset_chat(c); lib.minigpt4_begin_chat(c, "hi")
+    toks = [lib.minigpt4_end_chat(c, temp=0.8, top_k=40, top_p=0.9) for _ in range(4)]
+    assert all(isinstance(t, str) for t in toks)
+    st = ext.stats(c)
+    assert st.kernel_launches > 0 and st.n_layer == 2 and st.tp_world == 1
+    lib.minigpt4_free(c)

@@ -1,0 +1,145 @@
+"""Host logic on CPU: tokenizer, samplers, file readers (product C++) against the oracle's independent Python
+restatement; generators/codecs against gguf-py; oracle single ops against numpy."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+TEXTS = ["Human: <Img>", "</Img> ", "### Assistant:", "what is this?", "héllo wörld ✓", "a", "", "   ", "Give the following image: <Img>ImageContent</Img>.",
+         "###", "the the the llama"]
+
+
+def test_tokenizer_matches_oracle(ext, orc, tiny):
+    _, vocab, _ = orc.read_ggjt(tiny["q4_1"])
+    tk = orc.Tokenizer(vocab)
+    for t in TEXTS:
+        for bos in (True, False):
+            assert ext.host_tokenize(tiny["q4_1"], t, bos) == tk.tokenize(t, bos), t
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        s = bytes(rng.integers(32, 127, size=int(rng.integers(1, 40))).tolist())
+        assert ext.host_tokenize(tiny["q4_1"], s, True) == tk.tokenize(s, True)
+
+
+def test_tokenizer_byte_fallback_and_bos(ext, tiny):
+    ids = ext.host_tokenize(tiny["q4_1"], b"\xff\xfe", True)
+    assert ids[0] == 1 and ids[1:] == [0xff + 3, 0xfe + 3]
+    assert ext.host_tokenize(tiny["q4_1"], "", True) == []  # llama_tokenize: empty text -> nothing, not even BOS
+
+
+def test_greedy_and_sampler_chain(ext):
+    rng = np.random.default_rng(1)
+    lg = rng.standard_normal(1000).astype(np.float32)
+    lg[[17, 400]] = 9.0  # tie -> first index
+    assert ext.host_sample(lg, seed=1, temp=0.0)[0] == 17
+    # top_k = 1 is deterministic arg-max regardless of seed
+    assert ext.host_sample(lg, seed=5, n_draws=8, temp=0.8, top_k=1).tolist() == [17] * 8
+    # same seed -> same draws; tokens stay inside the top-k set
+    a = ext.host_sample(lg, seed=42, n_draws=64, temp=0.8, top_k=5, top_p=1.0)
+    b = ext.host_sample(lg, seed=42, n_draws=64, temp=0.8, top_k=5, top_p=1.0)
+    assert a.tolist() == b.tolist()
+    top5 = set(np.argsort(-lg, kind="stable")[:5].tolist())
+    assert set(a.tolist()) <= top5
+    # top_p tiny keeps only the head
+    assert set(ext.host_sample(lg, seed=3, n_draws=16, temp=1.0, top_k=0, top_p=0.01).tolist()) <= {17, 400}
+    # distribution sanity: empirical frequencies follow softmax(logits/temp) over top-k
+    lg2 = np.array([2.0, 1.0, 0.0, -1.0] + [-50.0] * 96, np.float32)
+    d = ext.host_sample(lg2, seed=7, n_draws=4000, temp=1.0, top_k=4, top_p=1.0)
+    p = np.exp(lg2[:4]) / np.exp(lg2[:4]).sum()
+    freq = np.bincount(d, minlength=4)[:4] / 4000
+    assert np.abs(freq - p).max() < 0.03
+    # mirostat variants and tail-free / typical run and return valid ids
+    for kw in (dict(mirostat=1), dict(mirostat=2), dict(tfs_z=0.5), dict(typical_p=0.5)):
+        out = ext.host_sample(lg, seed=9, n_draws=8, temp=0.8, top_k=40, **kw)
+        assert ((out >= 0) & (out < 1000)).all()
+
+
+def test_file_readers(ext, mg, tiny, tmp_path):
+    nm, nt, ne = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert ext.L.minigpt4_b200_host_inspect_container(tiny["vision"].encode(), ctypes.byref(nm), ctypes.byref(nt), ctypes.byref(ne)) == 0
+    assert nm.value == 5 and ne.value == 4096 and nt.value > 60
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"gggg" + b"\0" * 64)
+    assert ext.L.minigpt4_b200_host_inspect_container(str(bad).encode(), None, None, None) == 1  # LoadModelFileHeader
+    bad.write_bytes(b"ggml" + b"\0" * 64)
+    assert ext.L.minigpt4_b200_host_inspect_container(str(bad).encode(), None, None, None) == 2  # LoadModelFileVersion
+    nv, nE, nl, ntn = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert ext.L.minigpt4_b200_host_inspect_ggjt(tiny["q5_k"].encode(), ctypes.byref(nv), ctypes.byref(nE), ctypes.byref(nl), ctypes.byref(ntn)) == 0
+    assert (nv.value, nE.value, nl.value, ntn.value) == (1024, 512, 2, 3 + 9 * 2)
+    assert ext.L.minigpt4_b200_host_inspect_ggjt(str(bad).encode(), None, None, None, None) == 4  # LoadLanguageModel
+    # truncated file must be rejected, not read out of bounds
+    data = open(tiny["q4_1"], "rb").read()
+    (tmp_path / "trunc.bin").write_bytes(data[: len(data) // 2])
+    assert ext.L.minigpt4_b200_host_inspect_ggjt(str(tmp_path / "trunc.bin").encode(), None, None, None, None) == 4
+
+
+def test_quantize_model_roundtrip(lib, ext, orc, tiny, tmp_path):
+    """minigpt4_quantize_model (host tool): selection rule of reference minigpt4.cpp:2897-2923 and Q4 codecs."""
+    import minigpt4_cpp_b200 as m
+    out = str(tmp_path / "q41.bin")
+    lib.minigpt4_quantize_model(tiny["vision"], out, m.DataType.Q4_1)
+    _, src = orc.read_minigpt4(tiny["vision"])
+    _, dst = orc.read_minigpt4(out)
+    assert set(src) == set(dst)
+    qn = "visual_encoder.blocks.0.mlp.fc1.weight"
+    assert dst[qn].gtype == 3 and src[qn].gtype == 1
+    for keep in ("visual_encoder.patch_embed.proj.weight", "llama_proj.weight", "ln_vision.weight", "visual_encoder.blocks.0.norm1.weight",
+                 "Qformer.bert.encoder.layer.0.attention.output.LayerNorm.weight", "visual_encoder.pos_embed"):
+        assert dst[keep].gtype == src[keep].gtype and bytes(dst[keep].data) == bytes(src[keep].data)
+    rows, cols = src[qn].ne[1], src[qn].ne[0]
+    w = np.frombuffer(src[qn].data, np.float16).reshape(rows, cols).astype(np.float32)
+    wq = orc.dequant_rows(3, np.frombuffer(dst[qn].data, np.uint8), rows, cols)
+    err = np.abs(w - wq).max()
+    assert err <= (w.max(axis=None) - w.min(axis=None)) / 15 * 0.51 + 1e-3
+    import gguf
+    import gguf.quants as gq
+    ref = gq.quantize(w[:4], gguf.GGMLQuantizationType.Q4_1)
+    assert np.mean(np.frombuffer(dst[qn].data, np.uint8)[: ref.size] == ref.reshape(-1)) > 0.99
+    with pytest.raises(RuntimeError, match="LoadModelMiniGPT4DataType"):
+        lib.minigpt4_quantize_model(tiny["vision"], out, m.DataType.Q2_K)
+
+
+@pytest.mark.parametrize("name,gt", [("q4_0", 2), ("q4_1", 3), ("q5_k", 13), ("q6_k", 14)])
+def test_block_codecs_match_gguf(orc, mg, name, gt):
+    import gguf
+    import gguf.quants as gq
+    qt = getattr(gguf.GGMLQuantizationType, name.upper())
+    rng = np.random.default_rng(gt)
+    raw = mg.synth_quant(rng, gt, 6, 1024, 0.02)
+    ref = gq.dequantize(raw, qt)
+    assert np.array_equal(mg.dequant(gt, raw, 1024), ref)
+    assert np.array_equal(orc.dequant_rows(gt, raw, 6, 1024), ref)
+    # quantised mul_mat stays within the activation-quantisation error of the float product
+    x = rng.standard_normal((4, 1024)).astype(np.float32)
+    assert rel_err(orc.mul_mat(gt, raw, 6, 1024, x), x @ ref.T) < 2e-2
+
+
+def test_oracle_activation_quantisers_match_gguf(orc):
+    import gguf
+    import gguf.quants as gq
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((4, 256)).astype(np.float32)
+    q80 = np.zeros((4, 8, 34), np.uint8)
+    for r in range(4):
+        orc.lib().oracle_quantize_q8_0(x[r].ctypes.data_as(ctypes.c_void_p), q80[r].ctypes.data_as(ctypes.c_void_p), 256)
+    ref = gq.quantize(x, gguf.GGMLQuantizationType.Q8_0)
+    assert np.mean(q80.reshape(4, -1) == ref) > 0.995  # gguf rounds half away from zero; AVX2 ggml rounds to even: ties only
+
+
+def test_oracle_single_ops_against_numpy(orc):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((5, 96)).astype(np.float32)
+    w, b = rng.standard_normal(96).astype(np.float32), rng.standard_normal(96).astype(np.float32)
+    mu, var = x.mean(-1, keepdims=True), x.var(-1, keepdims=True)
+    assert rel_err(orc.layernorm(x, w, b), (x - mu) / np.sqrt(var + 1e-5) * w + b) < 1e-5
+    assert rel_err(orc.rms_norm_mul(x, w), x / np.sqrt((x * x).mean(-1, keepdims=True) + 1e-6) * w) < 1e-5
+    s = np.exp(x - x.max(-1, keepdims=True)); s /= s.sum(-1, keepdims=True)
+    assert rel_err(orc.softmax(x), s) < 2e-3  # fp16 exp LUT
+    assert rel_err(orc.silu(x), x / (1 + np.exp(-x))) < 2e-3
+    g = 0.5 * x * (1 + np.tanh(0.7978845608 * x * (1 + 0.044715 * x * x)))
+    assert rel_err(orc.gelu(x), g) < 2e-3
+    m = np.full((1, 8), -np.inf, np.float32); m[0, :3] = [0.0, 1.0, 2.0]
+    p = orc.softmax(m)
+    assert np.all(p[0, 3:] == 0) and abs(p.sum() - 1) < 1e-3  # -inf -> 0 (ggml_diag_mask_inf + soft_max)

@@ -1,0 +1,85 @@
+"""Kernel-level parity (GPU): each production CUDA kernel, driven through the C ABI, against the CPU oracle op
+(the oracle replaces the 'plain PyTorch reference' for this tier).  Integer block dots are exact; only float
+summation order differs, hence tolerances ~1e-5 relative to the output scale (stated per test)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TYPES = {"q4_0": 2, "q4_1": 3, "q5_k": 13, "q6_k": 14, "f16": 1}
+
+
+@pytest.mark.parametrize("wt", list(TYPES))
+@pytest.mark.parametrize("shape", [(64, 512), (130, 4096), (48, 11008), (33, 256)])
+@pytest.mark.parametrize("n", [1, 3, 8, 11])
+def test_matvec_matches_oracle(ext, orc, mg, wt, shape, n):
+    rows, cols = shape
+    gt = TYPES[wt]
+    rng = np.random.default_rng(rows * 7 + cols + n)
+    raw = mg.synth_quant(rng, gt, rows, cols, 0.02)
+    x = rng.standard_normal((n, cols)).astype(np.float32)
+    x[0, :32] = 0.0  # an all-zero block (amax == 0 path)
+    want = orc.mul_mat(gt, raw, rows, cols, x)
+    got = ext.op_matvec(gt, raw, rows, cols, x)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < 2e-5  # float summation order only
+
+
+def test_matvec_ragged_and_extreme(ext, orc, mg):
+    rng = np.random.default_rng(5)
+    raw = mg.synth_quant(rng, 3, 2, 32, 0.5)  # smallest legal matrix: 2 rows x one block
+    x = np.array([[1e4] * 16 + [-1e-4] * 16], np.float32)
+    assert rel_err(ext.op_matvec(3, raw, 2, 32, x), orc.mul_mat(3, raw, 2, 32, x)) < 2e-5
+    x0 = np.zeros((1, 32), np.float32)
+    assert np.all(ext.op_matvec(3, raw, 2, 32, x0) == 0)
+
+
+@pytest.mark.parametrize("M,T,K", [(128, 16, 64), (256, 32, 768), (1408, 257, 1408), (128, 257, 6144), (768, 256, 640), (384, 100, 128)])
+def test_tcgen05_gemm_matches_oracle(ext, orc, M, T, K):
+    rng = np.random.default_rng(M + T + K)
+    w = (rng.standard_normal((M, K)) * 0.05).astype(np.float16)
+    x = rng.standard_normal((T, K)).astype(np.float16)
+    bias = rng.standard_normal(M).astype(np.float32)
+    want = orc.mul_mat(1, w.view(np.uint8).reshape(M, -1), M, K, x.astype(np.float32)) + bias
+    got = ext.op_gemm_f16(w, x, bias, 0)
+    assert rel_err(got, want) < 1e-5  # F16 products are exact in F32; accumulation order only
+
+
+def test_tcgen05_gemm_gelu_epilogue(ext, orc):
+    rng = np.random.default_rng(3)
+    M, T, K = 256, 257, 512
+    w = (rng.standard_normal((M, K)) * 0.05).astype(np.float16)
+    x = rng.standard_normal((T, K)).astype(np.float16)
+    bias = rng.standard_normal(M).astype(np.float32)
+    pre = orc.mul_mat(1, w.view(np.uint8).reshape(M, -1), M, K, x.astype(np.float32)) + bias
+    want = orc.gelu(pre)
+    got = ext.op_gemm_f16(w, x, bias, 2)
+    # the fp16 LUT makes the op discontinuous at F16 rounding boundaries: allow 1 F16 ulp on <0.1 % of entries
+    diff = np.abs(got - want)
+    assert np.mean(diff > 0) < 1e-3 and diff.max() <= np.abs(want).max() * 2 ** -9
+
+
+def test_layernorm_matches_oracle(ext, orc):
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((257, 1408)) * 3 + 0.5).astype(np.float32)
+    w = rng.standard_normal(1408).astype(np.float32); b = rng.standard_normal(1408).astype(np.float32)
+    assert rel_err(ext.op_layernorm(x, w, b), orc.layernorm(x, w, b)) < 1e-6
+
+
+@pytest.mark.parametrize("nq,nk,heads,dh,div", [(257, 257, 16, 88, 1.0), (32, 32, 12, 64, 8.0), (32, 257, 12, 64, 8.0)])
+def test_attention_matches_oracle(ext, orc, nq, nk, heads, dh, div):
+    rng = np.random.default_rng(nq + nk)
+    q = rng.standard_normal((nq, heads * dh)).astype(np.float32) * (0.3 if div == 1.0 else 1.0)
+    k = rng.standard_normal((nk, heads * dh)).astype(np.float32)
+    v = rng.standard_normal((nk, heads * dh)).astype(np.float32)
+    got = ext.op_attention(q, k, v, heads, dh, div)
+    want = np.empty_like(q)
+    for h in range(heads):
+        sl = slice(h * dh, (h + 1) * dh)
+        s = (q[:, sl] @ k[:, sl].T) / div
+        p = orc.softmax(s.astype(np.float32))
+        want[:, sl] = p @ v[:, sl]
+    want = want.astype(np.float16).astype(np.float32)
+    assert rel_err(got, want) < 2e-3  # output is rounded to F16; exp LUT boundary flips allowed
