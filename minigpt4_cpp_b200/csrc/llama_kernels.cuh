@@ -5,6 +5,11 @@
 // the same formulation the reference's CPU path uses, which is also the bandwidth-optimal one.  Only float
 // summation order differs from the CPU path.
 //
+// BIT-EXACT PARITY: every float reduction here follows the canonical order the CPU oracle fixes (oracle/oracle.cpp
+// "FLOAT REDUCTION ORDER"): lane l accumulates blocks l, l+32, ... in increasing order, lanes are combined with an
+// xor-butterfly (16,8,4,2,1); FMAs only where written (fmaf); the file is compiled with -fmad=false.  Changing a loop
+// order or a reduction here REQUIRES the same change in the oracle.
+//
 // The decode matvec is HBM-bound: weights are read exactly once with 128-bit non-allocating loads from the
 // repacked planes; activations live in shared memory; reductions use warp shuffles.  Tensor cores are NOT
 // used for N=1 on purpose (north_star).
@@ -221,7 +226,7 @@ __device__ __forceinline__ void dot2_q4(const QMat &w, bool q41, int r0, const u
                     for (int r = 0; r < 2; ++r) {
                         int s = __dp4a(lo[r][0], a0.x, 0); s = __dp4a(lo[r][1], a0.y, s); s = __dp4a(lo[r][2], a0.z, s); s = __dp4a(lo[r][3], a0.w, s);
                         s = __dp4a(hi[r][0], a1.x, s); s = __dp4a(hi[r][1], a1.y, s); s = __dp4a(hi[r][2], a1.z, s); s = __dp4a(hi[r][3], a1.w, s);
-                        if (q41) { accd[r][t] = fmaf(dv[r][i] * ad, (float)s, accd[r][t]); accm[r][t] += mv[r][i] * as; }
+                        if (q41) { accd[r][t] = fmaf(dv[r][i] * ad, (float)s, accd[r][t]); accm[r][t] = fmaf(mv[r][i], as, accm[r][t]); }
                         else { accd[r][t] += ((float)s * dv[r][i]) * ad; }
                     }
                 }

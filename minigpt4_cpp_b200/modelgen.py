@@ -210,6 +210,12 @@ class LlamaSpec:
     tok_type: str | None = None
     overrides: dict = field(default_factory=dict)  # name-suffix -> type, e.g. {"attention.wv.weight": "q6_k"}
     seed: int = 2
+    # weight-scale knobs (multipliers on the 1/sqrt(fan_in) default) — see DESIGN.md "synthetic weights / conditioning"
+    qk_gain: float = 1.0      # wq, wk
+    v_gain: float = 1.0       # wv
+    o_gain: float = 0.5       # wo
+    ffn_gain: float = 1.0     # w1, w3
+    down_gain: float = 0.5    # w2
 
     @property
     def n_ff(self) -> int:
@@ -275,14 +281,14 @@ def write_llama_ggjt(path: str | Path, spec: LlamaSpec) -> dict:
         mat("output.weight", spec.n_vocab, E, sig)
         for i in range(spec.n_layer):
             p = f"layers.{i}."
-            mat(p + "attention.wq.weight", E, E, sig)
-            mat(p + "attention.wk.weight", E, E, sig)
-            mat(p + "attention.wv.weight", E, E, sig)
-            mat(p + "attention.wo.weight", E, E, sig * 0.5)
+            mat(p + "attention.wq.weight", E, E, sig * spec.qk_gain)
+            mat(p + "attention.wk.weight", E, E, sig * spec.qk_gain)
+            mat(p + "attention.wv.weight", E, E, sig * spec.v_gain)
+            mat(p + "attention.wo.weight", E, E, sig * spec.o_gain)
             vec(p + "attention_norm.weight", E)
-            mat(p + "feed_forward.w1.weight", FF, E, sig)
-            mat(p + "feed_forward.w2.weight", E, FF, 0.5 / np.sqrt(FF))
-            mat(p + "feed_forward.w3.weight", FF, E, sig)
+            mat(p + "feed_forward.w1.weight", FF, E, sig * spec.ffn_gain)
+            mat(p + "feed_forward.w2.weight", E, FF, spec.down_gain / np.sqrt(FF))
+            mat(p + "feed_forward.w3.weight", FF, E, sig * spec.ffn_gain)
             vec(p + "ffn_norm.weight", E)
     return stats
 

@@ -15,7 +15,19 @@
 // transformers' Blip2/Llama float models by tests/test_oracle_*.py (not the parity target,
 // an independent sanity pin).
 //
-// Build: g++ -O3 -mavx2 -mfma -mf16c -fopenmp -shared -fPIC (the reference's default ISA
+// FLOAT REDUCTION ORDER.  ggml leaves the order of float accumulation to the build (AVX2 sums in 8 lanes, AVX-512 in 16,
+// NEON in 4, scalar in 1, and the thread count changes nothing only because each dot is single-threaded).  Because the
+// Q8 activation quantisers are discontinuous, a 1-ulp difference in a matvec output is amplified to ~1e-2 in the logits
+// of a deep model (measured, DESIGN.md "Conditioning"), so token-level parity needs ONE fixed order.  For the language
+// path this file therefore fixes a canonical "32-lane strided + xor-butterfly" order (lane l accumulates blocks
+// l, l+32, ... in increasing order; lanes are combined with offsets 16,8,4,2,1) — i.e. what a 32-wide SIMD build of ggml
+// would do — and the CUDA kernels implement exactly the same order, which makes logits bit-identical.  All formulas,
+// rounding points, integer block dots and table lookups are ggml's.  FP contraction is disabled on both sides
+// (-ffp-contract=off here, -fmad=false in nvcc); FMAs appear only where written explicitly (fmaf), as in ggml's
+// _mm256_fmadd_ps sites.  The vision graph keeps the AVX2-shaped order (tensor-core accumulation order is not
+// reproducible anyway; it has no quantisers and agrees to ~3e-4).
+//
+// Build: g++ -O3 -mavx2 -mfma -mf16c -ffp-contract=off -fopenmp -shared -fPIC (the reference's default ISA
 // set, reference CMakeLists.txt:27-30,218-227).
 #include <immintrin.h>
 #include <math.h>
@@ -291,6 +303,125 @@ static float vec_dot_f32(int n, const float *x, const float *y) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// canonical-order reductions (language path) — mirrored 1:1 by csrc/llama_kernels.cuh
+// ---------------------------------------------------------------------------------------------
+template <typename T> static inline T butterfly(T *v, int n) {  // v'[l] = v[l] + v[l ^ o], o = n/2 .. 1 ; returns lane 0
+    T t[32];
+    for (int o = n / 2; o > 0; o >>= 1) { for (int l = 0; l < n; ++l) t[l] = v[l] + v[l ^ o]; for (int l = 0; l < n; ++l) v[l] = t[l]; }
+    return v[0];
+}
+// block_sum of llama_kernels.cuh: 256 threads, thread t owns elements t, t+256, ...; warp butterflies, then a butterfly over the 8 warp sums
+static double block_sum_256(const double *partial /*[256]*/) {
+    double w[32];
+    for (int l = 0; l < 32; ++l) w[l] = 0.0;
+    for (int wi = 0; wi < 8; ++wi) { double v[32]; for (int l = 0; l < 32; ++l) v[l] = partial[wi * 32 + l]; w[wi] = butterfly(v, 32); }
+    return butterfly(w, 32);
+}
+
+static float dot_canon_q4_1(int n, const block_q4_1 *x, const block_q8_1 *y) {
+    const int nb = n / QK;
+    float accd[32], accm[32];
+#if defined(__AVX2__)
+    __m256 A[4], M[4];
+    for (int k = 0; k < 4; ++k) { A[k] = _mm256_setzero_ps(); M[k] = _mm256_setzero_ps(); }
+    const __m256i ones = _mm256_set1_epi16(1);
+    int b0 = 0;
+    for (; b0 + 32 <= nb; b0 += 32) {
+        for (int k = 0; k < 4; ++k) {
+            __m256i s[8]; float dd[8] __attribute__((aligned(32))), mm[8] __attribute__((aligned(32))), ss[8] __attribute__((aligned(32)));
+            for (int j = 0; j < 8; ++j) {
+                const int b = b0 + 8 * k + j;
+                const __m256i bx = bytes_from_nibbles_32(x[b].qs), by = _mm256_loadu_si256((const __m256i *)y[b].qs);
+                s[j] = _mm256_madd_epi16(ones, _mm256_maddubs_epi16(bx, by));
+                dd[j] = h2f(x[b].d) * y[b].d; mm[j] = h2f(x[b].m); ss[j] = y[b].s;
+            }
+            const __m256i t0 = _mm256_hadd_epi32(s[0], s[1]), t1 = _mm256_hadd_epi32(s[2], s[3]), t2 = _mm256_hadd_epi32(s[4], s[5]), t3 = _mm256_hadd_epi32(s[6], s[7]);
+            const __m256i u0 = _mm256_hadd_epi32(t0, t1), u1 = _mm256_hadd_epi32(t2, t3);
+            const __m256i tot = _mm256_add_epi32(_mm256_permute2x128_si256(u0, u1, 0x20), _mm256_permute2x128_si256(u0, u1, 0x31));
+            A[k] = _mm256_fmadd_ps(_mm256_load_ps(dd), _mm256_cvtepi32_ps(tot), A[k]);
+            M[k] = _mm256_fmadd_ps(_mm256_load_ps(mm), _mm256_load_ps(ss), M[k]);
+        }
+    }
+    for (int k = 0; k < 4; ++k) { _mm256_storeu_ps(accd + 8 * k, A[k]); _mm256_storeu_ps(accm + 8 * k, M[k]); }
+    for (int b = b0; b < nb; ++b) {  // ragged tail: lane = b mod 32
+        const int l = b & 31;
+        accd[l] = fmaf(h2f(x[b].d) * y[b].d, (float)dot_q4_block(x[b].qs, y[b].qs, 0), accd[l]);
+        accm[l] = fmaf(h2f(x[b].m), y[b].s, accm[l]);
+    }
+#else
+    for (int l = 0; l < 32; ++l) { accd[l] = 0.f; accm[l] = 0.f; }
+    for (int b = 0; b < nb; ++b) { const int l = b & 31;
+        accd[l] = fmaf(h2f(x[b].d) * y[b].d, (float)dot_q4_block(x[b].qs, y[b].qs, 0), accd[l]); accm[l] = fmaf(h2f(x[b].m), y[b].s, accm[l]); }
+#endif
+    const float sd = butterfly(accd, 32), sm = butterfly(accm, 32);
+    return sd + sm;
+}
+static float dot_canon_q4_0(int n, const block_q4_0 *x, const block_q8_0 *y) {
+    const int nb = n / QK;
+    float acc[32];
+    for (int l = 0; l < 32; ++l) acc[l] = 0.f;
+    for (int b = 0; b < nb; ++b) { const int l = b & 31; acc[l] += ((float)dot_q4_block(x[b].qs, y[b].qs, 8) * h2f(x[b].d)) * h2f(y[b].d); }
+    return butterfly(acc, 32);
+}
+// K-quants: 8 lanes per super-block, 4 super-blocks per warp pass (lane = 8*(sb%4) + part)
+static float dot_canon_q5_K(int n, const block_q5_K *x, const block_q8_K *y) {
+    const int nsb = n / QK_K;
+    float accd[32], accm[32];
+    for (int l = 0; l < 32; ++l) { accd[l] = 0.f; accm[l] = 0.f; }
+    for (int sb = 0; sb < nsb; ++sb) {
+        const float d = h2f(x[sb].d), dmin = h2f(x[sb].dmin), d8 = y[sb].d;
+        for (int part = 0; part < 8; ++part) {
+            const int l = 8 * (sb & 3) + part, j = part >> 1, hf = part & 1;
+            uint8_t sca, mna, scb, mnb;
+            get_scale_min_k4(2 * j, x[sb].scales, &sca, &mna); get_scale_min_k4(2 * j + 1, x[sb].scales, &scb, &mnb);
+            int s0 = 0, s1 = 0;
+            for (int i = 0; i < 16; ++i) {
+                const uint8_t qb = x[sb].qs[32 * j + 16 * hf + i], hb = x[sb].qh[16 * hf + i];
+                const int lo = (qb & 0xF) + (((hb >> (2 * j)) & 1) << 4), hi = (qb >> 4) + (((hb >> (2 * j + 1)) & 1) << 4);
+                s0 += lo * y[sb].qs[64 * j + 16 * hf + i]; s1 += hi * y[sb].qs[64 * j + 32 + 16 * hf + i];
+            }
+            accd[l] += (d * d8) * (float)(sca * s0 + scb * s1);
+            accm[l] += (dmin * d8) * (float)(mna * y[sb].bsums[4 * j + hf] + mnb * y[sb].bsums[4 * j + 2 + hf]);
+        }
+    }
+    const float sd = butterfly(accd, 32), sm = butterfly(accm, 32);
+    return sd - sm;
+}
+static float dot_canon_q6_K(int n, const block_q6_K *x, const block_q8_K *y) {
+    const int nsb = n / QK_K;
+    float acc[32];
+    for (int l = 0; l < 32; ++l) acc[l] = 0.f;
+    for (int sb = 0; sb < nsb; ++sb) {
+        const float d = h2f(x[sb].d), d8 = y[sb].d;
+        for (int part = 0; part < 8; ++part) {
+            const int l = 8 * (sb & 3) + part, nn = part >> 2, u = part & 3;
+            int isum = 0;
+            for (int kq = 0; kq < 4; ++kq) {
+                int s = 0;
+                for (int i = 0; i < 8; ++i) {
+                    const int li = 8 * u + i;
+                    const uint8_t lb = x[sb].ql[64 * nn + (kq & 1) * 32 + li];
+                    const int nib = (kq >= 2) ? (lb >> 4) : (lb & 0xF);
+                    const int hb = (x[sb].qh[32 * nn + li] >> (2 * kq)) & 3;
+                    s += ((nib | (hb << 4)) - 32) * y[sb].qs[128 * nn + 32 * kq + li];
+                }
+                isum += x[sb].scales[8 * nn + 2 * kq + (u >> 1)] * s;
+            }
+            acc[l] += (d * d8) * (float)isum;
+        }
+    }
+    return butterfly(acc, 32);
+}
+// F16 weights: lane l owns 8-element vectors l, l+32, ... ; inside a vector elements are accumulated in order with FMA
+static float dot_canon_f16(int n, const f16_t *x, const f16_t *y) {
+    const int nv = n / 8;
+    float acc[32];
+    for (int l = 0; l < 32; ++l) acc[l] = 0.f;
+    for (int v = 0; v < nv; ++v) { const int l = v & 31; for (int e = 0; e < 8; ++e) acc[l] = fmaf(h2f(x[8 * v + e]), h2f(y[8 * v + e]), acc[l]); }
+    return butterfly(acc, 32);
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic tensor + mul_mat (ggml_compute_forward_mul_mat dispatch)
 // W: [rows][cols] in `type`; X: F32 [n][cols]; Y: F32 [n][rows].  Y[n][r] = dot(W[r], X[n])
 // ---------------------------------------------------------------------------------------------
@@ -305,7 +436,7 @@ static size_t row_bytes(int type, int64_t cols) {
     fprintf(stderr, "oracle: unsupported type %d\n", type); abort();
 }
 
-static void mul_mat(const Tensor &W, const float *X, int n, float *Y) {
+static void mul_mat(const Tensor &W, const float *X, int n, float *Y, bool canon = false) {
     const int64_t cols = W.ne[0], rows = W.ne[1];
     const size_t rb = row_bytes(W.type, cols);
     const uint8_t *wd = (const uint8_t *)W.data;
@@ -339,7 +470,13 @@ static void mul_mat(const Tensor &W, const float *X, int n, float *Y) {
         const uint8_t *w = wd + r * rb;
         for (int i = 0; i < n; ++i) {
             const uint8_t *q = wdata.data() + qrb * i; float v;
-            switch (W.type) {
+            if (canon) switch (W.type) {
+                case T_F16: v = dot_canon_f16((int)cols, (const f16_t *)w, (const f16_t *)q); break;
+                case T_Q4_0: v = dot_canon_q4_0((int)cols, (const block_q4_0 *)w, (const block_q8_0 *)q); break;
+                case T_Q4_1: v = dot_canon_q4_1((int)cols, (const block_q4_1 *)w, (const block_q8_1 *)q); break;
+                case T_Q5_K: v = dot_canon_q5_K((int)cols, (const block_q5_K *)w, (const block_q8_K *)q); break;
+                default: v = dot_canon_q6_K((int)cols, (const block_q6_K *)w, (const block_q8_K *)q); break;
+            } else switch (W.type) {
                 case T_F16: v = vec_dot_f16((int)cols, (const f16_t *)w, (const f16_t *)q); break;
                 case T_Q4_0: v = vec_dot_q4_0_q8_0((int)cols, (const block_q4_0 *)w, (const block_q8_0 *)q); break;
                 case T_Q4_1: v = vec_dot_q4_1_q8_1((int)cols, (const block_q4_1 *)w, (const block_q8_1 *)q); break;
@@ -413,7 +550,9 @@ static void op_layernorm(const float *x, float *y, int n, int rows, const float 
 static void op_rms_norm_mul(const float *x, float *y, int n, int rows, const float *w) {  // ggml_rms_norm eps 1e-6, then ggml_mul
     for (int r = 0; r < rows; ++r) {
         const float *xr = x + (size_t)r * n; float *yr = y + (size_t)r * n;
-        double sum = 0; for (int i = 0; i < n; ++i) sum += (double)(xr[i] * xr[i]);
+        double part[256];  // canonical order: 256 strided partial sums in double, then block_sum_256
+        for (int t = 0; t < 256; ++t) { double s = 0; for (int i = t; i < n; i += 256) s += (double)(xr[i] * xr[i]); part[t] = s; }
+        const double sum = block_sum_256(part);
         const float mean = (float)(sum / n);
         const float scale = 1.0f / sqrtf(mean + 1e-6f);
         for (int i = 0; i < n; ++i) yr[i] = (xr[i] * scale) * w[i];
@@ -434,7 +573,7 @@ static inline float op_silu(float x) { return h2f(g_tab_silu[f2h(x)]); }
 
 // exported single ops for kernel-level parity tests ------------------------------------------------
 ORACLE_API void oracle_mul_mat(int type, int64_t rows, int64_t cols, const void *w, const float *x, int n, float *y) {
-    oracle_init(); Tensor W{type, {cols, rows, 1, 1}, w}; mul_mat(W, x, n, y);
+    oracle_init(); Tensor W{type, {cols, rows, 1, 1}, w}; mul_mat(W, x, n, y, true);
 }
 ORACLE_API void oracle_dequant_row(int type, int64_t cols, const void *wrow, float *y) {
     Tensor W{type, {cols, 1, 1, 1}, wrow}; dequant_row(W, 0, y);
@@ -646,9 +785,9 @@ ORACLE_API int oracle_llama_eval(void *l, const int32_t *tokens, const float *em
     for (int il = 0; il < L->n_layer; ++il) {
         const std::string p = "layers." + std::to_string(il) + ".";
         op_rms_norm_mul(inp.data(), cur.data(), E, N, F(m, p + "attention_norm.weight"));
-        mul_mat(T(m, p + "attention.wk.weight"), cur.data(), N, k.data());
-        mul_mat(T(m, p + "attention.wq.weight"), cur.data(), N, q.data());
-        mul_mat(T(m, p + "attention.wv.weight"), cur.data(), N, vv.data());
+        mul_mat(T(m, p + "attention.wk.weight"), cur.data(), N, k.data(), true);
+        mul_mat(T(m, p + "attention.wq.weight"), cur.data(), N, q.data(), true);
+        mul_mat(T(m, p + "attention.wv.weight"), cur.data(), N, vv.data(), true);
         // ggml_rope_inplace mode 0, n_rot = head_dim: adjacent pairs, theta by repeated multiply
         for (int i = 0; i < N; ++i) for (int h = 0; h < H; ++h) {
             float theta = (float)(n_past + i);
@@ -663,31 +802,40 @@ ORACLE_API int oracle_llama_eval(void *l, const int32_t *tokens, const float *em
         const int nkv = n_past + N;
 #pragma omp parallel for schedule(dynamic) collapse(2)
         for (int h = 0; h < H; ++h) for (int i = 0; i < N; ++i) {
-            std::vector<f16_t> qh(hd), ph(nkv), vcol(nkv); std::vector<float> pr(nkv);
+            // canonical orders = csrc/llama_kernels.cuh attn_kernel: 16 lanes x 8 dims per key then a 16-lane butterfly;
+            // soft-max sum: 256 strided double partials + block_sum_256; P.V: 4 key groups (key mod 4), combined (a+b)+(c+d)
+            std::vector<f16_t> qh(hd), ph(nkv); std::vector<float> pr(nkv);
             for (int d = 0; d < hd; ++d) qh[d] = f2h(q[(size_t)i * E + h * hd + d]);
-            for (int t = 0; t < nkv; ++t) {
-                float s = vec_dot_f16(hd, &kc[(size_t)t * E + h * hd], qh.data()) * kq_scale;
-                pr[t] = (t > n_past + i) ? -INFINITY : s;  // ggml_diag_mask_inf
+            const int nvis = n_past + i + 1;  // keys visible to this row (ggml_diag_mask_inf masks the rest to -inf -> 0)
+            for (int t = 0; t < nvis; ++t) {
+                const f16_t *kr = &kc[(size_t)t * E + h * hd];
+                float lane[16];
+                for (int l = 0; l < 16; ++l) { float sacc = 0.f; for (int e = 0; e < 8; ++e) sacc = fmaf(h2f(kr[l * 8 + e]), h2f(qh[l * 8 + e]), sacc); lane[l] = sacc; }
+                pr[t] = butterfly(lane, 16) * kq_scale;
             }
-            op_softmax_row(pr.data(), nkv);
-            for (int t = 0; t < nkv; ++t) ph[t] = f2h(pr[t]);
+            float mx = -INFINITY; for (int t = 0; t < nvis; ++t) mx = fmaxf(mx, pr[t]);
+            double part[256];
+            for (int tt = 0; tt < 256; ++tt) { double sacc = 0; for (int t = tt; t < nvis; t += 256) { const float e = h2f(g_tab_exp[f2h(pr[t] - mx)]); pr[t] = e; sacc += (double)e; } part[tt] = sacc; }
+            const float inv = (float)(1.0 / block_sum_256(part));
+            for (int t = 0; t < nvis; ++t) ph[t] = f2h(pr[t] * inv);
             for (int d = 0; d < hd; ++d) {
-                for (int t = 0; t < nkv; ++t) vcol[t] = vc[(size_t)t * E + h * hd + d];
-                att[(size_t)i * E + h * hd + d] = vec_dot_f16(nkv, vcol.data(), ph.data());
+                float g4[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int t = 0; t < nvis; ++t) g4[t & 3] = fmaf(h2f(vc[(size_t)t * E + h * hd + d]), h2f(ph[t]), g4[t & 3]);
+                att[(size_t)i * E + h * hd + d] = (g4[0] + g4[1]) + (g4[2] + g4[3]);
             }
         }
-        mul_mat(T(m, p + "attention.wo.weight"), att.data(), N, cur.data());
+        mul_mat(T(m, p + "attention.wo.weight"), att.data(), N, cur.data(), true);
         for (size_t i = 0; i < (size_t)N * E; ++i) inp[i] = cur[i] + inp[i];  // inpFF
         op_rms_norm_mul(inp.data(), cur.data(), E, N, F(m, p + "ffn_norm.weight"));
-        mul_mat(T(m, p + "feed_forward.w3.weight"), cur.data(), N, ff3.data());
-        mul_mat(T(m, p + "feed_forward.w1.weight"), cur.data(), N, ff1.data());
+        mul_mat(T(m, p + "feed_forward.w3.weight"), cur.data(), N, ff3.data(), true);
+        mul_mat(T(m, p + "feed_forward.w1.weight"), cur.data(), N, ff1.data(), true);
         for (size_t i = 0; i < (size_t)N * FF; ++i) ff1[i] = op_silu(ff1[i]) * ff3[i];
-        mul_mat(T(m, p + "feed_forward.w2.weight"), ff1.data(), N, cur.data());
+        mul_mat(T(m, p + "feed_forward.w2.weight"), ff1.data(), N, cur.data(), true);
         for (size_t i = 0; i < (size_t)N * E; ++i) inp[i] = cur[i] + inp[i];
         if (hidden_tap && tap_layer == il) memcpy(hidden_tap, inp.data(), sizeof(float) * N * E);
     }
     op_rms_norm_mul(inp.data(), cur.data(), E, N, F(m, "norm.weight"));
-    mul_mat(T(m, "output.weight"), &cur[(size_t)(N - 1) * E], 1, L->logits.data());
+    mul_mat(T(m, "output.weight"), &cur[(size_t)(N - 1) * E], 1, L->logits.data(), true);
     if (logits_out) memcpy(logits_out, L->logits.data(), sizeof(float) * L->n_vocab);
     return 0;
 }
