@@ -331,7 +331,7 @@ def main():
         lib.minigpt4_reset_chat(ctx)
         emb = ext.encode_array(ctx, img)
         ext.eval_embd(ctx, emb); e.eval_embd(emb)
-        lg, lc = ext.logits(ctx), e.logits
+        lg, lc = ext.logits(ctx), e.logits.copy()  # copy: the oracle reuses its logits buffer on every eval
         g_ids, c_ids = [], []
         for _ in range(args.cpu_tokens):
             t = ext.greedy_id(ctx); g_ids.append(t); ext.eval_tokens(ctx, [t]); c_ids.append(e.end_chat_greedy()[0])

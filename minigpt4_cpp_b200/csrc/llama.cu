@@ -1,6 +1,8 @@
 // llama.cu — host side of the device-resident LLaMA step (see llama.h, llama_kernels.cuh).
 #include "llama_kernels.cuh"
+#include "llama_mega.cuh"
 #include "tp.h"
+#include <stdlib.h>
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -61,8 +63,8 @@ static void qmat_alloc(QMat &m, int type, int rows, int cols) {
     const size_t R = (size_t)m.rows;
     auto zalloc = [](void **p, size_t n) { CUDA_CHECK(cudaMalloc(p, n)); CUDA_CHECK(cudaMemset(*p, 0, n)); };
     switch (type) {
-        case GG_Q4_0: zalloc(&m.p0, R * cols / 32 * 16); zalloc(&m.p1, R * cols / 32 * 2); break;
-        case GG_Q4_1: zalloc(&m.p0, R * cols / 32 * 16); zalloc(&m.p1, R * cols / 32 * 4); break;
+        case GG_Q4_0: m.row_bytes = (cols / 32 * 18 + 15) & ~15; zalloc(&m.p0, R * m.row_bytes + 256); break;
+        case GG_Q4_1: m.row_bytes = (cols / 32 * 20 + 15) & ~15; zalloc(&m.p0, R * m.row_bytes + 256); break;
         case GG_Q5_K: zalloc(&m.p0, R * cols / 256 * 128); zalloc(&m.p1, R * cols / 256 * 32); zalloc(&m.p2, R * cols / 256 * 16); break;
         case GG_Q6_K: zalloc(&m.p0, R * cols / 256 * 128); zalloc(&m.p1, R * cols / 256 * 64); zalloc(&m.p2, R * cols / 256 * 16); zalloc(&m.p3, R * cols / 256 * 2); break;
         case GG_F16: zalloc(&m.p0, R * cols * 2); break;
@@ -94,8 +96,8 @@ static void repack_into(QMat &dst, const HostTensor &src, Stager &st, int row0, 
     const size_t n = (size_t)nrows * nblk;
     const int th = 256; const unsigned gr = (unsigned)((n + th - 1) / th);
     switch (src.gg) {
-        case GG_Q4_0: repack_q4<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, false, (uint4 *)dst.p0, dst.p1, dst_nb, row_mul, row_off, dblk0); break;
-        case GG_Q4_1: repack_q4<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, true, (uint4 *)dst.p0, dst.p1, dst_nb, row_mul, row_off, dblk0); break;
+        case GG_Q4_0: repack_q4<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, false, (unsigned char *)dst.p0, dst_nb, dst.row_bytes, row_mul, row_off, dblk0); break;
+        case GG_Q4_1: repack_q4<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, true, (unsigned char *)dst.p0, dst_nb, dst.row_bytes, row_mul, row_off, dblk0); break;
         case GG_Q5_K: repack_q5k<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, (unsigned char *)dst.p0, (unsigned char *)dst.p1, (unsigned char *)dst.p2, dst_nb, row_mul, row_off, dblk0); break;
         case GG_Q6_K: repack_q6k<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, (unsigned char *)dst.p0, (unsigned char *)dst.p1, (unsigned char *)dst.p2, (unsigned short *)dst.p3, dst_nb, row_mul, row_off, dblk0); break;
         case GG_F16: repack_f16<<<gr, th>>>((const unsigned short *)raw, src_cols, col0, ncols, nrows, (unsigned short *)dst.p0, dst.cols, row_mul, row_off, dst_col0); break;
@@ -119,6 +121,9 @@ LlamaDevice::~LlamaDevice() {
     qmat_free(output_);
     for (void *p : {(void *)final_norm_, tok_raw_, (void *)kcache_, (void *)vcache_, (void *)rope_, (void *)tab_exp_, (void *)tab_silu_, (void *)x_, (void *)q_, (void *)att_,
                     (void *)act_, (void *)logits_, (void *)partial_, (void *)embd_in_, (void *)state_}) if (p) cudaFree(p);
+    if (mega_ops_) cudaFree(mega_ops_);
+    if (mega_barrier_) cudaFree(mega_barrier_);
+    delete (mk::MegaParams *)mega_params_;
     if (h_state_) cudaFreeHost(h_state_);
     if (h_argmax_) cudaFreeHost(h_argmax_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -346,16 +351,104 @@ void LlamaDevice::hidden_to_host(float *dst, int n) {
 // decode step as a CUDA graph: embed(tokens[0]) -> layers -> logits/arg-max -> finalize (n_past++, tokens[0] = arg-max)
 // positions and the token come from *state_, so the same graph serves every step
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// persistent megakernel program (llama_mega.cuh)
+// ------------------------------------------------------------------------------------------------
+bool LlamaDevice::build_mega() {
+    using namespace mk;
+    if (getenv("MINIGPT4_B200_NO_MEGAKERNEL")) return false;
+    if (tp_ && tp_->world > 1) return false;
+    const int wt = output_.type;
+    if (wt != GG_Q4_0 && wt != GG_Q4_1) return false;
+    for (auto &L : layers_) if (!L.fused_qkv || L.qkv.type != wt || L.wo.type != wt || L.w13.type != wt || L.w2.type != wt) return false;
+    if (d_.n_embd % 256 || d_.n_ff % 256) return false;
+    int coop = 0, dev = 0; CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) return false;
+    const int E = d_.n_embd, FF = d_.n_ff;
+    const int act = act_of(wt);
+    size_t act_b = std::max(act_bytes(act, FF), act_bytes(act, E));
+    act_b = std::max(act_b, (size_t)d_.n_ctx * 6);
+    act_b = (act_b + 127) & ~(size_t)127;
+    const int rb_e = layers_[0].qkv.row_bytes, rb_ff = layers_[0].w2.row_bytes;
+    int slot = std::max(2 * rb_e, 2 * rb_ff);
+    slot = std::max(slot, 4 * rb_e);
+    slot = (slot + 127) & ~127;
+    cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    const size_t budget = prop.sharedMemPerBlockOptin - 2048;  // static shared + slack
+    const int n_slots = (int)std::min<size_t>(24, (budget - act_b - 512) / (size_t)slot);
+    if (n_slots < 4) return false;
+    auto su_rows_for = [&](int row_bytes) { int r = (slot / row_bytes) & ~1; return std::max(2, std::min(r, 4)); };
+    std::vector<MegaOp> ops;
+    auto add = [&](int kind, int layer, const QMat *m, const float *norm) {
+        MegaOp o{}; o.kind = kind; o.layer = layer; o.norm_w = norm;
+        if (m) { o.rows = m->rows; o.cols = m->cols; o.row_bytes = m->row_bytes; o.su_rows = su_rows_for(m->row_bytes); o.n_su = (m->rows + o.su_rows - 1) / o.su_rows; o.w = (const unsigned char *)m->p0; }
+        ops.push_back(o);
+    };
+    add(OP_EMBED, 0, nullptr, nullptr);
+    for (int il = 0; il < d_.n_layer; ++il) {
+        Layer &L = layers_[(size_t)il];
+        add(OP_QKV, il, &L.qkv, L.attn_norm);
+        add(OP_ATTN, il, nullptr, nullptr);
+        add(OP_WO, il, &L.wo, nullptr);
+        add(OP_GATEUP, il, &L.w13, L.ffn_norm);
+        add(OP_DOWN, il, &L.w2, nullptr);
+    }
+    add(OP_OUTPUT, 0, &output_, final_norm_);
+    add(OP_FINAL, 0, nullptr, nullptr);
+    CUDA_CHECK(cudaMalloc(&mega_ops_, ops.size() * sizeof(MegaOp)));
+    CUDA_CHECK(cudaMemcpy(mega_ops_, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc((void **)&mega_barrier_, 64)); CUDA_CHECK(cudaMemset(mega_barrier_, 0, 64));
+    MegaParams *P = new MegaParams();
+    P->ops = (const MegaOp *)mega_ops_; P->n_ops = (int)ops.size();
+    P->n_slots = n_slots; P->slot_bytes = slot; P->act_bytes = (int)act_b;
+    P->E = E; P->FF = FF; P->n_head = d_.n_head; P->n_ctx = d_.n_ctx; P->n_vocab = d_.n_vocab;
+    P->kq_scale = 1.0f / sqrtf((float)d_.n_embd / (float)d_.n_head);
+    P->x = x_; P->q = q_; P->att = att_; P->act = act_; P->logits = logits_; P->kcache = kcache_; P->vcache = vcache_;
+    P->rope = rope_; P->tab_exp = tab_exp_; P->tab_silu = tab_silu_;
+    P->tok = (const unsigned char *)tok_raw_; P->tok_type = tok_type_; P->tok_row_bytes = gg_row_bytes(tok_type_, (size_t)E);
+    P->state = state_; P->barrier = mega_barrier_;
+    mega_params_ = P;
+    mega_smem_ = (size_t)n_slots * slot + act_b + (size_t)n_slots * 16 + 64;
+    mega_type_ = wt;
+    if (wt == GG_Q4_1) CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<GG_Q4_1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_));
+    else CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<GG_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_));
+    int occ = 0;
+    if (wt == GG_Q4_1) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_megakernel<GG_Q4_1>, kMegaThreads, mega_smem_));
+    else CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_megakernel<GG_Q4_0>, kMegaThreads, mega_smem_));
+    if (occ < 1) { MG4_ERR("megakernel does not fit on an SM (smem %zu)", mega_smem_); return false; }
+    MG4_INFO("decode megakernel: %d ops/token, ring %d x %d B, act %zu B, %zu B shared per CTA, grid %d", (int)ops.size(), n_slots, slot, act_b, mega_smem_, sm_count_);
+    return true;
+}
+void LlamaDevice::launch_mega() {
+    using namespace mk;
+    CUDA_CHECK(cudaMemsetAsync(mega_barrier_, 0, 4, stream_));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)sm_count_); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = mega_smem_; cfg.stream = stream_;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const MegaParams &P = *(const MegaParams *)mega_params_;
+    if (mega_type_ == GG_Q4_1) CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_megakernel<GG_Q4_1>, P));
+    else CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_megakernel<GG_Q4_0>, P));
+    ++launches_;
+    CUDA_CHECK(cudaMemcpyAsync(h_argmax_, &state_->argmax_id, 4, cudaMemcpyDeviceToHost, stream_));
+}
+
 void LlamaDevice::build_graph() {
     cudaGraph_t g = nullptr;
     const unsigned long long before = launches_;
+    mega_ = build_mega();
     CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
-    embed_kernel<<<1, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, state_, x_);
-    launch_layers(1, 1, true);
+    if (mega_) launch_mega();
+    else {
+        embed_kernel<<<1, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, state_, x_);
+        launch_layers(1, 1, true);
+    }
     CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
     CUDA_CHECK(cudaGraphInstantiate(&graph_, g, 0));
     CUDA_CHECK(cudaGraphDestroy(g));
-    graph_kernels_ = (int)(launches_ - before) + 1;
+    graph_kernels_ = (int)(launches_ - before) + (mega_ ? 0 : 1);
     launches_ = before;
 }
 bool LlamaDevice::decode_step(int32_t id, int n_past) {

@@ -3,7 +3,7 @@
 //
 // Data layout in HBM (owned by this engine; algorithmic bytes == file bytes):
 //   * every quantised matrix is repacked at load into SoA planes so that each warp-level access is a
-//     128-bit aligned vector (Q4_1: 16 B nibble plane + half2{d,m} plane; Q4_0: nibbles + half d;
+//     128-bit aligned vector (Q4_1/Q4_0: row-packed [nb x 16 B nibbles][nb x half2{d,m} | half d] so a run of rows is ONE contiguous range for cp.async.bulk;
 //     Q5_K: qs 128 B + qh 32 B + {scales[12],d,dmin} 16 B; Q6_K: ql 128 B + qh 64 B + scales 16 B + half d)
 //   * wq|wk|wv are concatenated row-wise (one launch), w1/w3 are row-interleaved (gate r, up r adjacent)
 //   * KV cache: F16 [layer][n_ctx][n_embd_local] for K and V (token-major; values as in ggml's cache)
@@ -21,6 +21,7 @@ struct QMat {          // one repacked weight matrix (or a fused group of matric
     int rows = 0, cols = 0;
     void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
     size_t bytes = 0;  // algorithmic bytes (rows * row_bytes)
+    int row_bytes = 0; // Q4_0/Q4_1 row-packed layout: p0 holds rows of [nb x 16 B nibbles][nb x scales], row_bytes each
 };
 
 struct LlamaDims { int n_vocab, n_embd, n_head, n_layer, n_ff, n_ctx, head_dim; };
@@ -49,6 +50,7 @@ public:
     int32_t argmax();                  // greedy id of the current logits (already in pinned host memory after a sync)
     void sync();
     int sm_count() const { return sm_count_; }
+    bool uses_megakernel() const { return mega_; }
     // one decode step through the captured CUDA graph: feeds `id` (or, if id < 0, the on-device arg-max of the
     // previous step), leaves new logits/arg-max on device.
     bool decode_step(int32_t id, int n_past);
@@ -72,6 +74,8 @@ private:
     void run_chunk(int n, bool want_logits, bool from_tokens);
     void launch_layers(int nt, int ntok, bool want_logits);
     void build_graph();
+    bool build_mega();               // persistent one-launch-per-token decode (homogeneous Q4_0/Q4_1, single GPU)
+    void launch_mega();
     LlamaDims d_{};
     int n_head_local_ = 0, n_embd_local_ = 0, n_ff_local_ = 0;
     TPLink *tp_ = nullptr;
@@ -93,6 +97,7 @@ private:
     size_t bytes_per_token_ = 0;
     unsigned long long launches_ = 0;
     int graph_kernels_ = 0;
+    bool mega_ = false; void *mega_ops_ = nullptr; unsigned *mega_barrier_ = nullptr; void *mega_params_ = nullptr; size_t mega_smem_ = 0; int mega_type_ = -1;
     int sm_count_ = 148;
 };
 

@@ -84,24 +84,33 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ double block_sum(double v, double *red) {  // red: >= 33 doubles of shared memory
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+// Two execution contexts share these helpers: stand-alone kernels (all 256 threads of the CTA, __syncthreads, plain loads)
+// and the persistent decode megakernel (MEGA: 256 consumer threads + a producer warp, named barrier 1, and L2-only
+// loads because inputs were written by OTHER CTAs earlier in the same launch and L1 may hold stale lines).
+template <bool MEGA> __device__ __forceinline__ void cta_sync() {
+    if (MEGA) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads();
+}
+template <bool MEGA> __device__ __forceinline__ float ld_act(const float *p) { return MEGA ? __ldcg(p) : *p; }
+template <bool MEGA>
+__device__ __forceinline__ double block_sum(double v, double *red) {  // red: >= 33 doubles of shared memory; 256 threads
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = warp_sum(v);
-    __syncthreads();
+    cta_sync<MEGA>();
     if (lane == 0) red[warp] = v;
-    __syncthreads();
-    if (warp == 0) { double t = lane < nw ? red[lane] : 0.0; t = warp_sum(t); if (lane == 0) red[32] = t; }
-    __syncthreads();
+    cta_sync<MEGA>();
+    if (warp == 0) { double t = lane < 8 ? red[lane] : 0.0; t = warp_sum(t); if (lane == 0) red[32] = t; }
+    cta_sync<MEGA>();
     return red[32];
 }
+template <bool MEGA>
 __device__ __forceinline__ float block_max(float v, float *red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = warp_max(v);
-    __syncthreads();
+    cta_sync<MEGA>();
     if (lane == 0) red[warp] = v;
-    __syncthreads();
-    if (warp == 0) { float t = lane < nw ? red[lane] : -INFINITY; t = warp_max(t); if (lane == 0) red[32] = t; }
-    __syncthreads();
+    cta_sync<MEGA>();
+    if (warp == 0) { float t = lane < 8 ? red[lane] : -INFINITY; t = warp_max(t); if (lane == 0) red[32] = t; }
+    cta_sync<MEGA>();
     return red[32];
 }
 __device__ __forceinline__ float lut_f16(const __half *tab, float x) {  // ggml fp16 LUT op: in rounded to F16, out F16
@@ -112,27 +121,27 @@ __device__ __forceinline__ float lut_f16(const __half *tab, float x) {  // ggml 
 // activation staging: F32 row (optionally RMS-normalised, eps 1e-6, double accumulation like ggml_rms_norm)
 // -> shared memory in the weight type's vec_dot format (quantize_row_q8_0 / q8_1 AVX2 semantics, q8_K)
 // ---------------------------------------------------------------------------------------------
-template <int ACT>
+template <int ACT, bool MEGA>
 __device__ void stage_act(const float *__restrict__ x, const float *__restrict__ nw, int cols, unsigned char *sm, double *red) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5; constexpr int nwarps = 8, nthreads = 256;
     float scale = 1.0f;
     if (nw) {
         double ss = 0.0;
-        for (int i = tid; i < cols; i += blockDim.x) { const float v = x[i]; ss += (double)(v * v); }
-        const double tot = block_sum(ss, red);
+        for (int i = tid; i < cols; i += nthreads) { const float v = ld_act<MEGA>(x + i); ss += (double)(v * v); }
+        const double tot = block_sum<MEGA>(ss, red);
         const float mean = (float)(tot / (double)cols);
         scale = 1.0f / sqrtf(mean + 1e-6f);
     }
     if (ACT == ACT_F16) {
         __half *h = (__half *)sm;
-        for (int i = tid; i < cols; i += blockDim.x) { float v = x[i]; if (nw) v = (v * scale) * nw[i]; h[i] = __float2half_rn(v); }
+        for (int i = tid; i < cols; i += nthreads) { float v = ld_act<MEGA>(x + i); if (nw) v = (v * scale) * nw[i]; h[i] = __float2half_rn(v); }
     } else if (ACT == ACT_Q8_K) {
         int8_t *qs = (int8_t *)sm; float *d = (float *)(sm + cols); int16_t *bs = (int16_t *)(sm + cols + cols / 256 * 4);
         for (int sb = warp; sb < cols / 256; sb += nwarps) {
             float v[8]; float amax = 0.f, mx = 0.f; int mi = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int i = sb * 256 + lane * 8 + j; float t = x[i]; if (nw) t = (t * scale) * nw[i]; v[j] = t;
+                const int i = sb * 256 + lane * 8 + j; float t = ld_act<MEGA>(x + i); if (nw) t = (t * scale) * nw[i]; v[j] = t;
                 const float a = fabsf(t); if (a > amax) { amax = a; mx = t; mi = lane * 8 + j; }
             }
 #pragma unroll
@@ -157,7 +166,7 @@ __device__ void stage_act(const float *__restrict__ x, const float *__restrict__
         int8_t *qs = (int8_t *)sm; float *d = (float *)(sm + cols); float *s = d + cols / 32;
         for (int b = warp; b < cols / 32; b += nwarps) {
             const int i = b * 32 + lane;
-            float v = x[i]; if (nw) v = (v * scale) * nw[i];
+            float v = ld_act<MEGA>(x + i); if (nw) v = (v * scale) * nw[i];
             const float amax = warp_max(fabsf(v));
             const float dd = amax / 127.f;
             const float id = amax != 0.0f ? 127.f / amax : 0.0f;
@@ -176,10 +185,12 @@ __device__ void stage_act(const float *__restrict__ x, const float *__restrict__
 // per-codec partial dot products of TWO adjacent rows against NT staged activation vectors.
 // Each returns lane-partial sums; the caller finishes with warp_sum.
 // ---------------------------------------------------------------------------------------------
-template <int NT>
-__device__ __forceinline__ void dot2_q4(const QMat &w, bool q41, int r0, const unsigned char *act, size_t astride, int lane, float (&res)[2][NT]) {
-    const int nb = w.cols / 32;
-    const uint4 *qs0 = (const uint4 *)w.p0 + (size_t)r0 * nb, *qs1 = qs0 + nb;
+// Q4_0 / Q4_1, row-packed layout: row = [nb x 16 B nibbles][nb x {half d | half2 d,m}]; row0/row1 may point to global
+// memory (stand-alone kernels) or to a shared-memory ring slot filled by cp.async.bulk (megakernel).
+template <int NT, bool SMEM>
+__device__ __forceinline__ void dot2_q4(const unsigned char *row0, const unsigned char *row1, int nb, int cols, bool q41, const unsigned char *act, size_t astride, int lane, float (&res)[2][NT]) {
+    const uint4 *qs0 = (const uint4 *)row0, *qs1 = (const uint4 *)row1;
+    const unsigned char *sc0 = row0 + (size_t)nb * 16, *sc1 = row1 + (size_t)nb * 16;
     float accd[2][NT], accm[2][NT];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
@@ -191,13 +202,13 @@ __device__ __forceinline__ void dot2_q4(const QMat &w, bool q41, int r0, const u
         for (int i = 0; i < 4; ++i) {
             const int b = b0 + i * 32 + lane;
             if (b < nb) {
-                q[0][i] = ldg_stream(qs0 + b); q[1][i] = ldg_stream(qs1 + b);
+                if (SMEM) { q[0][i] = qs0[b]; q[1][i] = qs1[b]; } else { q[0][i] = ldg_stream(qs0 + b); q[1][i] = ldg_stream(qs1 + b); }
                 if (q41) {
-                    const unsigned a0 = ldg_stream((const unsigned *)w.p1 + (size_t)r0 * nb + b), a1 = ldg_stream((const unsigned *)w.p1 + (size_t)(r0 + 1) * nb + b);
+                    const unsigned a0 = SMEM ? ((const unsigned *)sc0)[b] : ldg_stream((const unsigned *)sc0 + b), a1 = SMEM ? ((const unsigned *)sc1)[b] : ldg_stream((const unsigned *)sc1 + b);
                     const float2 f0 = __half22float2(*(const __half2 *)&a0), f1 = __half22float2(*(const __half2 *)&a1);
                     dv[0][i] = f0.x; mv[0][i] = f0.y; dv[1][i] = f1.x; mv[1][i] = f1.y;
                 } else {
-                    dv[0][i] = __half2float(((const __half *)w.p1)[(size_t)r0 * nb + b]); dv[1][i] = __half2float(((const __half *)w.p1)[(size_t)(r0 + 1) * nb + b]);
+                    dv[0][i] = __half2float(((const __half *)sc0)[b]); dv[1][i] = __half2float(((const __half *)sc1)[b]);
                     mv[0][i] = 0.f; mv[1][i] = 0.f;
                 }
             }
@@ -219,15 +230,15 @@ __device__ __forceinline__ void dot2_q4(const QMat &w, bool q41, int r0, const u
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
                     const unsigned char *at = act + t * astride;
-                    const int4 a0 = *(const int4 *)(at + b * 16), a1 = *(const int4 *)(at + w.cols / 2 + b * 16);
-                    const float ad = ((const float *)(at + w.cols))[b];
-                    const float as = ((const float *)(at + w.cols))[nb + b];
+                    const int4 a0 = *(const int4 *)(at + b * 16), a1 = *(const int4 *)(at + cols / 2 + b * 16);
+                    const float ad = ((const float *)(at + cols))[b];
+                    const float as = ((const float *)(at + cols))[nb + b];
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
-                        int s = __dp4a(lo[r][0], a0.x, 0); s = __dp4a(lo[r][1], a0.y, s); s = __dp4a(lo[r][2], a0.z, s); s = __dp4a(lo[r][3], a0.w, s);
-                        s = __dp4a(hi[r][0], a1.x, s); s = __dp4a(hi[r][1], a1.y, s); s = __dp4a(hi[r][2], a1.z, s); s = __dp4a(hi[r][3], a1.w, s);
-                        if (q41) { accd[r][t] = fmaf(dv[r][i] * ad, (float)s, accd[r][t]); accm[r][t] = fmaf(mv[r][i], as, accm[r][t]); }
-                        else { accd[r][t] += ((float)s * dv[r][i]) * ad; }
+                        int sdot = __dp4a(lo[r][0], a0.x, 0); sdot = __dp4a(lo[r][1], a0.y, sdot); sdot = __dp4a(lo[r][2], a0.z, sdot); sdot = __dp4a(lo[r][3], a0.w, sdot);
+                        sdot = __dp4a(hi[r][0], a1.x, sdot); sdot = __dp4a(hi[r][1], a1.y, sdot); sdot = __dp4a(hi[r][2], a1.z, sdot); sdot = __dp4a(hi[r][3], a1.w, sdot);
+                        if (q41) { accd[r][t] = fmaf(dv[r][i] * ad, (float)sdot, accd[r][t]); accm[r][t] = fmaf(mv[r][i], as, accm[r][t]); }
+                        else { accd[r][t] += ((float)sdot * dv[r][i]) * ad; }
                     }
                 }
             }
@@ -415,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 2) matvec_kernel(const MatvecArgs a)
     constexpr int ACT = act_of(WT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t astride = act_bytes(ACT, a.w.cols);
-    for (int t = 0; t < a.ntok; ++t) stage_act<ACT>(a.x + (size_t)t * a.x_stride, a.norm_w, a.w.cols, smem + t * astride, red);
+    for (int t = 0; t < a.ntok; ++t) stage_act<ACT, false>(a.x + (size_t)t * a.x_stride, a.norm_w, a.w.cols, smem + t * astride, red);
     __syncthreads();
 
     const int row_begin = (blockIdx.x * kWarps + warp) * a.rows_per_warp;
@@ -423,8 +434,10 @@ __global__ void __launch_bounds__(kThreads, 2) matvec_kernel(const MatvecArgs a)
     unsigned long long best = 0ull;
     for (int r0 = row_begin; r0 < row_end; r0 += 2) {
         float res[2][NT];
-        if (WT == GG_Q4_1) dot2_q4<NT>(a.w, true, r0, smem, astride, lane, res);
-        else if (WT == GG_Q4_0) dot2_q4<NT>(a.w, false, r0, smem, astride, lane, res);
+        if (WT == GG_Q4_1 || WT == GG_Q4_0) {
+            const unsigned char *row0 = (const unsigned char *)a.w.p0 + (size_t)r0 * a.w.row_bytes;
+            dot2_q4<NT, false>(row0, row0 + a.w.row_bytes, a.w.cols / 32, a.w.cols, WT == GG_Q4_1, smem, astride, lane, res);
+        }
         else if (WT == GG_Q5_K) dot2_q5k<NT>(a.w, r0, smem, astride, lane, res);
         else if (WT == GG_Q6_K) dot2_q6k<NT>(a.w, r0, smem, astride, lane, res);
         else dot2_f16<NT>(a.w, r0, smem, astride, lane, res);
@@ -477,6 +490,83 @@ __global__ void __launch_bounds__(kThreads, 2) matvec_kernel(const MatvecArgs a)
 // rounded to F16, dots accumulate in F32, exp through the fp16 LUT, soft-max sum in double
 // grid (n_head_local, ntok), block 256, dynamic smem = n_ctx * 6 bytes
 // ---------------------------------------------------------------------------------------------
+template <bool MEGA> __device__ __forceinline__ uint4 ld_kv16(const __half *p) { return MEGA ? __ldcg((const uint4 *)p) : *(const uint4 *)p; }
+template <bool MEGA> __device__ __forceinline__ __half2 ld_kv4(const __half *p) {
+    if (MEGA) { const unsigned u = __ldcg((const unsigned *)p); return *(const __half2 *)&u; }
+    return *(const __half2 *)p;
+}
+// one (head h, token t) of decode/prefill attention; 256 threads; dyn = n_ctx * 6 bytes of shared scratch
+template <bool MEGA>
+__device__ __forceinline__ void attention_head(const float *__restrict__ q, const __half *__restrict__ kc, const __half *__restrict__ vc, float *__restrict__ out,
+                                               int pos, int h, int t, int E, int n_ctx, float kq_scale, const __half *__restrict__ tab_exp,
+                                               unsigned char *dyn, double *red, float *redf, __half *qh, float2 (*part)[64]) {
+    float *sc = (float *)dyn; __half *ph = (__half *)(dyn + (size_t)n_ctx * 4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nkv = pos + 1;
+    if (tid < 128) qh[tid] = __float2half_rn(ld_act<MEGA>(q + (size_t)t * E + h * 128 + tid));
+    cta_sync<MEGA>();
+    // scores: each half-warp takes one key (16 lanes x 8 halves = 128)
+    {
+        const int sub = lane >> 4, l16 = lane & 15;
+        const uint4 qv = *(const uint4 *)(qh + l16 * 8);
+        const __half2 *q2 = (const __half2 *)&qv;
+        constexpr int B = 8;  // keys in flight per half-warp: all loads of a batch are issued before the first use
+        for (int kb0 = warp * 2; kb0 < nkv; kb0 += 16 * B) {  // warp-uniform trip counts (both half-warps shuffle together)
+            uint4 kv[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const int key = kb0 + u * 16 + sub;
+                if (key < nkv) kv[u] = ld_kv16<MEGA>(kc + (size_t)key * E + h * 128 + l16 * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                if (kb0 + u * 16 >= nkv) break;
+                const int key = kb0 + u * 16 + sub;
+                float s = 0.f;
+                if (key < nkv) {
+                    const __half2 *k2 = (const __half2 *)&kv[u];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float2 a = __half22float2(k2[j]), b = __half22float2(q2[j]); s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); }
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (key < nkv && l16 == 0) sc[key] = s * kq_scale;
+            }
+        }
+    }
+    cta_sync<MEGA>();
+    float mx = -INFINITY;
+    for (int i = tid; i < nkv; i += 256) mx = fmaxf(mx, sc[i]);
+    mx = block_max<MEGA>(mx, redf);
+    double sum = 0.0;
+    for (int i = tid; i < nkv; i += 256) { const float v = lut_f16(tab_exp, sc[i] - mx); sc[i] = v; sum += (double)v; }
+    const double tot = block_sum<MEGA>(sum, red);
+    const float inv = (float)(1.0 / tot);
+    for (int i = tid; i < nkv; i += 256) ph[i] = __float2half_rn(sc[i] * inv);
+    cta_sync<MEGA>();
+    // P.V : thread = (key group g of 4, dim pair d2 of 64)
+    {
+        const int g = tid >> 6, d2 = tid & 63;
+        float2 acc = make_float2(0.f, 0.f);
+        constexpr int B = 8;
+        for (int key0 = g; key0 < nkv; key0 += 4 * B) {  // batch the V loads; the FMA order over keys stays sequential
+            __half2 vv[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) { const int key = key0 + 4 * u; if (key < nkv) vv[u] = ld_kv4<MEGA>(vc + (size_t)key * E + h * 128 + d2 * 2); }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const int key = key0 + 4 * u;
+                if (key < nkv) { const float p = __half2float(ph[key]); const float2 v = __half22float2(vv[u]); acc.x = fmaf(v.x, p, acc.x); acc.y = fmaf(v.y, p, acc.y); }
+            }
+        }
+        part[g][d2] = acc;
+    }
+    cta_sync<MEGA>();
+    if (tid < 64) {
+        const float2 a = part[0][tid], b = part[1][tid], c = part[2][tid], d = part[3][tid];
+        *(float2 *)(out + (size_t)t * E + h * 128 + tid * 2) = make_float2((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y));
+    }
+}
 __global__ void __launch_bounds__(256) attn_kernel(const float *__restrict__ q, const __half *__restrict__ kc, const __half *__restrict__ vc,
                                                    float *__restrict__ out, const DeviceState *st, int E, int n_ctx, float kq_scale,
                                                    const __half *__restrict__ tab_exp) {
@@ -485,56 +575,7 @@ __global__ void __launch_bounds__(256) attn_kernel(const float *__restrict__ q, 
     __shared__ float redf[34];
     __shared__ __align__(16) __half qh[128];
     __shared__ float2 part[4][64];
-    float *sc = (float *)smem; __half *ph = (__half *)(smem + (size_t)n_ctx * 4);
-    const int h = blockIdx.x, t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pos = st->n_past + t, nkv = pos + 1;
-    if (tid < 128) qh[tid] = __float2half_rn(q[(size_t)t * E + h * 128 + tid]);
-    __syncthreads();
-    // scores: each half-warp takes one key (16 lanes x 8 halves = 128)
-    {
-        const int sub = lane >> 4, l16 = lane & 15;
-        const uint4 qv = *(const uint4 *)(qh + l16 * 8);
-        const __half2 *q2 = (const __half2 *)&qv;
-        for (int kb = warp * 2; kb < nkv; kb += 16) {  // warp-uniform trip count (both half-warps shuffle together)
-            const int key = kb + sub;
-            float s = 0.f;
-            if (key < nkv) {
-                const uint4 kv = *(const uint4 *)(kc + (size_t)key * E + h * 128 + l16 * 8);
-                const __half2 *k2 = (const __half2 *)&kv;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const float2 a = __half22float2(k2[j]), b = __half22float2(q2[j]); s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); }
-            }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (key < nkv && l16 == 0) sc[key] = s * kq_scale;
-        }
-    }
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int i = tid; i < nkv; i += blockDim.x) mx = fmaxf(mx, sc[i]);
-    mx = block_max(mx, redf);
-    double sum = 0.0;
-    for (int i = tid; i < nkv; i += blockDim.x) { const float v = lut_f16(tab_exp, sc[i] - mx); sc[i] = v; sum += (double)v; }
-    const double tot = block_sum(sum, red);
-    const float inv = (float)(1.0 / tot);
-    for (int i = tid; i < nkv; i += blockDim.x) ph[i] = __float2half_rn(sc[i] * inv);
-    __syncthreads();
-    // P.V : thread = (key group g of 4, dim pair d2 of 64)
-    {
-        const int g = tid >> 6, d2 = tid & 63;
-        float2 acc = make_float2(0.f, 0.f);
-        for (int key = g; key < nkv; key += 4) {
-            const float p = __half2float(ph[key]);
-            const float2 v = __half22float2(*(const __half2 *)(vc + (size_t)key * E + h * 128 + d2 * 2));
-            acc.x = fmaf(v.x, p, acc.x); acc.y = fmaf(v.y, p, acc.y);
-        }
-        part[g][d2] = acc;
-    }
-    __syncthreads();
-    if (tid < 64) {
-        const float2 a = part[0][tid], b = part[1][tid], c = part[2][tid], d = part[3][tid];
-        *(float2 *)(out + (size_t)t * E + h * 128 + tid * 2) = make_float2((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y));
-    }
+    attention_head<false>(q, kc, vc, out, st->n_past + (int)blockIdx.y, (int)blockIdx.x, (int)blockIdx.y, E, n_ctx, kq_scale, tab_exp, smem, red, redf, qh, part);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -589,18 +630,19 @@ __global__ void add_kernel(float *x, const float *y, int n) {
 // load-time repack kernels: raw ggml blocks (row-major) -> SoA planes.  dst_row = r * row_mul + row_off.
 // src block range [blk0, blk0 + nblk) of each source row (tensor-parallel column shards).
 // ---------------------------------------------------------------------------------------------
-__global__ void repack_q4(const unsigned char *src, int src_nb, int blk0, int nblk, int rows, bool q41, uint4 *qs, void *sc, int dst_nb, int row_mul, int row_off, int dst_blk0) {
+__global__ void repack_q4(const unsigned char *src, int src_nb, int blk0, int nblk, int rows, bool q41, unsigned char *dst, int dst_nb, int dst_row_bytes, int row_mul, int row_off, int dst_blk0) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * nblk) return;
     const int r = (int)(i / nblk), b = (int)(i % nblk);
     const int bs = q41 ? 20 : 18, hdr = q41 ? 4 : 2;
     const unsigned char *p = src + ((size_t)r * src_nb + blk0 + b) * bs;
-    const size_t o = (size_t)(r * row_mul + row_off) * dst_nb + dst_blk0 + b;
+    unsigned char *drow = dst + (size_t)(r * row_mul + row_off) * (size_t)dst_row_bytes;
     unsigned w[4];
     for (int j = 0; j < 4; ++j) w[j] = p[hdr + 4 * j] | (p[hdr + 4 * j + 1] << 8) | (p[hdr + 4 * j + 2] << 16) | ((unsigned)p[hdr + 4 * j + 3] << 24);
-    qs[o] = make_uint4(w[0], w[1], w[2], w[3]);
-    if (q41) ((unsigned *)sc)[o] = p[0] | (p[1] << 8) | (p[2] << 16) | ((unsigned)p[3] << 24);
-    else ((unsigned short *)sc)[o] = (unsigned short)(p[0] | (p[1] << 8));
+    ((uint4 *)drow)[dst_blk0 + b] = make_uint4(w[0], w[1], w[2], w[3]);
+    unsigned char *sc = drow + (size_t)dst_nb * 16;
+    if (q41) ((unsigned *)sc)[dst_blk0 + b] = p[0] | (p[1] << 8) | (p[2] << 16) | ((unsigned)p[3] << 24);
+    else ((unsigned short *)sc)[dst_blk0 + b] = (unsigned short)(p[0] | (p[1] << 8));
 }
 __global__ void repack_q5k(const unsigned char *src, int src_nb, int blk0, int nblk, int rows, unsigned char *qs, unsigned char *qh, unsigned char *sc, int dst_nb, int row_mul, int row_off, int dst_blk0) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

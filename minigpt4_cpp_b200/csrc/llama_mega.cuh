@@ -1,0 +1,201 @@
+// llama_mega.cuh — the persistent decode megakernel: ONE launch per generated token.
+//
+// Why: a 7B Q4_1 token streams 4.13 GB of weights in ~160 dependent matvecs of 1.6-12 us each; launched one by one the
+// HBM pipe drains at every kernel boundary (launch gap + prologue + tail) and never gets above ~25 % of peak.  Weights do
+// not depend on activations, so this kernel keeps the weight stream running ACROSS op boundaries:
+//   * grid = one CTA per SM (cooperative launch), 9 warps: warp 8 is the PRODUCER, warps 0-7 are CONSUMERS
+//   * the producer walks the whole op program of the token and copies this CTA's share of every weight matrix
+//     HBM -> shared-memory ring with cp.async.bulk (1-D TMA) + mbarrier complete_tx; it runs ahead of the consumers by
+//     the ring depth (~200 KB per SM = ~30 MB in flight chip-wide), straight through grid barriers and the attention op
+//   * consumers: per op [grid barrier -> stage activations (RMSNorm + Q8 quantise) -> per ring slot: dp4a dot products
+//     with warp-shuffle reductions -> fused epilogue], releasing each slot back to the producer through an mbarrier
+//   * ops communicate through L2 (x, q, att, act, KV cache) with ld.global.cg loads; a grid barrier (atomic counter)
+//     separates dependent ops
+// Reduction orders are the canonical ones of llama_kernels.cuh / oracle.cpp, so results are bit-identical to the
+// stand-alone kernels and to the CPU oracle.
+#pragma once
+#include "llama_kernels.cuh"
+
+namespace mg4 {
+namespace mk {
+using namespace k;
+
+enum OpKind : int { OP_EMBED = 0, OP_QKV = 1, OP_ATTN = 2, OP_WO = 3, OP_GATEUP = 4, OP_DOWN = 5, OP_OUTPUT = 6, OP_FINAL = 7 };
+
+struct MegaOp {
+    int kind, layer, rows, cols;
+    int row_bytes, su_rows, n_su, pad;   // su = "super-unit": su_rows consecutive rows = one ring slot, consumed by one warp
+    const unsigned char *w;              // row-packed Q4 weights (null for non-matvec ops)
+    const float *norm_w;
+};
+
+struct MegaParams {
+    const MegaOp *ops; int n_ops;
+    int n_slots, slot_bytes, act_bytes;
+    int E, FF, n_head, n_ctx, n_vocab;
+    float kq_scale;
+    float *x, *q, *att, *act, *logits;
+    __half *kcache, *vcache;
+    const float2 *rope; const __half *tab_exp, *tab_silu;
+    const unsigned char *tok; int tok_type; size_t tok_row_bytes;
+    DeviceState *state; unsigned *barrier;
+};
+
+constexpr int kMegaThreads = 288;  // 8 consumer warps + 1 producer warp
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count)); }
+__device__ __forceinline__ void mb_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mb_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
+__device__ __forceinline__ void mb_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MB_DONE;\n\t"
+        "bra MB_WAIT;\n\t"
+        "MB_DONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// all consumer threads of all CTAs; `target` = number of arrivals that complete this barrier (monotonic counter)
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
+    __threadfence();
+    cta_sync<true>();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
+        __threadfence();
+    }
+    cta_sync<true>();
+}
+
+template <int WT>
+__global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ double red[34];
+    __shared__ float redf[34];
+    __shared__ __align__(16) __half qh[128];
+    __shared__ float2 part[4][64];
+    constexpr int ACT = act_of(WT);
+    constexpr bool Q41 = WT == GG_Q4_1;
+    unsigned char *ring = smem, *actb = smem + (size_t)P.n_slots * P.slot_bytes;
+    uint64_t *full = (uint64_t *)(actb + P.act_bytes), *empty = full + P.n_slots;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < P.n_slots; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the only CTA-wide barrier; afterwards consumers use named barrier 1 (256 threads)
+
+    if (warp == 8) {  // ------------------------------ producer ------------------------------
+        if (lane == 0) {
+            unsigned n = 0;
+            for (int oi = 0; oi < P.n_ops; ++oi) {
+                const MegaOp op = P.ops[oi];
+                if (!op.w) continue;
+                const int lo = (int)((long long)cta * op.n_su / G), hi = (int)((long long)(cta + 1) * op.n_su / G);
+                for (int su = lo; su < hi; ++su, ++n) {
+                    const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
+                    mb_wait(&empty[s], ph ^ 1u);
+                    const int r0 = su * op.su_rows, nr = min(op.su_rows, op.rows - r0);
+                    const unsigned bytes = (unsigned)nr * (unsigned)op.row_bytes;
+                    mb_expect_tx(&full[s], bytes);
+                    bulk_g2s(ring + (size_t)s * P.slot_bytes, op.w + (size_t)r0 * op.row_bytes, bytes, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ------------------------------------ consumers ------------------------------------
+    unsigned n_base = 0, bar_target = 0;
+    for (int oi = 0; oi < P.n_ops; ++oi) {
+        const MegaOp op = P.ops[oi];
+        if (oi > 0) { bar_target += (unsigned)G; grid_barrier(P.barrier, bar_target); }
+
+        if (op.kind == OP_EMBED) {
+            const int token = __ldcg(&P.state->tokens[0]);
+            const unsigned char *row = P.tok + (size_t)token * P.tok_row_bytes;
+            for (int i = cta * 256 + tid; i < P.E; i += G * 256) P.x[i] = dequant_elem(P.tok_type, row, i);
+            continue;
+        }
+        if (op.kind == OP_ATTN) {
+            if (cta < P.n_head) {
+                const size_t lo = (size_t)op.layer * P.n_ctx * P.E;
+                attention_head<true>(P.q, P.kcache + lo, P.vcache + lo, P.att, __ldcg(&P.state->n_past), cta, 0, P.E, P.n_ctx, P.kq_scale, P.tab_exp, actb, red, redf, qh, part);
+            }
+            continue;
+        }
+        if (op.kind == OP_FINAL) {
+            if (cta == 0 && tid == 0) {
+                DeviceState *st = P.state;
+                const unsigned long long key = __ldcg((const unsigned long long *)&st->argmax_key);
+                const int id = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+                st->argmax_id = id; st->tokens[0] = id; st->argmax_key = 0ull;
+                st->n_past += 1; st->n_tok = 1;
+            }
+            continue;
+        }
+
+        // ---- matvec ops -------------------------------------------------------------------------------------
+        const float *src = op.kind == OP_WO ? P.att : op.kind == OP_DOWN ? P.act : P.x;
+        stage_act<ACT, true>(src, op.norm_w, op.cols, actb, red);
+        cta_sync<true>();
+        const int nb = op.cols / 32;
+        const int lo = (int)((long long)cta * op.n_su / G), hi = (int)((long long)(cta + 1) * op.n_su / G);
+        const int pos = op.kind == OP_QKV ? __ldcg(&P.state->n_past) : 0;
+        unsigned long long best = 0ull;
+        for (int su = lo + warp; su < hi; su += 8) {
+            const unsigned n = n_base + (unsigned)(su - lo);
+            const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
+            mb_wait(&full[s], ph);
+            const unsigned char *slot = ring + (size_t)s * P.slot_bytes;
+            for (int rp = 0; rp < op.su_rows; rp += 2) {
+                const int r0 = su * op.su_rows + rp;
+                if (r0 >= op.rows) break;
+                float res[2][1];
+                dot2_q4<1, true>(slot + (size_t)rp * op.row_bytes, slot + (size_t)(rp + 1) * op.row_bytes, nb, op.cols, Q41, actb, 0, lane, res);
+                const float v0 = res[0][0], v1 = res[1][0];
+                if (lane == 0) switch (op.kind) {
+                    case OP_QKV: {
+                        const int E = P.E, partn = r0 / E, rr = r0 % E;
+                        const size_t kvo = ((size_t)op.layer * P.n_ctx + pos) * E + rr;
+                        if (partn == 2) { *(__half2 *)(P.vcache + kvo) = __floats2half2_rn(v0, v1); }
+                        else {
+                            const float2 cs = P.rope[(size_t)pos * 64 + (rr % 128) / 2];
+                            const float o0 = v0 * cs.x - v1 * cs.y, o1 = v0 * cs.y + v1 * cs.x;
+                            if (partn == 0) *(float2 *)(P.q + rr) = make_float2(o0, o1);
+                            else *(__half2 *)(P.kcache + kvo) = __floats2half2_rn(o0, o1);
+                        }
+                    } break;
+                    case OP_WO: case OP_DOWN: {
+                        const float2 rs = __ldcg((const float2 *)(P.x + r0));
+                        *(float2 *)(P.x + r0) = make_float2(v0 + rs.x, v1 + rs.y);
+                    } break;
+                    case OP_GATEUP: P.act[r0 >> 1] = lut_f16(P.tab_silu, v0) * v1; break;
+                    default: {  // OP_OUTPUT
+                        P.logits[r0] = v0;
+                        const unsigned long long k0 = argmax_key(v0, r0);
+                        best = best > k0 ? best : k0;
+                        if (r0 + 1 < P.n_vocab) { P.logits[r0 + 1] = v1; const unsigned long long k1 = argmax_key(v1, r0 + 1); best = best > k1 ? best : k1; }
+                    } break;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mb_arrive(&empty[s]);
+        }
+        if (op.kind == OP_OUTPUT && lane == 0 && best) atomicMax(&P.state->argmax_key, best);
+        n_base += (unsigned)(hi - lo);
+    }
+}
+
+}  // namespace mk
+}  // namespace mg4

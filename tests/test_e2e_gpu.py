@@ -90,6 +90,30 @@ def test_batch_invariance_and_chain(ext, tiny):
     ext.base.minigpt4_free(c1); ext.base.minigpt4_free(c2)
 
 
+def test_megakernel_equals_per_op_path(ext, orc, tiny, monkeypatch):
+    """The persistent one-launch-per-token megakernel (homogeneous Q4_0/Q4_1) and the per-op graph are the same function."""
+    import os
+    for wt in ("q4_1", "q4_0"):
+        ids = list(range(7, 19))
+        monkeypatch.setenv("MINIGPT4_B200_NO_MEGAKERNEL", "1")
+        c1 = ext.llm_load(tiny[wt], n_ctx=128)
+        monkeypatch.delenv("MINIGPT4_B200_NO_MEGAKERNEL")
+        c2 = ext.llm_load(tiny[wt], n_ctx=128)
+        e = orc.OracleEngine(None, tiny[wt], n_ctx=128)
+        ext.eval_tokens(c1, ids); ext.eval_tokens(c2, ids); e.eval_tokens(ids)
+        for _ in range(24):  # single-token steps go through the decode graph: per-op kernels (c1) vs megakernel (c2)
+            t1, t2 = ext.greedy_id(c1), ext.greedy_id(c2)
+            assert t1 == t2 == int(np.argmax(e.logits))
+            ext.eval_tokens(c1, [t1]); ext.eval_tokens(c2, [t2]); e.eval_tokens([t1])
+            assert np.array_equal(ext.logits(c1), ext.logits(c2)) and np.array_equal(ext.logits(c2), e.logits)
+        ch, _ = ext.decode_chain(c2, 8)
+        host = []
+        for _ in range(8):
+            t = ext.greedy_id(c1); host.append(t); ext.eval_tokens(c1, [t])
+        assert ch.tolist() == host
+        ext.base.minigpt4_free(c1); ext.base.minigpt4_free(c2)
+
+
 def test_context_overflow_is_an_error(ext, tiny):
     c = ext.llm_load(tiny["q4_1"], n_ctx=16)
     with pytest.raises(RuntimeError, match="FailedToAddString"):
