@@ -53,12 +53,18 @@ struct MiniGPT4B200Stats {
     double last_encode_ms;              /* CUDA-event time of the last encode graph */
     unsigned long long kernel_launches; /* kernels of this library launched so far (both graphs) */
     int n_layer, n_embd, n_ff, n_vocab, n_ctx, tp_rank, tp_world, sm_count;
+    int decode_megakernel;              /* 1: decode step = one persistent kernel per token; 0: one launch per op (graph) */
+    int reserved;
 };
 MINIGPT4_API int minigpt4_b200_stats(struct MiniGPT4Context *ctx, struct MiniGPT4B200Stats *out);
 
 /* measurement seam for bench.py's roofline: average CUDA-event duration of one launch of the decode matvec `kind`
  * (0 qkv, 1 wo, 2 gate/up, 3 down, 4 output), cycling through the layers so every launch streams cold weights */
 MINIGPT4_API int minigpt4_b200_time_matvec(struct MiniGPT4Context *ctx, int kind, int reps, float *avg_ms, double *bytes_per_launch);
+
+/* debug: per-op clock64 stamps {op start, grid barrier passed, activations staged, op done} of CTA 0 and CTA G-1 in the last
+ * decode megakernel launch; only recorded when the context was loaded with MINIGPT4_B200_MEGA_TRACE set. Returns #values. */
+MINIGPT4_API int minigpt4_b200_mega_trace(struct MiniGPT4Context *ctx, long long *out, int max_values);
 
 /* kernel-level seams (each runs the production kernel on cuda:current and returns to host) -------------- */
 /* y[n][rows] = W . x  with W given as raw ggml blocks of `ggml_type` (2 Q4_0, 3 Q4_1, 13 Q5_K, 14 Q6_K, 1 F16) */

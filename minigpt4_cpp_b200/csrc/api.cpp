@@ -172,11 +172,13 @@ int minigpt4_b200_stats(struct MiniGPT4Context *ctx, struct MiniGPT4B200Stats *o
     out->last_encode_ms = e->last_encode_ms;
     out->n_layer = d.n_layer; out->n_embd = d.n_embd; out->n_ff = d.n_ff; out->n_vocab = d.n_vocab; out->n_ctx = d.n_ctx;
     out->tp_rank = e->tp.rank; out->tp_world = e->tp.world; out->sm_count = e->llm().sm_count();
+    out->decode_megakernel = e->llm().uses_megakernel() ? 1 : 0;
     return 0;
 }
 int minigpt4_b200_time_matvec(struct MiniGPT4Context *ctx, int kind, int reps, float *avg_ms, double *bytes_per_launch) {
     *avg_ms = E(ctx)->llm().time_matvec(kind, reps, bytes_per_launch); return 0;
 }
+int minigpt4_b200_mega_trace(struct MiniGPT4Context *ctx, long long *out, int max_values) { return E(ctx)->llm().mega_trace(out, max_values); }
 int minigpt4_b200_op_matvec(int ggml_type, int rows, int cols, const void *w_blocks, const float *x, int n, float *y) {
     LlamaDevice::test_matvec(ggml_type, rows, cols, w_blocks, x, n, y); return 0;
 }

@@ -32,7 +32,21 @@ static void launch_mv_nt(int nt, const MatvecArgs &a, int grid, size_t smem, cud
 }
 static int nt_for(int ntok) { return ntok <= 1 ? 1 : ntok <= 2 ? 2 : ntok <= 4 ? 4 : 8; }
 
-static void launch_matvec(MatvecArgs a, int nt, int sm_count, cudaStream_t s, unsigned long long *counter) {
+static void launch_stage(const MatvecArgs &a, cudaStream_t s, unsigned long long *counter) {
+    const int act = act_of(a.w.type);
+    const size_t astride = act_bytes(act, a.w.cols);
+    switch (act) {
+        case ACT_Q8_0: stage_kernel<ACT_Q8_0><<<a.ntok, kThreads, 0, s>>>(a.x, a.x_stride, a.norm_w, a.w.cols, a.staged, astride); break;
+        case ACT_Q8_1: stage_kernel<ACT_Q8_1><<<a.ntok, kThreads, 0, s>>>(a.x, a.x_stride, a.norm_w, a.w.cols, a.staged, astride); break;
+        case ACT_Q8_K: stage_kernel<ACT_Q8_K><<<a.ntok, kThreads, 0, s>>>(a.x, a.x_stride, a.norm_w, a.w.cols, a.staged, astride); break;
+        default: stage_kernel<ACT_F16><<<a.ntok, kThreads, 0, s>>>(a.x, a.x_stride, a.norm_w, a.w.cols, a.staged, astride); break;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    if (counter) ++*counter;
+}
+// restage = false when the previous launch staged the same input in the same format (unfused q/k/v of one type)
+static void launch_matvec(MatvecArgs a, int nt, int sm_count, cudaStream_t s, unsigned long long *counter, bool restage = true) {
+    if (restage) launch_stage(a, s, counter);
     const int rows = a.w.rows;
     const int target = 2 * sm_count * kWarps;
     int rpw = (rows + target - 1) / target;
@@ -120,9 +134,10 @@ LlamaDevice::~LlamaDevice() {
     for (auto &L : layers_) { qmat_free(L.qkv); qmat_free(L.wq); qmat_free(L.wk); qmat_free(L.wv); qmat_free(L.wo); qmat_free(L.w13); qmat_free(L.w2); cudaFree(L.attn_norm); cudaFree(L.ffn_norm); }
     qmat_free(output_);
     for (void *p : {(void *)final_norm_, tok_raw_, (void *)kcache_, (void *)vcache_, (void *)rope_, (void *)tab_exp_, (void *)tab_silu_, (void *)x_, (void *)q_, (void *)att_,
-                    (void *)act_, (void *)logits_, (void *)partial_, (void *)embd_in_, (void *)state_}) if (p) cudaFree(p);
+                    (void *)act_, (void *)logits_, (void *)partial_, (void *)qact_, (void *)embd_in_, (void *)state_}) if (p) cudaFree(p);
     if (mega_ops_) cudaFree(mega_ops_);
     if (mega_barrier_) cudaFree(mega_barrier_);
+    if (mega_trace_) cudaFree(mega_trace_);
     delete (mk::MegaParams *)mega_params_;
     if (h_state_) cudaFreeHost(h_state_);
     if (h_argmax_) cudaFreeHost(h_argmax_);
@@ -226,6 +241,7 @@ bool LlamaDevice::load(const LlamaFile &f, int n_ctx, TPLink *tp) {
     CUDA_CHECK(cudaMalloc((void **)&att_, (size_t)8 * El * 4));
     CUDA_CHECK(cudaMalloc((void **)&act_, (size_t)8 * FFl * 4));
     CUDA_CHECK(cudaMalloc((void **)&partial_, (size_t)8 * E * 4));
+    CUDA_CHECK(cudaMalloc((void **)&qact_, (size_t)8 * ((size_t)std::max(E, FF) * 2 + 4096)));
     CUDA_CHECK(cudaMalloc((void **)&logits_, (size_t)(d_.n_vocab + 1) * 4));
     CUDA_CHECK(cudaMalloc((void **)&embd_in_, (size_t)512 * E * 4));
     CUDA_CHECK(cudaMalloc((void **)&state_, sizeof(DeviceState))); CUDA_CHECK(cudaMemset(state_, 0, sizeof(DeviceState)));
@@ -250,18 +266,21 @@ void LlamaDevice::launch_layers(int nt, int ntok, bool want_logits) {
         Layer &L = layers_[(size_t)il];
         __half *kc = kcache_ + (size_t)il * C * El, *vc = vcache_ + (size_t)il * C * El;
         MatvecArgs a{};
-        a.x = x_; a.x_stride = E; a.norm_w = L.attn_norm; a.ntok = ntok; a.epi = EPI_QKV;
+        a.x = x_; a.x_stride = E; a.norm_w = L.attn_norm; a.ntok = ntok; a.epi = EPI_QKV; a.staged = qact_;
         a.q_out = q_; a.kcache = kc; a.vcache = vc; a.rope = rope_; a.e_local = El; a.half_dim = 64; a.state = state_; a.tab_silu = tab_silu_;
         if (L.fused_qkv) { a.w = L.qkv; a.part = -1; a.n_valid = a.w.rows; launch_matvec(a, nt, sm_count_, stream_, &launches_); }
         else {
             const QMat *ms[3] = {&L.wq, &L.wk, &L.wv};
-            for (int part = 0; part < 3; ++part) { a.w = *ms[part]; a.part = part; a.n_valid = a.w.rows; launch_matvec(a, nt, sm_count_, stream_, &launches_); }
+            for (int part = 0; part < 3; ++part) {
+                const bool same = part > 0 && act_of(ms[part]->type) == act_of(ms[part - 1]->type);
+                a.w = *ms[part]; a.part = part; a.n_valid = a.w.rows; launch_matvec(a, nt, sm_count_, stream_, &launches_, !same);
+            }
         }
         attn_kernel<<<dim3((unsigned)n_head_local_, (unsigned)ntok), 256, attn_smem, stream_>>>(q_, kc, vc, att_, state_, El, C, kq_scale, tab_exp_);
         CUDA_CHECK(cudaGetLastError()); ++launches_;
 
         MatvecArgs b{};
-        b.w = L.wo; b.x = att_; b.x_stride = El; b.norm_w = nullptr; b.ntok = ntok; b.n_valid = b.w.rows; b.state = state_; b.tab_silu = tab_silu_;
+        b.w = L.wo; b.x = att_; b.x_stride = El; b.norm_w = nullptr; b.ntok = ntok; b.n_valid = b.w.rows; b.state = state_; b.tab_silu = tab_silu_; b.staged = qact_;
         if (!tp) { b.epi = EPI_RESID; b.out = x_; b.out_stride = E; b.resid = x_; launch_matvec(b, nt, sm_count_, stream_, &launches_); }
         else {
             b.epi = EPI_PLAIN; b.out = partial_; b.out_stride = E; launch_matvec(b, nt, sm_count_, stream_, &launches_);
@@ -270,10 +289,10 @@ void LlamaDevice::launch_layers(int nt, int ntok, bool want_logits) {
         }
         MatvecArgs c{};
         c.w = L.w13; c.x = x_; c.x_stride = E; c.norm_w = L.ffn_norm; c.ntok = ntok; c.epi = EPI_SWIGLU; c.out = act_; c.out_stride = FFl; c.n_valid = c.w.rows;
-        c.state = state_; c.tab_silu = tab_silu_;
+        c.state = state_; c.tab_silu = tab_silu_; c.staged = qact_;
         launch_matvec(c, nt, sm_count_, stream_, &launches_);
         MatvecArgs e{};
-        e.w = L.w2; e.x = act_; e.x_stride = FFl; e.norm_w = nullptr; e.ntok = ntok; e.n_valid = e.w.rows; e.state = state_; e.tab_silu = tab_silu_;
+        e.w = L.w2; e.x = act_; e.x_stride = FFl; e.norm_w = nullptr; e.ntok = ntok; e.n_valid = e.w.rows; e.state = state_; e.tab_silu = tab_silu_; e.staged = qact_;
         if (!tp) { e.epi = EPI_RESID; e.out = x_; e.out_stride = E; e.resid = x_; launch_matvec(e, nt, sm_count_, stream_, &launches_); }
         else {
             e.epi = EPI_PLAIN; e.out = partial_; e.out_stride = E; launch_matvec(e, nt, sm_count_, stream_, &launches_);
@@ -284,7 +303,7 @@ void LlamaDevice::launch_layers(int nt, int ntok, bool want_logits) {
     if (want_logits) {
         MatvecArgs o{};
         o.w = output_; o.x = x_ + (size_t)(ntok - 1) * E; o.x_stride = E; o.norm_w = final_norm_; o.ntok = 1; o.epi = EPI_LOGITS; o.out = logits_; o.n_valid = d_.n_vocab;
-        o.state = state_; o.tab_silu = tab_silu_;
+        o.state = state_; o.tab_silu = tab_silu_; o.staged = qact_;
         launch_matvec(o, 1, sm_count_, stream_, &launches_);
     }
     finalize_kernel<<<1, 32, 0, stream_>>>(state_, want_logits ? 1 : 0, nullptr); ++launches_;
@@ -408,6 +427,9 @@ bool LlamaDevice::build_mega() {
     P->rope = rope_; P->tab_exp = tab_exp_; P->tab_silu = tab_silu_;
     P->tok = (const unsigned char *)tok_raw_; P->tok_type = tok_type_; P->tok_row_bytes = gg_row_bytes(tok_type_, (size_t)E);
     P->state = state_; P->barrier = mega_barrier_;
+    P->trace = nullptr;
+    if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, ops.size() * 8 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, ops.size() * 8 * sizeof(long long))); P->trace = mega_trace_; }
+    mega_n_ops_ = (int)ops.size();
     mega_params_ = P;
     mega_smem_ = (size_t)n_slots * slot + act_b + (size_t)n_slots * 16 + 64;
     mega_type_ = wt;
@@ -480,6 +502,13 @@ float LlamaDevice::decode_chain(int steps, int n_past, int32_t *ids_out) {
     return ms;
 }
 
+int LlamaDevice::mega_trace(long long *out, int max_values) {
+    if (!mega_trace_) return 0;
+    const int n = std::min(max_values, mega_n_ops_ * 8);
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    CUDA_CHECK(cudaMemcpy(out, mega_trace_, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+    return n;
+}
 float LlamaDevice::time_matvec(int kind, int reps, double *bytes_per_launch) {
     const int E = d_.n_embd, El = n_embd_local_, FFl = n_ff_local_, C = d_.n_ctx;
     void *flush = nullptr; const size_t flush_bytes = 256u << 20;
@@ -490,7 +519,7 @@ float LlamaDevice::time_matvec(int kind, int reps, double *bytes_per_launch) {
     auto one = [&](int il) {
         Layer &L = layers_[(size_t)(kind == 4 ? 0 : il)];
         MatvecArgs a{};
-        a.ntok = 1; a.state = state_; a.tab_silu = tab_silu_;
+        a.ntok = 1; a.state = state_; a.tab_silu = tab_silu_; a.staged = qact_;
         switch (kind) {
             case 0: a.w = L.fused_qkv ? L.qkv : L.wq; a.x = x_; a.x_stride = E; a.norm_w = L.attn_norm; a.epi = EPI_QKV; a.q_out = q_;
                     a.kcache = kcache_ + (size_t)il * C * El; a.vcache = vcache_ + (size_t)il * C * El; a.rope = rope_; a.e_local = El; a.half_dim = 64; a.part = L.fused_qkv ? -1 : 0; break;
@@ -538,21 +567,22 @@ void LlamaDevice::test_matvec(int gg, int rows, int cols, const void *w_host, co
     QMat m; Stager st;
     qmat_alloc(m, gg, rows, cols);
     repack_into(m, t, st, 0, rows, 0, cols, 1, 0, 0);
-    float *x, *y; DeviceState *stt;
+    float *x, *y; DeviceState *stt; unsigned char *stg;
+    CUDA_CHECK(cudaMalloc((void **)&stg, (size_t)8 * ((size_t)cols * 2 + 4096)));
     CUDA_CHECK(cudaMalloc((void **)&x, (size_t)n * cols * 4)); CUDA_CHECK(cudaMalloc((void **)&y, (size_t)n * m.rows * 4));
     CUDA_CHECK(cudaMalloc((void **)&stt, sizeof(DeviceState))); CUDA_CHECK(cudaMemset(stt, 0, sizeof(DeviceState)));
     CUDA_CHECK(cudaMemcpy(x, x_host, (size_t)n * cols * 4, cudaMemcpyHostToDevice));
     for (int i = 0; i < n; i += 8) {
         const int c = std::min(8, n - i);
         MatvecArgs a{};
-        a.w = m; a.x = x + (size_t)i * cols; a.x_stride = cols; a.ntok = c; a.epi = EPI_PLAIN; a.out = y + (size_t)i * m.rows; a.out_stride = m.rows; a.n_valid = rows; a.state = stt;
+        a.w = m; a.x = x + (size_t)i * cols; a.x_stride = cols; a.ntok = c; a.epi = EPI_PLAIN; a.out = y + (size_t)i * m.rows; a.out_stride = m.rows; a.n_valid = rows; a.state = stt; a.staged = stg;
         launch_matvec(a, nt_for(c), prop.multiProcessorCount, 0, nullptr);
     }
     CUDA_CHECK(cudaDeviceSynchronize());
     std::vector<float> tmp((size_t)n * m.rows);
     CUDA_CHECK(cudaMemcpy(tmp.data(), y, tmp.size() * 4, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) memcpy(y_host + (size_t)i * rows, tmp.data() + (size_t)i * m.rows, (size_t)rows * 4);
-    cudaFree(x); cudaFree(y); cudaFree(stt); qmat_free(m);
+    cudaFree(x); cudaFree(y); cudaFree(stt); cudaFree(stg); qmat_free(m);
 }
 
 }  // namespace mg4

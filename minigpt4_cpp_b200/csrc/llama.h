@@ -51,6 +51,7 @@ public:
     void sync();
     int sm_count() const { return sm_count_; }
     bool uses_megakernel() const { return mega_; }
+    int mega_trace(long long *out, int max_values);  // debug: per-op clock64 stamps of the last megakernel launch (env MINIGPT4_B200_MEGA_TRACE)
     // one decode step through the captured CUDA graph: feeds `id` (or, if id < 0, the on-device arg-max of the
     // previous step), leaves new logits/arg-max on device.
     bool decode_step(int32_t id, int n_past);
@@ -88,6 +89,7 @@ private:
     __half *tab_exp_ = nullptr, *tab_silu_ = nullptr;  // ggml's fp16 LUTs
     float *x_ = nullptr, *q_ = nullptr, *att_ = nullptr, *act_ = nullptr, *logits_ = nullptr, *partial_ = nullptr;
     float *embd_in_ = nullptr;
+    unsigned char *qact_ = nullptr;                 // per-op staged (quantised) activations for the per-op kernels
     DeviceState *state_ = nullptr;
     DeviceState *h_state_ = nullptr;  // pinned
     int32_t *h_argmax_ = nullptr;     // pinned
@@ -97,6 +99,7 @@ private:
     size_t bytes_per_token_ = 0;
     unsigned long long launches_ = 0;
     int graph_kernels_ = 0;
+    long long *mega_trace_ = nullptr; int mega_n_ops_ = 0;
     bool mega_ = false; void *mega_ops_ = nullptr; unsigned *mega_barrier_ = nullptr; void *mega_params_ = nullptr; size_t mega_smem_ = 0; int mega_type_ = -1;
     int sm_count_ = 148;
 };

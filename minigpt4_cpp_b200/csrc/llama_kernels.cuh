@@ -40,6 +40,7 @@ struct MatvecArgs {
     QMat w;
     const float *x; int x_stride;     // F32 input rows [ntok][x_stride]
     const float *norm_w;              // fused RMSNorm weight (nullable)
+    unsigned char *staged;            // global scratch [ntok][act_bytes]: activations quantised ONCE per op by stage_kernel
     int ntok; int rows_per_warp; int epi; int n_valid;  // n_valid: real row count (rows may be padded to even)
     float *out; int out_stride; const float *resid;
     // EPI_QKV
@@ -419,14 +420,24 @@ __device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {  //
 // the matvec family: y[t][r] = W[r] . act(x[t]) for t < ntok (<= NT), with a fused prologue (RMSNorm + quantise)
 // and a fused epilogue (RoPE + KV append | residual add | SwiGLU | logits + arg-max)
 // ---------------------------------------------------------------------------------------------
+// RMSNorm + quantise the op's input rows once (grid = ntok); every matvec CTA then just copies the staged bytes
+template <int ACT>
+__global__ void __launch_bounds__(kThreads) stage_kernel(const float *x, int x_stride, const float *norm_w, int cols, unsigned char *out, size_t astride) {
+    __shared__ double red[34];
+    stage_act<ACT, false>(x + (size_t)blockIdx.x * x_stride, norm_w, cols, out + (size_t)blockIdx.x * astride, red);
+}
+
 template <int WT, int NT>
 __global__ void __launch_bounds__(kThreads, 2) matvec_kernel(const MatvecArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double red[34];
     constexpr int ACT = act_of(WT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t astride = act_bytes(ACT, a.w.cols);
-    for (int t = 0; t < a.ntok; ++t) stage_act<ACT, false>(a.x + (size_t)t * a.x_stride, a.norm_w, a.w.cols, smem + t * astride, red);
+    {   // activations were staged once per op by stage_kernel: copy them into shared memory
+        const uint4 *src = (const uint4 *)a.staged; uint4 *dst = (uint4 *)smem;
+        const int n16 = (int)((size_t)a.ntok * astride / 16);
+        for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = src[i];
+    }
     __syncthreads();
 
     const int row_begin = (blockIdx.x * kWarps + warp) * a.rows_per_warp;

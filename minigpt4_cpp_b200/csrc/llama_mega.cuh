@@ -39,6 +39,7 @@ struct MegaParams {
     const float2 *rope; const __half *tab_exp, *tab_silu;
     const unsigned char *tok; int tok_type; size_t tok_row_bytes;
     DeviceState *state; unsigned *barrier;
+    long long *trace;  // optional [2 CTAs][n_ops][4] clock64 stamps: op start, barrier passed, activations staged, op done
 };
 
 constexpr int kMegaThreads = 288;  // 8 consumer warps + 1 producer warp
@@ -73,6 +74,47 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
         __threadfence();
     }
     cta_sync<true>();
+}
+
+// Register-resident activation staging for the megakernel (Q8_0 / Q8_1 targets).  Thread t owns elements t, t+256, ...
+// for BOTH passes (RMS partial sum and quantisation: block b = warp + 8k holds element b*32 + lane = t + 256k), so the
+// input vector is fetched from L2 exactly once, all loads in flight together (one L2 round trip instead of one per block).
+// Same arithmetic and reduction order as k::stage_act.
+constexpr int kStageMaxK = 56;  // supports up to 14336 columns
+template <int ACT>
+__device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, const float *__restrict__ nw, int cols, unsigned char *sm, double *red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nk = cols >> 8;  // cols is a multiple of 256
+    float v[kStageMaxK];
+#pragma unroll
+    for (int k = 0; k < kStageMaxK; ++k) if (k < nk) v[k] = __ldcg(x + tid + 256 * k);
+    if (nw) {
+        double ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < kStageMaxK; ++k) if (k < nk) ss += (double)(v[k] * v[k]);
+        const double tot = block_sum<true>(ss, red);
+        const float mean = (float)(tot / (double)cols);
+        const float scale = 1.0f / sqrtf(mean + 1e-6f);
+#pragma unroll
+        for (int k = 0; k < kStageMaxK; ++k) if (k < nk) v[k] = (v[k] * scale) * nw[tid + 256 * k];
+    }
+    int8_t *qs = (int8_t *)sm; float *d = (float *)(sm + cols); float *s = d + cols / 32;
+#pragma unroll
+    for (int k = 0; k < kStageMaxK; ++k) {
+        if (k < nk) {
+            const int b = warp + 8 * k;
+            const float amax = warp_max(fabsf(v[k]));
+            const float dd = amax / 127.f;
+            const float id = amax != 0.0f ? 127.f / amax : 0.0f;
+            const int q = __float2int_rn(v[k] * id);
+            qs[(lane < 16 ? 0 : cols / 2) + b * 16 + (lane & 15)] = (int8_t)q;
+            const int sum = warp_sum(q);
+            if (lane == 0) {
+                if (ACT == ACT_Q8_0) { d[b] = __half2float(__float2half_rn(dd)); s[b] = 0.f; }
+                else { d[b] = dd; s[b] = dd * (float)sum; }
+            }
+        }
+    }
 }
 
 template <int WT>
@@ -117,9 +159,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
 
     // ------------------------------------ consumers ------------------------------------
     unsigned n_base = 0, bar_target = 0;
+    const int pos = __ldcg(&P.state->n_past);  // position of the token being decoded (state only changes in OP_FINAL)
     for (int oi = 0; oi < P.n_ops; ++oi) {
         const MegaOp op = P.ops[oi];
+        long long *tr = (P.trace && tid == 0 && (cta == 0 || cta == G - 1)) ? P.trace + ((size_t)(cta == 0 ? 0 : 1) * P.n_ops + oi) * 4 : nullptr;
+        if (tr) { tr[0] = clock64(); tr[2] = 0; }
         if (oi > 0) { bar_target += (unsigned)G; grid_barrier(P.barrier, bar_target); }
+        if (tr) tr[1] = clock64();
 
         if (op.kind == OP_EMBED) {
             const int token = __ldcg(&P.state->tokens[0]);
@@ -130,7 +176,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         if (op.kind == OP_ATTN) {
             if (cta < P.n_head) {
                 const size_t lo = (size_t)op.layer * P.n_ctx * P.E;
-                attention_head<true>(P.q, P.kcache + lo, P.vcache + lo, P.att, __ldcg(&P.state->n_past), cta, 0, P.E, P.n_ctx, P.kq_scale, P.tab_exp, actb, red, redf, qh, part);
+                attention_head<true>(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, 0, P.E, P.n_ctx, P.kq_scale, P.tab_exp, actb, red, redf, qh, part);
             }
             continue;
         }
@@ -147,15 +193,20 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
 
         // ---- matvec ops -------------------------------------------------------------------------------------
         const float *src = op.kind == OP_WO ? P.att : op.kind == OP_DOWN ? P.act : P.x;
-        stage_act<ACT, true>(src, op.norm_w, op.cols, actb, red);
+        stage_act_mega<ACT>(src, op.norm_w, op.cols, actb, red);
         cta_sync<true>();
+        if (tr) tr[2] = clock64();
         const int nb = op.cols / 32;
         const int lo = (int)((long long)cta * op.n_su / G), hi = (int)((long long)(cta + 1) * op.n_su / G);
-        const int pos = op.kind == OP_QKV ? __ldcg(&P.state->n_past) : 0;
         unsigned long long best = 0ull;
         for (int su = lo + warp; su < hi; su += 8) {
             const unsigned n = n_base + (unsigned)(su - lo);
             const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
+            float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};  // residual rows of this slot, fetched before the wait
+            if (op.kind == OP_WO || op.kind == OP_DOWN) {
+                rs[0] = __ldcg((const float2 *)(P.x + su * op.su_rows));
+                if (op.su_rows > 2) rs[1] = __ldcg((const float2 *)(P.x + su * op.su_rows + 2));
+            }
             mb_wait(&full[s], ph);
             const unsigned char *slot = ring + (size_t)s * P.slot_bytes;
             for (int rp = 0; rp < op.su_rows; rp += 2) {
@@ -177,8 +228,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
                         }
                     } break;
                     case OP_WO: case OP_DOWN: {
-                        const float2 rs = __ldcg((const float2 *)(P.x + r0));
-                        *(float2 *)(P.x + r0) = make_float2(v0 + rs.x, v1 + rs.y);
+                        const float2 r2 = rp == 0 ? rs[0] : rs[1];
+                        *(float2 *)(P.x + r0) = make_float2(v0 + r2.x, v1 + r2.y);
                     } break;
                     case OP_GATEUP: P.act[r0 >> 1] = lut_f16(P.tab_silu, v0) * v1; break;
                     default: {  // OP_OUTPUT
@@ -194,6 +245,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         }
         if (op.kind == OP_OUTPUT && lane == 0 && best) atomicMax(&P.state->argmax_key, best);
         n_base += (unsigned)(hi - lo);
+        if (tr) tr[3] = clock64();  // (thread 0 = warp 0 only; other warps may still be consuming)
     }
 }
 

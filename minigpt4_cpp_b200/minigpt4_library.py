@@ -190,7 +190,8 @@ def load_library() -> MiniGPT4SharedLibrary:
 class Stats(C.Structure):
     _fields_ = [("llm_weight_bytes_per_token", C.c_double), ("vision_flops_per_image", C.c_double), ("vision_weight_bytes", C.c_double),
                 ("last_encode_ms", C.c_double), ("kernel_launches", C.c_ulonglong), ("n_layer", C.c_int), ("n_embd", C.c_int), ("n_ff", C.c_int),
-                ("n_vocab", C.c_int), ("n_ctx", C.c_int), ("tp_rank", C.c_int), ("tp_world", C.c_int), ("sm_count", C.c_int)]
+                ("n_vocab", C.c_int), ("n_ctx", C.c_int), ("tp_rank", C.c_int), ("tp_world", C.c_int), ("sm_count", C.c_int), ("decode_megakernel", C.c_int),
+                ("reserved", C.c_int)]
 
 
 _VP = C.c_void_p
@@ -214,6 +215,7 @@ _EXT = {
     "minigpt4_b200_encode_images": ([_CTX, C.POINTER(MiniGPT4Images), C.POINTER(MiniGPT4Embeddings)], _I),
     "minigpt4_b200_stats": ([_CTX, C.POINTER(Stats)], _I),
     "minigpt4_b200_time_matvec": ([_CTX, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_double)], _I),
+    "minigpt4_b200_mega_trace": ([_CTX, _VP, _I], _I),
     "minigpt4_b200_op_matvec": ([_I, _I, _I, _VP, _VP, _I, _VP], _I),
     "minigpt4_b200_op_gemm_f16": ([_I, _I, _I, _VP, _VP, _VP, _I, _VP], _I),
     "minigpt4_b200_op_layernorm": ([_VP, _I, _I, _VP, _VP, _VP], _I),
@@ -289,6 +291,11 @@ class B200:
         ms, nb = C.c_float(0), C.c_double(0)
         self._chk(self.L.minigpt4_b200_time_matvec(ctx.ptr, kind, reps, C.byref(ms), C.byref(nb)))
         return ms.value, nb.value
+
+    def mega_trace(self, ctx) -> np.ndarray:
+        buf = np.zeros(2 * 400 * 4, np.int64)
+        n = self.L.minigpt4_b200_mega_trace(ctx.ptr, _ptr(buf), buf.size)
+        return buf[:n].reshape(2, -1, 4) if n else buf[:0]
 
     def stats(self, ctx) -> Stats:
         s = Stats()

@@ -1,0 +1,32 @@
+"""Per-op timeline of the decode megakernel (needs MINIGPT4_B200_MEGA_TRACE=1): prints where a token's time goes."""
+import os, sys, json
+os.environ["MINIGPT4_B200_MEGA_TRACE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import minigpt4_cpp_b200 as m
+import bench
+lib = m.load_library(); ext = m.B200(lib)
+vis, llm, _ = bench.ensure_models("7b", "q4_1", 39)
+ctx = ext.llm_load(llm, n_ctx=2048)
+rows = np.random.default_rng(0).standard_normal((32, 4096)).astype(np.float32)
+ext.eval_embd(ctx, rows)
+ids, ms = ext.decode_chain(ctx, 128)
+print("chain ms/token", ms / 128)
+tr = ext.mega_trace(ctx).astype(np.float64)  # last launch
+names = {0: "embed", 1: "qkv", 2: "attn", 3: "wo", 4: "gate_up", 5: "down", 6: "output", 7: "final"}
+kinds = [0] + [1, 2, 3, 4, 5] * 32 + [6, 7]
+mhz = 1965.0
+for c in range(2):
+    t = tr[c]
+    tot = (t[-1, 1] - t[0, 0]) / mhz
+    print(f"CTA {'0' if c == 0 else 'G-1'}: total {tot:.1f} us")
+    agg = {}
+    for i, k in enumerate(kinds):
+        start, bar, staged, done = t[i]
+        nxt = t[i + 1, 0] if i + 1 < len(kinds) else t[i, 1]
+        a = agg.setdefault(names[k], [0, 0.0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += (bar - start) / mhz
+        if staged: a[2] += (staged - bar) / mhz; a[3] += (done - staged) / mhz
+        a[4] += (nxt - start) / mhz
+    for k, a in agg.items():
+        print(f"  {k:8s} n={a[0]:3d} barrier {a[1]/a[0]:6.2f} us  stage {a[2]/a[0]:6.2f} us  consume {a[3]/a[0]:6.2f} us  total/op {a[4]/a[0]:6.2f} us  sum {a[4]:8.1f} us")
