@@ -380,7 +380,7 @@ bool LlamaDevice::build_mega() {
     const int wt = output_.type;
     if (wt != GG_Q4_0 && wt != GG_Q4_1) return false;
     for (auto &L : layers_) if (!L.fused_qkv || L.qkv.type != wt || L.wo.type != wt || L.w13.type != wt || L.w2.type != wt) return false;
-    if (d_.n_embd % 256 || d_.n_ff % 256) return false;
+    if (d_.n_embd % 256 || d_.n_ff % 256 || std::max(d_.n_embd, d_.n_ff) > 2048 * mk::kStageMaxK || d_.n_embd % 128 || d_.n_ff % 128) return false;
     int coop = 0, dev = 0; CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     if (!coop) return false;
@@ -433,14 +433,24 @@ bool LlamaDevice::build_mega() {
     mega_params_ = P;
     mega_smem_ = (size_t)n_slots * slot + act_b + (size_t)n_slots * 16 + 64;
     mega_type_ = wt;
-    if (wt == GG_Q4_1) CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<GG_Q4_1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_));
-    else CUDA_CHECK(cudaFuncSetAttribute(decode_megakernel<GG_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_));
+    mega_stk_ = (std::max(E, FF) + 2047) / 2048;
+    const void *fn = mega_fn();
+    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_));
     int occ = 0;
-    if (wt == GG_Q4_1) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_megakernel<GG_Q4_1>, kMegaThreads, mega_smem_));
-    else CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_megakernel<GG_Q4_0>, kMegaThreads, mega_smem_));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kMegaThreads, mega_smem_));
     if (occ < 1) { MG4_ERR("megakernel does not fit on an SM (smem %zu)", mega_smem_); return false; }
     MG4_INFO("decode megakernel: %d ops/token, ring %d x %d B, act %zu B, %zu B shared per CTA, grid %d", (int)ops.size(), n_slots, slot, act_b, mega_smem_, sm_count_);
     return true;
+}
+const void *LlamaDevice::mega_fn() const {
+    using namespace mk;
+    const bool q41 = mega_type_ == GG_Q4_1;
+    switch (mega_stk_) {
+        case 1: case 2: return q41 ? (const void *)decode_megakernel<GG_Q4_1, 2> : (const void *)decode_megakernel<GG_Q4_0, 2>;
+        case 3: case 4: return q41 ? (const void *)decode_megakernel<GG_Q4_1, 4> : (const void *)decode_megakernel<GG_Q4_0, 4>;
+        case 5: case 6: return q41 ? (const void *)decode_megakernel<GG_Q4_1, 6> : (const void *)decode_megakernel<GG_Q4_0, 6>;
+        default: return q41 ? (const void *)decode_megakernel<GG_Q4_1, 7> : (const void *)decode_megakernel<GG_Q4_0, 7>;
+    }
 }
 void LlamaDevice::launch_mega() {
     using namespace mk;
@@ -450,9 +460,8 @@ void LlamaDevice::launch_mega() {
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    const MegaParams &P = *(const MegaParams *)mega_params_;
-    if (mega_type_ == GG_Q4_1) CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_megakernel<GG_Q4_1>, P));
-    else CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_megakernel<GG_Q4_0>, P));
+    void *args[1] = {mega_params_};
+    CUDA_CHECK(cudaLaunchKernelExC(&cfg, mega_fn(), args));
     ++launches_;
     CUDA_CHECK(cudaMemcpyAsync(h_argmax_, &state_->argmax_id, 4, cudaMemcpyDeviceToHost, stream_));
 }

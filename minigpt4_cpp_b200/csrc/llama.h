@@ -77,6 +77,7 @@ private:
     void build_graph();
     bool build_mega();               // persistent one-launch-per-token decode (homogeneous Q4_0/Q4_1, single GPU)
     void launch_mega();
+    const void *mega_fn() const;
     LlamaDims d_{};
     int n_head_local_ = 0, n_embd_local_ = 0, n_ff_local_ = 0;
     TPLink *tp_ = nullptr;
@@ -100,6 +101,7 @@ private:
     unsigned long long launches_ = 0;
     int graph_kernels_ = 0;
     long long *mega_trace_ = nullptr; int mega_n_ops_ = 0;
+    int mega_stk_ = 7;
     bool mega_ = false; void *mega_ops_ = nullptr; unsigned *mega_barrier_ = nullptr; void *mega_params_ = nullptr; size_t mega_smem_ = 0; int mega_type_ = -1;
     int sm_count_ = 148;
 };

@@ -127,9 +127,24 @@ __device__ void stage_act(const float *__restrict__ x, const float *__restrict__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5; constexpr int nwarps = 8, nthreads = 256;
     float scale = 1.0f;
     if (nw) {
-        double ss = 0.0;
-        for (int i = tid; i < cols; i += nthreads) { const float v = ld_act<MEGA>(x + i); ss += (double)(v * v); }
-        const double tot = block_sum<MEGA>(ss, red);
+        // canonical RMS order (oracle.cpp): 512 partials, partial p owns elements 2048k + 4p + e; 16 warp butterflies + a top
+        // butterfly.  This 256-thread kernel computes partials p = tid and p = tid + 256.
+        double ssa = 0.0, ssb = 0.0;
+        for (int k = 0; 2048 * k < cols; ++k) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ia = 2048 * k + 4 * tid + e, ib = ia + 1024;
+                if (ia < cols) { const float v = ld_act<MEGA>(x + ia); ssa += (double)(v * v); }
+                if (ib < cols) { const float v = ld_act<MEGA>(x + ib); ssb += (double)(v * v); }
+            }
+        }
+        ssa = warp_sum(ssa); ssb = warp_sum(ssb);
+        cta_sync<MEGA>();
+        if (lane == 0) { red[warp] = ssa; red[warp + 8] = ssb; }
+        cta_sync<MEGA>();
+        if (warp == 0) { double t = lane < 16 ? red[lane] : 0.0; t = warp_sum(t); if (lane == 0) red[32] = t; }
+        cta_sync<MEGA>();
+        const double tot = red[32];
         const float mean = (float)(tot / (double)cols);
         scale = 1.0f / sqrtf(mean + 1e-6f);
     }
@@ -510,7 +525,7 @@ template <bool MEGA> __device__ __forceinline__ __half2 ld_kv4(const __half *p) 
 template <bool MEGA>
 __device__ __forceinline__ void attention_head(const float *__restrict__ q, const __half *__restrict__ kc, const __half *__restrict__ vc, float *__restrict__ out,
                                                int pos, int h, int t, int E, int n_ctx, float kq_scale, const __half *__restrict__ tab_exp,
-                                               unsigned char *dyn, double *red, float *redf, __half *qh, float2 (*part)[64]) {
+                                               unsigned char *dyn, double *red, float *redf, __half *qh, float *part /*[16*128]*/) {
     float *sc = (float *)dyn; __half *ph = (__half *)(dyn + (size_t)n_ctx * 4);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nkv = pos + 1;
@@ -555,27 +570,41 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
     const float inv = (float)(1.0 / tot);
     for (int i = tid; i < nkv; i += 256) ph[i] = __float2half_rn(sc[i] * inv);
     cta_sync<MEGA>();
-    // P.V : thread = (key group g of 4, dim pair d2 of 64)
+    // P.V : thread = (key group g of 16, dim octet o of 16); groups are combined by a pairwise tree (canonical order)
     {
-        const int g = tid >> 6, d2 = tid & 63;
-        float2 acc = make_float2(0.f, 0.f);
-        constexpr int B = 8;
-        for (int key0 = g; key0 < nkv; key0 += 4 * B) {  // batch the V loads; the FMA order over keys stays sequential
-            __half2 vv[B];
+        const int g = tid >> 4, o = tid & 15;
+        float acc[8];
 #pragma unroll
-            for (int u = 0; u < B; ++u) { const int key = key0 + 4 * u; if (key < nkv) vv[u] = ld_kv4<MEGA>(vc + (size_t)key * E + h * 128 + d2 * 2); }
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        constexpr int B = 8;
+        for (int key0 = g; key0 < nkv; key0 += 16 * B) {  // batch the V loads; the FMA order over keys stays sequential
+            uint4 vv[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) { const int key = key0 + 16 * u; if (key < nkv) vv[u] = ld_kv16<MEGA>(vc + (size_t)key * E + h * 128 + o * 8); }
 #pragma unroll
             for (int u = 0; u < B; ++u) {
-                const int key = key0 + 4 * u;
-                if (key < nkv) { const float p = __half2float(ph[key]); const float2 v = __half22float2(vv[u]); acc.x = fmaf(v.x, p, acc.x); acc.y = fmaf(v.y, p, acc.y); }
+                const int key = key0 + 16 * u;
+                if (key < nkv) {
+                    const float p = __half2float(ph[key]);
+                    const __half2 *v2 = (const __half2 *)&vv[u];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float2 v = __half22float2(v2[j]); acc[2 * j] = fmaf(v.x, p, acc[2 * j]); acc[2 * j + 1] = fmaf(v.y, p, acc[2 * j + 1]); }
+                }
             }
         }
-        part[g][d2] = acc;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) part[g * 128 + o * 8 + e] = acc[e];
     }
     cta_sync<MEGA>();
-    if (tid < 64) {
-        const float2 a = part[0][tid], b = part[1][tid], c = part[2][tid], d = part[3][tid];
-        *(float2 *)(out + (size_t)t * E + h * 128 + tid * 2) = make_float2((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y));
+    if (tid < 128) {
+        float v[16];
+#pragma unroll
+        for (int g = 0; g < 16; ++g) v[g] = part[g * 128 + tid];
+#pragma unroll
+        for (int st = 1; st < 16; st <<= 1)
+#pragma unroll
+            for (int g = 0; g < 16; g += 2 * st) v[g] = v[g] + v[g + st];
+        out[(size_t)t * E + h * 128 + tid] = v[0];
     }
 }
 __global__ void __launch_bounds__(256) attn_kernel(const float *__restrict__ q, const __half *__restrict__ kc, const __half *__restrict__ vc,
@@ -585,7 +614,7 @@ __global__ void __launch_bounds__(256) attn_kernel(const float *__restrict__ q, 
     __shared__ double red[34];
     __shared__ float redf[34];
     __shared__ __align__(16) __half qh[128];
-    __shared__ float2 part[4][64];
+    __shared__ float part[16 * 128];
     attention_head<false>(q, kc, vc, out, st->n_past + (int)blockIdx.y, (int)blockIdx.x, (int)blockIdx.y, E, n_ctx, kq_scale, tab_exp, smem, red, redf, qh, part);
 }
 

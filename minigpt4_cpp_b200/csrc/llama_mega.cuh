@@ -3,7 +3,8 @@
 // Why: a 7B Q4_1 token streams 4.13 GB of weights in ~160 dependent matvecs of 1.6-12 us each; launched one by one the
 // HBM pipe drains at every kernel boundary (launch gap + prologue + tail) and never gets above ~25 % of peak.  Weights do
 // not depend on activations, so this kernel keeps the weight stream running ACROSS op boundaries:
-//   * grid = one CTA per SM (cooperative launch), 9 warps: warp 8 is the PRODUCER, warps 0-7 are CONSUMERS
+//   * grid = one CTA per SM (cooperative launch), 16 warps (4 per SM sub-partition, 128 registers each): warp 15 is the
+//     PRODUCER, warps 0-14 are CONSUMERS (warps 0-7 also stage activations and run the attention op)
 //   * the producer walks the whole op program of the token and copies this CTA's share of every weight matrix
 //     HBM -> shared-memory ring with cp.async.bulk (1-D TMA) + mbarrier complete_tx; it runs ahead of the consumers by
 //     the ring depth (~200 KB per SM = ~30 MB in flight chip-wide), straight through grid barriers and the attention op
@@ -42,7 +43,10 @@ struct MegaParams {
     long long *trace;  // optional [2 CTAs][n_ops][4] clock64 stamps: op start, barrier passed, activations staged, op done
 };
 
-constexpr int kMegaThreads = 288;  // 8 consumer warps + 1 producer warp
+constexpr int kConsumerWarps = 15, kConsumerThreads = 480;
+constexpr int kMegaThreads = kConsumerThreads + 32;  // 15 consumer warps + 1 producer warp = 16 warps
+// named barriers: 1 = the 256 threads of warps 0-7 (activation staging, attention); 2 = all 480 consumer threads
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 2, 480;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count)); }
@@ -65,7 +69,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // all consumer threads of all CTAs; `target` = number of arrivals that complete this barrier (monotonic counter)
 __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
     __threadfence();
-    cta_sync<true>();
+    consumer_sync();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
@@ -73,57 +77,85 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
         do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
         __threadfence();
     }
-    cta_sync<true>();
+    consumer_sync();
 }
 
-// Register-resident activation staging for the megakernel (Q8_0 / Q8_1 targets).  Thread t owns elements t, t+256, ...
-// for BOTH passes (RMS partial sum and quantisation: block b = warp + 8k holds element b*32 + lane = t + 256k), so the
-// input vector is fetched from L2 exactly once, all loads in flight together (one L2 round trip instead of one per block).
-// Same arithmetic and reduction order as k::stage_act.
-constexpr int kStageMaxK = 56;  // supports up to 14336 columns
-template <int ACT>
+// Register-resident activation staging for the megakernel (Q8_0 / Q8_1 targets), executed by warps 0-7 (256 threads).
+// Thread t owns the float4s at elements 2048k + 4t and 2048k + 1024 + 4t (k = 0..): the input vector is fetched from L2
+// exactly once with all loads in flight together; its two RMS partials are canonical partials t and t + 256 (oracle.cpp
+// op_rms_norm_mul, same as k::stage_act); a 32-weight quant block is covered by 8 consecutive lanes, so amax / sum need
+// 3 shuffle steps and all (k, half) are independent work.  Quantisation is order-free (max, integer sums): identical bytes.
+constexpr int kStageMaxK = 7;  // up to 14336 columns
+template <int ACT, int STK>
 __device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, const float *__restrict__ nw, int cols, unsigned char *sm, double *red) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nk = cols >> 8;  // cols is a multiple of 256
-    float v[kStageMaxK];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // tid < 256
+    float4 v[STK][2];
 #pragma unroll
-    for (int k = 0; k < kStageMaxK; ++k) if (k < nk) v[k] = __ldcg(x + tid + 256 * k);
+    for (int k = 0; k < STK; ++k)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) { const int i = 2048 * k + 1024 * hf + 4 * tid; if (i < cols) v[k][hf] = __ldcg((const float4 *)(x + i)); }
     if (nw) {
-        double ss = 0.0;
+        double ssa = 0.0, ssb = 0.0;
 #pragma unroll
-        for (int k = 0; k < kStageMaxK; ++k) if (k < nk) ss += (double)(v[k] * v[k]);
-        const double tot = block_sum<true>(ss, red);
+        for (int k = 0; k < STK; ++k) {
+            const int ia = 2048 * k + 4 * tid, ib = ia + 1024;
+            if (ia < cols) { const float4 a = v[k][0]; ssa += (double)(a.x * a.x); ssa += (double)(a.y * a.y); ssa += (double)(a.z * a.z); ssa += (double)(a.w * a.w); }
+            if (ib < cols) { const float4 b = v[k][1]; ssb += (double)(b.x * b.x); ssb += (double)(b.y * b.y); ssb += (double)(b.z * b.z); ssb += (double)(b.w * b.w); }
+        }
+        ssa = warp_sum(ssa); ssb = warp_sum(ssb);
+        cta_sync<true>();
+        if (lane == 0) { red[warp] = ssa; red[warp + 8] = ssb; }
+        cta_sync<true>();
+        if (warp == 0) { double t = lane < 16 ? red[lane] : 0.0; t = warp_sum(t); if (lane == 0) red[32] = t; }
+        cta_sync<true>();
+        const double tot = red[32];
         const float mean = (float)(tot / (double)cols);
         const float scale = 1.0f / sqrtf(mean + 1e-6f);
 #pragma unroll
-        for (int k = 0; k < kStageMaxK; ++k) if (k < nk) v[k] = (v[k] * scale) * nw[tid + 256 * k];
-    }
-    int8_t *qs = (int8_t *)sm; float *d = (float *)(sm + cols); float *s = d + cols / 32;
+        for (int k = 0; k < STK; ++k)
 #pragma unroll
-    for (int k = 0; k < kStageMaxK; ++k) {
-        if (k < nk) {
-            const int b = warp + 8 * k;
-            const float amax = warp_max(fabsf(v[k]));
-            const float dd = amax / 127.f;
-            const float id = amax != 0.0f ? 127.f / amax : 0.0f;
-            const int q = __float2int_rn(v[k] * id);
-            qs[(lane < 16 ? 0 : cols / 2) + b * 16 + (lane & 15)] = (int8_t)q;
-            const int sum = warp_sum(q);
-            if (lane == 0) {
-                if (ACT == ACT_Q8_0) { d[b] = __half2float(__float2half_rn(dd)); s[b] = 0.f; }
-                else { d[b] = dd; s[b] = dd * (float)sum; }
+            for (int hf = 0; hf < 2; ++hf) {
+                const int i = 2048 * k + 1024 * hf + 4 * tid;
+                if (i < cols) {
+                    const float4 w4 = *(const float4 *)(nw + i);
+                    float4 &a = v[k][hf];
+                    a.x = (a.x * scale) * w4.x; a.y = (a.y * scale) * w4.y; a.z = (a.z * scale) * w4.z; a.w = (a.w * scale) * w4.w;
+                }
+            }
+    }
+    unsigned char *qs = sm; float *d = (float *)(sm + cols); float *s = d + cols / 32;
+    const int j8 = tid & 7;
+#pragma unroll
+    for (int k = 0; k < STK; ++k)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int i = 2048 * k + 1024 * hf + 4 * tid;
+            if (i < cols) {  // warp-uniform: cols is a multiple of 128
+                const float4 a = v[k][hf];
+                const int b = 64 * k + 32 * hf + (tid >> 3);
+                float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                const float dd = amax / 127.f;
+                const float id = amax != 0.0f ? 127.f / amax : 0.0f;
+                const int q0 = __float2int_rn(a.x * id), q1 = __float2int_rn(a.y * id), q2 = __float2int_rn(a.z * id), q3 = __float2int_rn(a.w * id);
+                *(unsigned *)(qs + (j8 < 4 ? 0 : cols / 2) + b * 16 + (j8 & 3) * 4) = (unsigned)(q0 & 0xff) | ((unsigned)(q1 & 0xff) << 8) | ((unsigned)(q2 & 0xff) << 16) | ((unsigned)(q3 & 0xff) << 24);
+                int sum = (q0 + q1) + (q2 + q3);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                if (j8 == 0) {
+                    if (ACT == ACT_Q8_0) { d[b] = __half2float(__float2half_rn(dd)); s[b] = 0.f; }
+                    else { d[b] = dd; s[b] = dd * (float)sum; }
+                }
             }
         }
-    }
 }
 
-template <int WT>
+template <int WT, int STK>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ double red[34];
     __shared__ float redf[34];
     __shared__ __align__(16) __half qh[128];
-    __shared__ float2 part[4][64];
+    __shared__ float part[16 * 128];
     constexpr int ACT = act_of(WT);
     constexpr bool Q41 = WT == GG_Q4_1;
     unsigned char *ring = smem, *actb = smem + (size_t)P.n_slots * P.slot_bytes;
@@ -135,9 +167,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         for (int s = 0; s < P.n_slots; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();  // the only CTA-wide barrier; afterwards consumers use named barrier 1 (256 threads)
+    __syncthreads();  // the only CTA-wide barrier; afterwards consumers use named barriers 2 (512 thr) and 1 (256 thr, attention)
 
-    if (warp == 8) {  // ------------------------------ producer ------------------------------
+    if (warp == kConsumerWarps) {  // ------------------------------ producer ------------------------------
         if (lane == 0) {
             unsigned n = 0;
             for (int oi = 0; oi < P.n_ops; ++oi) {
@@ -170,11 +202,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         if (op.kind == OP_EMBED) {
             const int token = __ldcg(&P.state->tokens[0]);
             const unsigned char *row = P.tok + (size_t)token * P.tok_row_bytes;
-            for (int i = cta * 256 + tid; i < P.E; i += G * 256) P.x[i] = dequant_elem(P.tok_type, row, i);
+            for (int i = cta * kConsumerThreads + tid; i < P.E; i += G * kConsumerThreads) P.x[i] = dequant_elem(P.tok_type, row, i);
             continue;
         }
         if (op.kind == OP_ATTN) {
-            if (cta < P.n_head) {
+            if (cta < P.n_head && tid < 256) {  // one head per CTA, 256 threads (named barrier 1)
                 const size_t lo = (size_t)op.layer * P.n_ctx * P.E;
                 attention_head<true>(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, 0, P.E, P.n_ctx, P.kq_scale, P.tab_exp, actb, red, redf, qh, part);
             }
@@ -193,13 +225,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
 
         // ---- matvec ops -------------------------------------------------------------------------------------
         const float *src = op.kind == OP_WO ? P.att : op.kind == OP_DOWN ? P.act : P.x;
-        stage_act_mega<ACT>(src, op.norm_w, op.cols, actb, red);
-        cta_sync<true>();
+        if (tid < 256) stage_act_mega<ACT, STK>(src, op.norm_w, op.cols, actb, red);
+        consumer_sync();
         if (tr) tr[2] = clock64();
         const int nb = op.cols / 32;
         const int lo = (int)((long long)cta * op.n_su / G), hi = (int)((long long)(cta + 1) * op.n_su / G);
         unsigned long long best = 0ull;
-        for (int su = lo + warp; su < hi; su += 8) {
+        for (int su = lo + warp; su < hi; su += kConsumerWarps) {
             const unsigned n = n_base + (unsigned)(su - lo);
             const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
             float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};  // residual rows of this slot, fetched before the wait

@@ -310,13 +310,14 @@ template <typename T> static inline T butterfly(T *v, int n) {  // v'[l] = v[l] 
     for (int o = n / 2; o > 0; o >>= 1) { for (int l = 0; l < n; ++l) t[l] = v[l] + v[l ^ o]; for (int l = 0; l < n; ++l) v[l] = t[l]; }
     return v[0];
 }
-// block_sum of llama_kernels.cuh: 256 threads, thread t owns elements t, t+256, ...; warp butterflies, then a butterfly over the 8 warp sums
-static double block_sum_256(const double *partial /*[256]*/) {
+// block_sum of llama_kernels.cuh: NW warps of 32 partials; warp butterflies, then a butterfly over the NW warp sums
+static double block_sum_n(const double *partial, int nw) {
     double w[32];
     for (int l = 0; l < 32; ++l) w[l] = 0.0;
-    for (int wi = 0; wi < 8; ++wi) { double v[32]; for (int l = 0; l < 32; ++l) v[l] = partial[wi * 32 + l]; w[wi] = butterfly(v, 32); }
+    for (int wi = 0; wi < nw; ++wi) { double v[32]; for (int l = 0; l < 32; ++l) v[l] = partial[wi * 32 + l]; w[wi] = butterfly(v, 32); }
     return butterfly(w, 32);
 }
+static double block_sum_256(const double *partial /*[256]*/) { return block_sum_n(partial, 8); }
 
 static float dot_canon_q4_1(int n, const block_q4_1 *x, const block_q8_1 *y) {
     const int nb = n / QK;
@@ -550,9 +551,9 @@ static void op_layernorm(const float *x, float *y, int n, int rows, const float 
 static void op_rms_norm_mul(const float *x, float *y, int n, int rows, const float *w) {  // ggml_rms_norm eps 1e-6, then ggml_mul
     for (int r = 0; r < rows; ++r) {
         const float *xr = x + (size_t)r * n; float *yr = y + (size_t)r * n;
-        double part[256];  // canonical order: 256 strided partial sums in double, then block_sum_256
-        for (int t = 0; t < 256; ++t) { double s = 0; for (int i = t; i < n; i += 256) s += (double)(xr[i] * xr[i]); part[t] = s; }
-        const double sum = block_sum_256(part);
+        double part[512];  // canonical order: 512 partials; partial p owns elements 2048k + 4p + e (k outer, e = 0..3 inner)
+        for (int t = 0; t < 512; ++t) { double s = 0; for (int k = 0; 2048 * k + 4 * t < n; ++k) for (int e = 0; e < 4; ++e) { const int i = 2048 * k + 4 * t + e; if (i < n) s += (double)(xr[i] * xr[i]); } part[t] = s; }
+        const double sum = block_sum_n(part, 16);
         const float mean = (float)(sum / n);
         const float scale = 1.0f / sqrtf(mean + 1e-6f);
         for (int i = 0; i < n; ++i) yr[i] = (xr[i] * scale) * w[i];
@@ -803,7 +804,7 @@ ORACLE_API int oracle_llama_eval(void *l, const int32_t *tokens, const float *em
 #pragma omp parallel for schedule(dynamic) collapse(2)
         for (int h = 0; h < H; ++h) for (int i = 0; i < N; ++i) {
             // canonical orders = csrc/llama_kernels.cuh attn_kernel: 16 lanes x 8 dims per key then a 16-lane butterfly;
-            // soft-max sum: 256 strided double partials + block_sum_256; P.V: 4 key groups (key mod 4), combined (a+b)+(c+d)
+            // soft-max sum: 256 strided double partials + block_sum_256; P.V: 16 key groups (key mod 16), combined by a pairwise tree
             std::vector<f16_t> qh(hd), ph(nkv); std::vector<float> pr(nkv);
             for (int d = 0; d < hd; ++d) qh[d] = f2h(q[(size_t)i * E + h * hd + d]);
             const int nvis = n_past + i + 1;  // keys visible to this row (ggml_diag_mask_inf masks the rest to -inf -> 0)
@@ -819,9 +820,11 @@ ORACLE_API int oracle_llama_eval(void *l, const int32_t *tokens, const float *em
             const float inv = (float)(1.0 / block_sum_256(part));
             for (int t = 0; t < nvis; ++t) ph[t] = f2h(pr[t] * inv);
             for (int d = 0; d < hd; ++d) {
-                float g4[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int t = 0; t < nvis; ++t) g4[t & 3] = fmaf(h2f(vc[(size_t)t * E + h * hd + d]), h2f(ph[t]), g4[t & 3]);
-                att[(size_t)i * E + h * hd + d] = (g4[0] + g4[1]) + (g4[2] + g4[3]);
+                float g16[16];
+                for (int g = 0; g < 16; ++g) g16[g] = 0.f;
+                for (int t = 0; t < nvis; ++t) g16[t & 15] = fmaf(h2f(vc[(size_t)t * E + h * hd + d]), h2f(ph[t]), g16[t & 15]);
+                for (int st = 1; st < 16; st <<= 1) for (int g = 0; g < 16; g += 2 * st) g16[g] = g16[g] + g16[g + st];  // pairwise tree
+                att[(size_t)i * E + h * hd + d] = g16[0];
             }
         }
         mul_mat(T(m, p + "attention.wo.weight"), att.data(), N, cur.data(), true);
