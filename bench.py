@@ -11,7 +11,8 @@ decode-only, 32-token image prefix + 128 generated tokens").  Reported per JSON 
   roofline   decode dequant-matvec family: algorithmic weight bytes / CUDA-event time per launch vs MEASURED_PEAKS hbm_gbs
   cpu_baseline  the CPU oracle (a restatement of the reference's ggml path) on this box's host cores, bounded sample
 `--impl reference` times that CPU path alone (the reference itself cannot be built here: DESIGN.md "Oracle").
-N > 1 (torchrun): the LLaMA step is tensor-parallel over N GPUs (one NCCL sum per row-split matmul); "scaling": "strong".
+N > 1 (torchrun): default --mode replicas = one independent decode stream per GPU (the path is per-session work; no data-path
+collective; "scaling": "weak"); --mode tp = the optional tensor-parallel LLaMA step of north_star ("strong").
 """
 from __future__ import annotations
 
@@ -190,7 +191,7 @@ def run_reference(args):
             enc_ms.append((t1 - t0) * 1e3); dec_s.append(t3 - t2); step_s.append(t3 - t0)
     v = n_tok * len(dec_s) / sum(dec_s)
     line = {"impl": "reference", "metric": "decode tokens/s (Vicuna-7B q4_1) + image-encode ms", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(step_s) / len(step_s), "higher_is_better": True, "scaling": "strong",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(step_s) / len(step_s), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8 x int4 dot (Q8_1 x Q4_1), f32 accumulate", "data": "synthetic",
             "config": {"workload": f"Vicuna-{args.size} {args.wtype} decode, {N_PREFIX}-row image prefix + {n_tok} generated tokens per step (bounded CPU sample of the 128-token workload)"},
             "encode_ms": max(enc_ms) if enc_ms else None,
@@ -212,6 +213,9 @@ def main():
     ap.add_argument("--cpu-tokens", type=int, default=8)
     ap.add_argument("--cpu-encode-every-step", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "tp"],
+                    help="N>1: 'replicas' = one independent decode stream per GPU, no data-path collective (weak scaling, default); "
+                         "'tp' = one stream, LLaMA layers tensor-parallel over the GPUs with an NCCL sum per row-split matmul (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -229,11 +233,12 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        uid = np.zeros(128, np.uint8)
-        if rank == 0:
-            ext.L.minigpt4_b200_tp_unique_id(uid.ctypes.data_as(ctypes.c_void_p))
-        t = torch.from_numpy(uid).cuda(); dist.broadcast(t, 0); uid = t.cpu().numpy()
-        ext.L.minigpt4_b200_tp_configure(rank, world, uid.ctypes.data_as(ctypes.c_void_p))
+        if args.mode == "tp":
+            uid = np.zeros(128, np.uint8)
+            if rank == 0:
+                ext.L.minigpt4_b200_tp_unique_id(uid.ctypes.data_as(ctypes.c_void_p))
+            t = torch.from_numpy(uid).cuda(); dist.broadcast(t, 0); uid = t.cpu().numpy()
+            ext.L.minigpt4_b200_tp_configure(rank, world, uid.ctypes.data_as(ctypes.c_void_p))
     if rank == 0:
         paths = ensure_models(args.size, args.wtype, args.blocks)
     if dist:
@@ -291,8 +296,9 @@ def main():
         t = torch.tensor([chain_ms, e2e_s, wall, enc_dev, enc_wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         chain_ms, e2e_s, wall, enc_dev, enc_wall = t.tolist()
-    value = args.steps * N_GEN / (chain_ms * 1e-3)
-    e2e = args.steps * N_GEN / e2e_s
+    streams = world if (world > 1 and args.mode == "replicas") else 1  # independent decode streams in the job
+    value = streams * args.steps * N_GEN / (chain_ms * 1e-3)   # whole-job tokens/s: all streams / slowest rank's time
+    e2e = streams * args.steps * N_GEN / e2e_s
 
     # roofline of the decode dequant-matvec family (CUDA events, cold weights: each launch streams a different layer)
     st = ext.stats(ctx)
@@ -301,7 +307,7 @@ def main():
         # the decode step IS one kernel (decode_megakernel, one launch per token): algorithmic bytes per launch = weight bytes
         # streamed per token; launch duration = CUDA-event time of the chained loop / launches (includes the in-kernel attention,
         # grid barriers and activation staging — nothing is hidden)
-        us = chain_ms * 1e3 / (args.steps * N_GEN)
+        us = chain_ms * 1e3 / (args.steps * N_GEN)  # per launch on one GPU (max over ranks)
         ach = st.llm_weight_bytes_per_token / us * 1e-3
         roofline = {"bound": "hbm", "kernel": f"decode_megakernel<{args.wtype}> (1 launch per token: {st.n_layer} x [qkv, attention, wo, gate_up, down] + output/arg-max)",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
@@ -321,9 +327,10 @@ def main():
 
     line = {"metric": "decode tokens/s (Vicuna-7B q4_1, 32-row image prefix + 128 generated) + image-encode ms", "value": value, "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int4 dot (Q8_1 x Q4_1) f32-accumulate decode; f16 x f16 -> f32 tcgen05 encode", "data": "synthetic",
+            "scaling": "weak" if streams > 1 or world == 1 else "strong", "vs_baseline": None,
+            "dtype": "int8 x int4 dot (Q8_1 x Q4_1) f32-accumulate decode; f16 x f16 -> f32 tcgen05 encode", "data": "synthetic",
             "config": {"workload": f"configs[1]: Vicuna-{args.size} {args.wtype} decode-only, {N_PREFIX}-row image prefix + {N_GEN} generated tokens; plus ViT-g f16 224x224 encode ({args.blocks} blocks) per step",
-                       "parallelism": f"tp{world}" if world > 1 else "single-gpu", "l2": "inputs larger than L2 (4.1 GB of weights streamed per token vs 126 MB L2)",
+                       "parallelism": (f"tp{world}" if args.mode == "tp" else f"dp{world} (one independent stream per GPU, no data-path collective)") if world > 1 else "single-gpu", "l2": "inputs larger than L2 (4.1 GB of weights streamed per token vs 126 MB L2)",
                        "value_region": "CUDA-event time of the 128-step device-chained greedy decode loop", "n_ctx": 2048},
             "encode_ms": enc_dev, "encode_e2e_ms": enc_wall,
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": int(img.nbytes + 32 * st.n_embd * 4 + 4 * 64), "d2h_bytes_per_step": int(32 * st.n_embd * 4 + 4 * N_GEN),

@@ -387,15 +387,16 @@ bool LlamaDevice::build_mega() {
     const int E = d_.n_embd, FF = d_.n_ff;
     const int act = act_of(wt);
     size_t act_b = std::max(act_bytes(act, FF), act_bytes(act, E));
-    act_b = std::max(act_b, (size_t)d_.n_ctx * 6);
     act_b = (act_b + 127) & ~(size_t)127;
+    size_t xs_b = std::max((size_t)std::max(E, FF) * 4, (size_t)d_.n_ctx * 6);  // F32 input vector / attention scratch
+    xs_b = (xs_b + 127) & ~(size_t)127;
     const int rb_e = layers_[0].qkv.row_bytes, rb_ff = layers_[0].w2.row_bytes;
     int slot = std::max(2 * rb_e, 2 * rb_ff);
     slot = std::max(slot, 4 * rb_e);
     slot = (slot + 127) & ~127;
     cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     const size_t budget = prop.sharedMemPerBlockOptin - 2048;  // static shared + slack
-    const int n_slots = (int)std::min<size_t>(24, (budget - act_b - 512) / (size_t)slot);
+    const int n_slots = (int)std::min<size_t>(24, (budget - 9216 - act_b - xs_b - 512) / (size_t)slot);  // 9 KB of static shared memory
     if (n_slots < 4) return false;
     auto su_rows_for = [&](int row_bytes) { int r = (slot / row_bytes) & ~1; return std::max(2, std::min(r, 4)); };
     std::vector<MegaOp> ops;
@@ -420,7 +421,7 @@ bool LlamaDevice::build_mega() {
     CUDA_CHECK(cudaMalloc((void **)&mega_barrier_, 64)); CUDA_CHECK(cudaMemset(mega_barrier_, 0, 64));
     MegaParams *P = new MegaParams();
     P->ops = (const MegaOp *)mega_ops_; P->n_ops = (int)ops.size();
-    P->n_slots = n_slots; P->slot_bytes = slot; P->act_bytes = (int)act_b;
+    P->n_slots = n_slots; P->slot_bytes = slot; P->act_bytes = (int)act_b; P->xs_bytes = (int)xs_b;
     P->E = E; P->FF = FF; P->n_head = d_.n_head; P->n_ctx = d_.n_ctx; P->n_vocab = d_.n_vocab;
     P->kq_scale = 1.0f / sqrtf((float)d_.n_embd / (float)d_.n_head);
     P->x = x_; P->q = q_; P->att = att_; P->act = act_; P->logits = logits_; P->kcache = kcache_; P->vcache = vcache_;
@@ -431,7 +432,7 @@ bool LlamaDevice::build_mega() {
     if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, ops.size() * 8 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, ops.size() * 8 * sizeof(long long))); P->trace = mega_trace_; }
     mega_n_ops_ = (int)ops.size();
     mega_params_ = P;
-    mega_smem_ = (size_t)n_slots * slot + act_b + (size_t)n_slots * 16 + 64;
+    mega_smem_ = (size_t)n_slots * slot + xs_b + act_b + (size_t)n_slots * 16 + 64;
     mega_type_ = wt;
     mega_stk_ = (std::max(E, FF) + 2047) / 2048;
     const void *fn = mega_fn();
@@ -439,18 +440,12 @@ bool LlamaDevice::build_mega() {
     int occ = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kMegaThreads, mega_smem_));
     if (occ < 1) { MG4_ERR("megakernel does not fit on an SM (smem %zu)", mega_smem_); return false; }
-    MG4_INFO("decode megakernel: %d ops/token, ring %d x %d B, act %zu B, %zu B shared per CTA, grid %d", (int)ops.size(), n_slots, slot, act_b, mega_smem_, sm_count_);
+    MG4_INFO("decode megakernel: %d ops/token, ring %d x %d B, xs %zu B, act %zu B, %zu B shared per CTA, grid %d", (int)ops.size(), n_slots, slot, xs_b, act_b, mega_smem_, sm_count_);
     return true;
 }
 const void *LlamaDevice::mega_fn() const {
     using namespace mk;
-    const bool q41 = mega_type_ == GG_Q4_1;
-    switch (mega_stk_) {
-        case 1: case 2: return q41 ? (const void *)decode_megakernel<GG_Q4_1, 2> : (const void *)decode_megakernel<GG_Q4_0, 2>;
-        case 3: case 4: return q41 ? (const void *)decode_megakernel<GG_Q4_1, 4> : (const void *)decode_megakernel<GG_Q4_0, 4>;
-        case 5: case 6: return q41 ? (const void *)decode_megakernel<GG_Q4_1, 6> : (const void *)decode_megakernel<GG_Q4_0, 6>;
-        default: return q41 ? (const void *)decode_megakernel<GG_Q4_1, 7> : (const void *)decode_megakernel<GG_Q4_0, 7>;
-    }
+    return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1> : (const void *)decode_megakernel<GG_Q4_0>;
 }
 void LlamaDevice::launch_mega() {
     using namespace mk;

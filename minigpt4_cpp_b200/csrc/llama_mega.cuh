@@ -32,7 +32,7 @@ struct MegaOp {
 
 struct MegaParams {
     const MegaOp *ops; int n_ops;
-    int n_slots, slot_bytes, act_bytes;
+    int n_slots, slot_bytes, act_bytes, xs_bytes;   // shared memory: [ring][xs: F32 input / attention scratch][act: staged Q8][mbarriers]
     int E, FF, n_head, n_ctx, n_vocab;
     float kq_scale;
     float *x, *q, *att, *act, *logits;
@@ -80,27 +80,78 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
     consumer_sync();
 }
 
-// Register-resident activation staging for the megakernel (Q8_0 / Q8_1 targets), executed by warps 0-7 (256 threads).
-// Thread t owns the float4s at elements 2048k + 4t and 2048k + 1024 + 4t (k = 0..): the input vector is fetched from L2
-// exactly once with all loads in flight together; its two RMS partials are canonical partials t and t + 256 (oracle.cpp
-// op_rms_norm_mul, same as k::stage_act); a 32-weight quant block is covered by 8 consecutive lanes, so amax / sum need
-// 3 shuffle steps and all (k, half) are independent work.  Quantisation is order-free (max, integer sums): identical bytes.
+// Two rows of a shared-memory ring slot against the staged activation vector.  Same per-lane block order and the same
+// arithmetic as k::dot2_q4 (lane l: blocks l, l+32, ... increasing; butterfly reductions), but one block at a time: shared
+// memory latency is short, so there is no need to keep 8 blocks in registers, and the megakernel stays free of spills.
+template <bool Q41>
+__device__ __forceinline__ void dot2_q4_slot(const unsigned char *row0, const unsigned char *row1, int nb, int cols, const unsigned char *act, int lane, float &r0, float &r1) {
+    const uint4 *qs0 = (const uint4 *)row0, *qs1 = (const uint4 *)row1;
+    const unsigned char *sc0 = row0 + (size_t)nb * 16, *sc1 = row1 + (size_t)nb * 16;
+    const float *ad = (const float *)(act + cols), *as = ad + nb;
+    float accd0 = 0.f, accd1 = 0.f, accm0 = 0.f, accm1 = 0.f;
+#pragma unroll 2
+    for (int b = lane; b < nb; b += 32) {
+        const uint4 q0 = qs0[b], q1 = qs1[b];
+        const int4 a0 = *(const int4 *)(act + b * 16), a1 = *(const int4 *)(act + cols / 2 + b * 16);
+        const float adv = ad[b];
+        float d0, m0 = 0.f, d1, m1 = 0.f;
+        if (Q41) {
+            const float2 f0 = __half22float2(((const __half2 *)sc0)[b]), f1 = __half22float2(((const __half2 *)sc1)[b]);
+            d0 = f0.x; m0 = f0.y; d1 = f1.x; m1 = f1.y;
+        } else { d0 = __half2float(((const __half *)sc0)[b]); d1 = __half2float(((const __half *)sc1)[b]); }
+        const unsigned w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w};
+        const int av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        int s0 = 0, s1 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int l0 = (int)(w0[j] & 0x0F0F0F0Fu), l1 = (int)(w1[j] & 0x0F0F0F0Fu);
+            if (!Q41) { l0 = (int)__vsub4((unsigned)l0, 0x08080808u); l1 = (int)__vsub4((unsigned)l1, 0x08080808u); }
+            s0 = __dp4a(l0, av[j], s0); s1 = __dp4a(l1, av[j], s1);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int h0 = (int)((w0[j] >> 4) & 0x0F0F0F0Fu), h1 = (int)((w1[j] >> 4) & 0x0F0F0F0Fu);
+            if (!Q41) { h0 = (int)__vsub4((unsigned)h0, 0x08080808u); h1 = (int)__vsub4((unsigned)h1, 0x08080808u); }
+            s0 = __dp4a(h0, av[4 + j], s0); s1 = __dp4a(h1, av[4 + j], s1);
+        }
+        if (Q41) {
+            const float asv = as[b];
+            accd0 = fmaf(d0 * adv, (float)s0, accd0); accm0 = fmaf(m0, asv, accm0);
+            accd1 = fmaf(d1 * adv, (float)s1, accd1); accm1 = fmaf(m1, asv, accm1);
+        } else { accd0 += ((float)s0 * d0) * adv; accd1 += ((float)s1 * d1) * adv; }
+    }
+    r0 = warp_sum(accd0) + warp_sum(accm0);
+    r1 = warp_sum(accd1) + warp_sum(accm1);
+}
+
+// Activation staging for the megakernel (Q8_0 / Q8_1 targets), executed by warps 0-7 (256 threads).
+// The F32 input vector is copied L2 -> shared memory with cp.async.cg (no registers held, all chunks in flight, L1
+// bypassed because other CTAs wrote it earlier in this launch); both passes (RMS partial sums, quantisation) then read
+// shared memory, so the routine is register-light and the megakernel has no spills.  Thread t owns the float4s at
+// elements 2048k + 4t and 2048k + 1024 + 4t: its RMS partials are canonical partials t and t + 256 (oracle.cpp
+// op_rms_norm_mul, same as k::stage_act); a 32-weight quant block is covered by 8 consecutive lanes, so amax / sum need 3
+// shuffle steps.  Quantisation is order-free (max, integer sums): identical bytes to k::stage_act.
 constexpr int kStageMaxK = 7;  // up to 14336 columns
-template <int ACT, int STK>
-__device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, const float *__restrict__ nw, int cols, unsigned char *sm, double *red) {
+template <int ACT>
+__device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, const float *__restrict__ nw, int cols, float *xs, unsigned char *sm, double *red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // tid < 256
-    float4 v[STK][2];
-#pragma unroll
-    for (int k = 0; k < STK; ++k)
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) { const int i = 2048 * k + 1024 * hf + 4 * tid; if (i < cols) v[k][hf] = __ldcg((const float4 *)(x + i)); }
+    const int nitem = cols >> 10;  // float4 items per thread (cols is a multiple of 1024? no: of 128 -> tail handled by i < cols)
+    for (int it = 0; it <= nitem; ++it) {
+        const int i = 1024 * it + 4 * tid;
+        if (i < cols) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(xs + i)), "l"(x + i) : "memory");
+            if (nw) asm volatile("prefetch.global.L1 [%0];" ::"l"(nw + i));
+        }
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    // each thread reads back only what it copied itself, so no barrier is needed before the passes below
+    float scale = 1.0f;
     if (nw) {
         double ssa = 0.0, ssb = 0.0;
-#pragma unroll
-        for (int k = 0; k < STK; ++k) {
+        for (int k = 0; 2048 * k < cols; ++k) {
             const int ia = 2048 * k + 4 * tid, ib = ia + 1024;
-            if (ia < cols) { const float4 a = v[k][0]; ssa += (double)(a.x * a.x); ssa += (double)(a.y * a.y); ssa += (double)(a.z * a.z); ssa += (double)(a.w * a.w); }
-            if (ib < cols) { const float4 b = v[k][1]; ssb += (double)(b.x * b.x); ssb += (double)(b.y * b.y); ssb += (double)(b.z * b.z); ssb += (double)(b.w * b.w); }
+            if (ia < cols) { const float4 a = *(const float4 *)(xs + ia); ssa += (double)(a.x * a.x); ssa += (double)(a.y * a.y); ssa += (double)(a.z * a.z); ssa += (double)(a.w * a.w); }
+            if (ib < cols) { const float4 b = *(const float4 *)(xs + ib); ssb += (double)(b.x * b.x); ssb += (double)(b.y * b.y); ssb += (double)(b.z * b.z); ssb += (double)(b.w * b.w); }
         }
         ssa = warp_sum(ssa); ssb = warp_sum(ssb);
         cta_sync<true>();
@@ -110,46 +161,34 @@ __device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, cons
         cta_sync<true>();
         const double tot = red[32];
         const float mean = (float)(tot / (double)cols);
-        const float scale = 1.0f / sqrtf(mean + 1e-6f);
-#pragma unroll
-        for (int k = 0; k < STK; ++k)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int i = 2048 * k + 1024 * hf + 4 * tid;
-                if (i < cols) {
-                    const float4 w4 = *(const float4 *)(nw + i);
-                    float4 &a = v[k][hf];
-                    a.x = (a.x * scale) * w4.x; a.y = (a.y * scale) * w4.y; a.z = (a.z * scale) * w4.z; a.w = (a.w * scale) * w4.w;
-                }
-            }
+        scale = 1.0f / sqrtf(mean + 1e-6f);
     }
     unsigned char *qs = sm; float *d = (float *)(sm + cols); float *s = d + cols / 32;
     const int j8 = tid & 7;
-#pragma unroll
-    for (int k = 0; k < STK; ++k)
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            const int i = 2048 * k + 1024 * hf + 4 * tid;
-            if (i < cols) {  // warp-uniform: cols is a multiple of 128
-                const float4 a = v[k][hf];
-                const int b = 64 * k + 32 * hf + (tid >> 3);
-                float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-                const float dd = amax / 127.f;
-                const float id = amax != 0.0f ? 127.f / amax : 0.0f;
-                const int q0 = __float2int_rn(a.x * id), q1 = __float2int_rn(a.y * id), q2 = __float2int_rn(a.z * id), q3 = __float2int_rn(a.w * id);
-                *(unsigned *)(qs + (j8 < 4 ? 0 : cols / 2) + b * 16 + (j8 & 3) * 4) = (unsigned)(q0 & 0xff) | ((unsigned)(q1 & 0xff) << 8) | ((unsigned)(q2 & 0xff) << 16) | ((unsigned)(q3 & 0xff) << 24);
-                int sum = (q0 + q1) + (q2 + q3);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 4); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                if (j8 == 0) {
-                    if (ACT == ACT_Q8_0) { d[b] = __half2float(__float2half_rn(dd)); s[b] = 0.f; }
-                    else { d[b] = dd; s[b] = dd * (float)sum; }
-                }
+#pragma unroll 2
+    for (int it = 0; it <= nitem; ++it) {
+        const int i = 1024 * it + 4 * tid;
+        if (i < cols) {  // warp-uniform: cols is a multiple of 128
+            float4 a = *(const float4 *)(xs + i);
+            if (nw) { const float4 w4 = *(const float4 *)(nw + i); a = make_float4((a.x * scale) * w4.x, (a.y * scale) * w4.y, (a.z * scale) * w4.z, (a.w * scale) * w4.w); }
+            const int b = i >> 5;
+            float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            const float dd = amax / 127.f;
+            const float id = amax != 0.0f ? 127.f / amax : 0.0f;
+            const int q0 = __float2int_rn(a.x * id), q1 = __float2int_rn(a.y * id), q2 = __float2int_rn(a.z * id), q3 = __float2int_rn(a.w * id);
+            *(unsigned *)(qs + (j8 < 4 ? 0 : cols / 2) + b * 16 + (j8 & 3) * 4) = (unsigned)(q0 & 0xff) | ((unsigned)(q1 & 0xff) << 8) | ((unsigned)(q2 & 0xff) << 16) | ((unsigned)(q3 & 0xff) << 24);
+            int sum = (q0 + q1) + (q2 + q3);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            if (j8 == 0) {
+                if (ACT == ACT_Q8_0) { d[b] = __half2float(__float2half_rn(dd)); s[b] = 0.f; }
+                else { d[b] = dd; s[b] = dd * (float)sum; }
             }
         }
+    }
 }
 
-template <int WT, int STK>
+template <int WT>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ double red[34];
@@ -158,7 +197,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
     __shared__ float part[16 * 128];
     constexpr int ACT = act_of(WT);
     constexpr bool Q41 = WT == GG_Q4_1;
-    unsigned char *ring = smem, *actb = smem + (size_t)P.n_slots * P.slot_bytes;
+    unsigned char *ring = smem, *xsb = smem + (size_t)P.n_slots * P.slot_bytes, *actb = xsb + P.xs_bytes;
     uint64_t *full = (uint64_t *)(actb + P.act_bytes), *empty = full + P.n_slots;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
@@ -208,7 +247,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         if (op.kind == OP_ATTN) {
             if (cta < P.n_head && tid < 256) {  // one head per CTA, 256 threads (named barrier 1)
                 const size_t lo = (size_t)op.layer * P.n_ctx * P.E;
-                attention_head<true>(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, 0, P.E, P.n_ctx, P.kq_scale, P.tab_exp, actb, red, redf, qh, part);
+                attention_head<true>(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, 0, P.E, P.n_ctx, P.kq_scale, P.tab_exp, xsb, red, redf, qh, part);
             }
             continue;
         }
@@ -225,7 +264,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
 
         // ---- matvec ops -------------------------------------------------------------------------------------
         const float *src = op.kind == OP_WO ? P.att : op.kind == OP_DOWN ? P.act : P.x;
-        if (tid < 256) stage_act_mega<ACT, STK>(src, op.norm_w, op.cols, actb, red);
+        if (tid < 256) stage_act_mega<ACT>(src, op.norm_w, op.cols, (float *)xsb, actb, red);
         consumer_sync();
         if (tr) tr[2] = clock64();
         const int nb = op.cols / 32;
@@ -244,9 +283,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
             for (int rp = 0; rp < op.su_rows; rp += 2) {
                 const int r0 = su * op.su_rows + rp;
                 if (r0 >= op.rows) break;
-                float res[2][1];
-                dot2_q4<1, true>(slot + (size_t)rp * op.row_bytes, slot + (size_t)(rp + 1) * op.row_bytes, nb, op.cols, Q41, actb, 0, lane, res);
-                const float v0 = res[0][0], v1 = res[1][0];
+                float v0, v1;
+                dot2_q4_slot<Q41>(slot + (size_t)rp * op.row_bytes, slot + (size_t)(rp + 1) * op.row_bytes, nb, op.cols, actb, lane, v0, v1);
                 if (lane == 0) switch (op.kind) {
                     case OP_QKV: {
                         const int E = P.E, partn = r0 / E, rr = r0 % E;

@@ -257,17 +257,30 @@ Error VisionDevice::load(const VisionFile &f) {
     return ErrNone;
 }
 
-static size_t attn_smem(int nk, int dh) { return ((size_t)nk * (dh + 1) + (size_t)nk * dh + 8 * dh + 8 * (size_t)((nk + 31) & ~31)) * 4; }
+static size_t attn_smem(int nk, int dh) { return ((size_t)nk * (dh + 4) + (size_t)nk * dh + 16 * dh + 16 * (size_t)((nk + 31) & ~31)) * 4; }
+static void launch_attention(int dh, dim3 grid, cudaStream_t s, const float *q, int ldq, const float *k, const float *v, int ldkv, int nq, int nk, float div, int qpc,
+                             __half *out, int ld_out, const __half *tab) {
+    static bool cfg = false;
+    if (!cfg) {
+        CUDA_CHECK(cudaFuncSetAttribute(attention_f32_kernel<88>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(attention_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        cfg = true;
+    }
+    if (nk > 288) MG4_PANIC("attention: at most 288 keys (got %d)", nk);
+    const size_t sm = attn_smem(nk, dh);
+    if (dh == 88) attention_f32_kernel<88><<<grid, 256, sm, s>>>(q, ldq, k, v, ldkv, nq, nk, div, qpc, out, ld_out, tab);
+    else if (dh == 64) attention_f32_kernel<64><<<grid, 256, sm, s>>>(q, ldq, k, v, ldkv, nq, nk, div, qpc, out, ld_out, tab);
+    else MG4_PANIC("attention: head_dim %d not instantiated", dh);
+    CUDA_CHECK(cudaGetLastError());
+}
 
 void VisionDevice::record() {
     const int D = d_.D, T = d_.T, QH = 768, NQ = 32;
     cudaStream_t s = stream_;
     auto ln = [&](const float *x, int rows, int n, const float *w, const float *b, __half *o16, float *o32) {
-        layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, rows, n, w, b, o16, o32, nullptr); ++launches_;
+        layernorm_kernel<<<(rows + 1) / 2, 64, 0, s>>>(x, rows, n, w, b, o16, o32, nullptr); ++launches_;
     };
     auto gemm = [&](GemmPlan *p) { launch_plan(p, s); ++launches_; };
-    static bool attn_cfg = false;
-    if (!attn_cfg) { CUDA_CHECK(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attn_cfg = true; }
 
     im2col_patch_kernel<<<256, 128, 0, s>>>(img_, patches_, 640); ++launches_;
     gemm(patch_);
@@ -276,8 +289,7 @@ void VisionDevice::record() {
     for (Block &b : blocks_) {
         ln(x_, T, D, b.n1w, b.n1b, ln16_, nullptr);
         gemm(b.qkv);
-        attention_f32_kernel<<<dim3((unsigned)d_.H, (unsigned)((T + qpc - 1) / qpc)), 256, attn_smem(T, d_.dh), s>>>(qkv_, 3 * D, qkv_ + D, qkv_ + 2 * D, 3 * D, T, T, d_.dh, 1.0f, qpc,
-                                                                                                                  ctx16_, D, tab_exp_); ++launches_;
+        launch_attention(d_.dh, dim3((unsigned)d_.H, (unsigned)((T + qpc - 1) / qpc)), s, qkv_, 3 * D, qkv_ + D, qkv_ + 2 * D, 3 * D, T, T, 1.0f, qpc, ctx16_, D, tab_exp_); ++launches_;
         gemm(b.proj);
         ln(x_, T, D, b.n2w, b.n2b, ln16_, nullptr);
         gemm(b.fc1);
@@ -287,13 +299,13 @@ void VisionDevice::record() {
     ln(qtok_, NQ, QH, qln_w_, qln_b_, hs16_, hs_);
     for (QLayer &L : qlayers_) {
         gemm(L.sa_qkv);
-        attention_f32_kernel<<<dim3(12, 1), 256, attn_smem(NQ, 64), s>>>(qqkv_, 3 * QH, qqkv_ + QH, qqkv_ + 2 * QH, 3 * QH, NQ, NQ, 64, 8.0f, NQ, qctx16_, QH, tab_exp_); ++launches_;
+        launch_attention(64, dim3(12, 1), s, qqkv_, 3 * QH, qqkv_ + QH, qqkv_ + 2 * QH, 3 * QH, NQ, NQ, 8.0f, NQ, qctx16_, QH, tab_exp_); ++launches_;
         gemm(L.sa_o);
         ln(qtmp_, NQ, QH, L.sa_ln_w, L.sa_ln_b, qa16_, qa_);
         if (L.cross) {
             gemm(L.ca_q);
             gemm(L.ca_kv);
-            attention_f32_kernel<<<dim3(12, 4), 256, attn_smem(T, 64), s>>>(qq_, QH, qkv_cross_, qkv_cross_ + QH, 2 * QH, NQ, T, 64, 8.0f, 8, qctx16_, QH, tab_exp_); ++launches_;
+            launch_attention(64, dim3(12, 2), s, qq_, QH, qkv_cross_, qkv_cross_ + QH, 2 * QH, NQ, T, 8.0f, 16, qctx16_, QH, tab_exp_); ++launches_;
             gemm(L.ca_o);
             ln(qtmp_, NQ, QH, L.ca_ln_w, L.ca_ln_b, qc16_, qc_);
         }
@@ -351,7 +363,7 @@ void VisionDevice::test_layernorm(const float *x, int rows, int n, const float *
     CUDA_CHECK(cudaMalloc((void **)&X, (size_t)rows * n * 4)); CUDA_CHECK(cudaMalloc((void **)&O, (size_t)rows * n * 4));
     CUDA_CHECK(cudaMalloc((void **)&W, (size_t)n * 4)); CUDA_CHECK(cudaMalloc((void **)&B, (size_t)n * 4));
     CUDA_CHECK(cudaMemcpy(X, x, (size_t)rows * n * 4, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(W, w, (size_t)n * 4, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(B, b, (size_t)n * 4, cudaMemcpyHostToDevice));
-    layernorm_kernel<<<(rows + 7) / 8, 256>>>(X, rows, n, W, B, nullptr, O, nullptr);
+    layernorm_kernel<<<(rows + 1) / 2, 64>>>(X, rows, n, W, B, nullptr, O, nullptr);
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy(out, O, (size_t)rows * n * 4, cudaMemcpyDeviceToHost));
     cudaFree(X); cudaFree(W); cudaFree(B); cudaFree(O);
@@ -362,9 +374,8 @@ void VisionDevice::test_attention(const float *q, const float *k, const float *v
     CUDA_CHECK(cudaMalloc((void **)&Q, (size_t)nq * ld * 4)); CUDA_CHECK(cudaMalloc((void **)&K, (size_t)nk * ld * 4)); CUDA_CHECK(cudaMalloc((void **)&V, (size_t)nk * ld * 4));
     CUDA_CHECK(cudaMalloc((void **)&O, (size_t)nq * ld * 2));
     CUDA_CHECK(cudaMemcpy(Q, q, (size_t)nq * ld * 4, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(K, k, (size_t)nk * ld * 4, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(V, v, (size_t)nk * ld * 4, cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     const int qpc = (nq + 3) / 4;
-    attention_f32_kernel<<<dim3((unsigned)heads, (unsigned)((nq + qpc - 1) / qpc)), 256, attn_smem(nk, dh)>>>(Q, ld, K, V, ld, nq, nk, dh, div, qpc, O, ld, tab);
+    launch_attention(dh, dim3((unsigned)heads, (unsigned)((nq + qpc - 1) / qpc)), 0, Q, ld, K, V, ld, nq, nk, div, qpc, O, ld, tab);
     CUDA_CHECK(cudaDeviceSynchronize());
     std::vector<__half> h((size_t)nq * ld); CUDA_CHECK(cudaMemcpy(h.data(), O, h.size() * 2, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < h.size(); ++i) out[i] = __half2float(h[i]);

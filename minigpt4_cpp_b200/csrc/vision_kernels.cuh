@@ -146,17 +146,34 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05(const __grid_constant
         for (int c0 = 0; c0 < g.t_pad; c0 += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            // No early exit inside the 16-token batch: every load of the batch (residual / positional embedding) is issued
+            // before its first use, so the epilogue pays one L2 round trip per batch instead of one per token.
+            float aux[16];
+            if (g.epi == GE_RESID || g.epi == GE_PATCH) {
+                const float *src = g.epi == GE_RESID ? g.resid : g.pos;
+                const int off = g.epi == GE_PATCH ? 1 : 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const int t = c0 + j; aux[j] = t < g.T ? src[(size_t)(t + off) * g.ld_out + m] : 0.f; }
+            }
+            if (g.epi == GE_GELU_F16) {
+                __half hv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hv[j] = g.tab_gelu[__half_as_ushort(__float2half_rn(bias + v[j]))];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const int t = c0 + j; if (t < g.T) g.out_f16[(size_t)t * g.ld_out + m] = hv[j]; }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int t = c0 + j;
-                if (t >= g.T) break;
-                float r = bias + v[j];
-                switch (g.epi) {
-                    case GE_QSCALE: r *= qs; g.out_f32[(size_t)t * g.ld_out + m] = r; break;
-                    case GE_GELU_F16: g.out_f16[(size_t)t * g.ld_out + m] = g.tab_gelu[__half_as_ushort(__float2half_rn(r))]; break;
-                    case GE_RESID: { const size_t o = (size_t)t * g.ld_out + m; g.out_f32[o] = g.resid[o] + r; } break;
-                    case GE_PATCH: { const size_t o = (size_t)(t + 1) * g.ld_out + m; g.out_f32[o] = (0.0f + r) + g.pos[o]; } break;
-                    default: g.out_f32[(size_t)t * g.ld_out + m] = r; if (g.out_f16) g.out_f16[(size_t)t * g.ld_out + m] = __float2half_rn(r); break;
+                if (t < g.T) {
+                    float r = bias + v[j];
+                    switch (g.epi) {
+                        case GE_QSCALE: r *= qs; g.out_f32[(size_t)t * g.ld_out + m] = r; break;
+                        case GE_RESID: g.out_f32[(size_t)t * g.ld_out + m] = aux[j] + r; break;
+                        case GE_PATCH: g.out_f32[(size_t)(t + 1) * g.ld_out + m] = (0.0f + r) + aux[j]; break;
+                        default: g.out_f32[(size_t)t * g.ld_out + m] = r; if (g.out_f16) g.out_f16[(size_t)t * g.ld_out + m] = __float2half_rn(r); break;
+                    }
                 }
             }
         }
@@ -186,66 +203,115 @@ __global__ void layernorm_kernel(const float *__restrict__ x, int rows, int n, c
     if (row >= rows) return;
     const float *xr = x + (size_t)row * n;
     const float *ar = add_in ? add_in + (size_t)row * n : nullptr;
+    constexpr int MAXE = 48;  // n <= 1536: the row lives in registers, one global pass
+    float v[MAXE];
+#pragma unroll
+    for (int k = 0; k < MAXE; ++k) { const int i = lane + 32 * k; if (i < n) v[k] = ar ? xr[i] + ar[i] : xr[i]; }
     double s = 0.0;
-    for (int i = lane; i < n; i += 32) s += (double)(ar ? xr[i] + ar[i] : xr[i]);
+#pragma unroll
+    for (int k = 0; k < MAXE; ++k) if (lane + 32 * k < n) s += (double)v[k];
     s = warp_sum_d(s);
     const float mean = (float)(s / (double)n);
     double s2 = 0.0;
-    for (int i = lane; i < n; i += 32) { const float v = (ar ? xr[i] + ar[i] : xr[i]) - mean; s2 += (double)(v * v); }
+#pragma unroll
+    for (int k = 0; k < MAXE; ++k) if (lane + 32 * k < n) { v[k] = v[k] - mean; s2 += (double)(v[k] * v[k]); }
     s2 = warp_sum_d(s2);
     const float variance = (float)(s2 / (double)n);
     const float scale = 1.0f / sqrtf(variance + 1e-5f);
-    for (int i = lane; i < n; i += 32) {
-        const float v = ((ar ? xr[i] + ar[i] : xr[i]) - mean) * scale;
-        float y = w[i] * v;
-        if (b) y = y + b[i];
-        if (out16) out16[(size_t)row * n + i] = __float2half_rn(y);
-        if (out32) out32[(size_t)row * n + i] = y;
+#pragma unroll
+    for (int k = 0; k < MAXE; ++k) {
+        const int i = lane + 32 * k;
+        if (i < n) {
+            float y = w[i] * (v[k] * scale);
+            if (b) y = y + b[i];
+            if (out16) out16[(size_t)row * n + i] = __float2half_rn(y);
+            if (out32) out32[(size_t)row * n + i] = y;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // F32 multi-head attention (ViT MHSA and Q-Former self/cross attention; ggml F32xF32 mul_mat + soft_max with fp16 exp LUT)
-// q: [nq][ldq] (+ head*dh), k,v: [nk][ldkv] (+ head*dh).  grid (heads, ceil(nq / q_per_cta)), block 256.
-// shared: K [nk][dh+1], V [nk][dh], per-warp q [dh] and p [nk_pad]
-// out: F16 [nq][ld_out] (operand of the following projection GEMM)
+// q: [nq][ldq] (+ head*DH), k,v: [nk][ldkv] (+ head*DH).  grid (heads, ceil(nq / q_per_cta)), block 256.
+// K ([nk][DH+4], float4 rows, odd float4 pitch -> conflict-free 128-bit reads) and V ([nk][DH]) of the head live in shared
+// memory; each warp processes TWO queries at a time so every K/V shared-memory read feeds two FMAs (the kernel is
+// shared-memory-bandwidth bound).  out: F16 [nq][ld_out] (operand of the following projection GEMM).
 // ---------------------------------------------------------------------------------------------
+template <int DH>
 __global__ void __launch_bounds__(256) attention_f32_kernel(const float *__restrict__ q, int ldq, const float *__restrict__ k, const float *__restrict__ v, int ldkv,
-                                                            int nq, int nk, int dh, float score_div, int q_per_cta, __half *__restrict__ out, int ld_out,
+                                                            int nq, int nk, float score_div, int q_per_cta, __half *__restrict__ out, int ld_out,
                                                             const __half *__restrict__ tab_exp) {
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int DH4 = DH / 4, KP = DH + 4, NKI = 9;  // nk <= 288
     const int nk_pad = (nk + 31) & ~31;
-    float *Ks = (float *)smem; float *Vs = Ks + (size_t)nk * (dh + 1); float *Qs = Vs + (size_t)nk * dh; float *Ps = Qs + 8 * dh;
+    float *Ks = (float *)smem; float *Vs = Ks + (size_t)nk * KP; float *Qs = Vs + (size_t)nk * DH; float *Ps = Qs + 8 * 2 * DH;
     const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < nk * dh; i += blockDim.x) {
-        const int t = i / dh, d = i % dh;
-        Ks[(size_t)t * (dh + 1) + d] = k[(size_t)t * ldkv + h * dh + d];
-        Vs[(size_t)t * dh + d] = v[(size_t)t * ldkv + h * dh + d];
+    for (int t = warp; t < nk; t += 8) {
+        if (lane < DH4) {
+            *(float4 *)(Ks + (size_t)t * KP + lane * 4) = *(const float4 *)(k + (size_t)t * ldkv + h * DH + lane * 4);
+            *(float4 *)(Vs + (size_t)t * DH + lane * 4) = *(const float4 *)(v + (size_t)t * ldkv + h * DH + lane * 4);
+        }
     }
     __syncthreads();
     const int q0 = blockIdx.y * q_per_cta, q1 = min(nq, q0 + q_per_cta);
-    float *qw = Qs + warp * dh, *pw = Ps + (size_t)warp * nk_pad;
-    for (int tq = q0 + warp; tq < q1; tq += 8) {
-        for (int d = lane; d < dh; d += 32) qw[d] = q[(size_t)tq * ldq + h * dh + d];
-        __syncwarp();
-        float mx = -INFINITY;
-        for (int j = lane; j < nk; j += 32) {
-            const float *kr = Ks + (size_t)j * (dh + 1);
-            float s = 0.f;
-            for (int d = 0; d < dh; ++d) s = fmaf(kr[d], qw[d], s);
-            s = s / score_div;
-            pw[j] = s; mx = fmaxf(mx, s);
+    float *qw = Qs + warp * 2 * DH, *pw = Ps + (size_t)warp * 2 * nk_pad;
+    for (int tq = q0 + 2 * warp; tq < q1; tq += 16) {
+        const bool two = tq + 1 < q1;
+        if (lane < DH4) {
+            *(float4 *)(qw + lane * 4) = *(const float4 *)(q + (size_t)tq * ldq + h * DH + lane * 4);
+            *(float4 *)(qw + DH + lane * 4) = two ? *(const float4 *)(q + (size_t)(tq + 1) * ldq + h * DH + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        mx = warp_max_f(mx);
-        double sum = 0.0;
-        for (int j = lane; j < nk; j += 32) { const float e = __half2float(tab_exp[__half_as_ushort(__float2half_rn(pw[j] - mx))]); pw[j] = e; sum += (double)e; }
-        sum = warp_sum_d(sum);
-        const float inv = (float)(1.0 / sum);
         __syncwarp();
-        for (int d = lane; d < dh; d += 32) {
-            float acc = 0.f;
-            for (int j = 0; j < nk; ++j) acc = fmaf(Vs[(size_t)j * dh + d], pw[j] * inv, acc);
-            out[(size_t)tq * ld_out + h * dh + d] = __float2half_rn(acc);
+        float sa[NKI], sb[NKI];
+#pragma unroll
+        for (int i = 0; i < NKI; ++i) { sa[i] = 0.f; sb[i] = 0.f; }
+        for (int c = 0; c < DH4; ++c) {
+            const float4 qa = *(const float4 *)(qw + c * 4), qb = *(const float4 *)(qw + DH + c * 4);
+#pragma unroll
+            for (int i = 0; i < NKI; ++i) {
+                const int j = lane + 32 * i;
+                if (j < nk) {
+                    const float4 kk = *(const float4 *)(Ks + (size_t)j * KP + c * 4);
+                    sa[i] = fmaf(kk.x, qa.x, sa[i]); sa[i] = fmaf(kk.y, qa.y, sa[i]); sa[i] = fmaf(kk.z, qa.z, sa[i]); sa[i] = fmaf(kk.w, qa.w, sa[i]);
+                    sb[i] = fmaf(kk.x, qb.x, sb[i]); sb[i] = fmaf(kk.y, qb.y, sb[i]); sb[i] = fmaf(kk.z, qb.z, sb[i]); sb[i] = fmaf(kk.w, qb.w, sb[i]);
+                }
+            }
+        }
+        float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NKI; ++i) if (lane + 32 * i < nk) { sa[i] = sa[i] / score_div; sb[i] = sb[i] / score_div; mxa = fmaxf(mxa, sa[i]); mxb = fmaxf(mxb, sb[i]); }
+        mxa = warp_max_f(mxa); mxb = warp_max_f(mxb);
+        double suma = 0.0, sumb = 0.0;
+#pragma unroll
+        for (int i = 0; i < NKI; ++i) if (lane + 32 * i < nk) {
+            sa[i] = __half2float(tab_exp[__half_as_ushort(__float2half_rn(sa[i] - mxa))]); suma += (double)sa[i];
+            sb[i] = __half2float(tab_exp[__half_as_ushort(__float2half_rn(sb[i] - mxb))]); sumb += (double)sb[i];
+        }
+        suma = warp_sum_d(suma); sumb = warp_sum_d(sumb);
+        const float inva = (float)(1.0 / suma), invb = (float)(1.0 / sumb);
+#pragma unroll
+        for (int i = 0; i < NKI; ++i) { const int j = lane + 32 * i; if (j < nk_pad) { pw[j] = j < nk ? sa[i] * inva : 0.f; pw[nk_pad + j] = j < nk ? sb[i] * invb : 0.f; } }
+        __syncwarp();
+        float oa[3] = {0.f, 0.f, 0.f}, ob[3] = {0.f, 0.f, 0.f};
+        for (int j4 = 0; j4 < nk_pad; j4 += 4) {
+            const float4 pa = *(const float4 *)(pw + j4), pb = *(const float4 *)(pw + nk_pad + j4);
+            const float pav[4] = {pa.x, pa.y, pa.z, pa.w}, pbv[4] = {pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j4 + u;
+                if (j < nk) {
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        const int d = lane + 32 * e;
+                        if (d < DH) { const float vv = Vs[(size_t)j * DH + d]; oa[e] = fmaf(vv, pav[u], oa[e]); ob[e] = fmaf(vv, pbv[u], ob[e]); }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int d = lane + 32 * e;
+            if (d < DH) { out[(size_t)tq * ld_out + h * DH + d] = __float2half_rn(oa[e]); if (two) out[(size_t)(tq + 1) * ld_out + h * DH + d] = __float2half_rn(ob[e]); }
         }
         __syncwarp();
     }
