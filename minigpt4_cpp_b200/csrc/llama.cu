@@ -388,7 +388,7 @@ bool LlamaDevice::build_mega() {
     const int act = act_of(wt);
     size_t act_b = std::max(act_bytes(act, FF), act_bytes(act, E));
     act_b = (act_b + 127) & ~(size_t)127;
-    size_t xs_b = std::max((size_t)std::max(E, FF) * 4, (size_t)d_.n_ctx * 6);  // F32 input vector / attention scratch
+    size_t xs_b = std::max((size_t)E * 4, (size_t)d_.n_ctx * 6);  // F32 copy of the RMS-normed input (n_embd wide) / attention scratch
     xs_b = (xs_b + 127) & ~(size_t)127;
     const int rb_e = layers_[0].qkv.row_bytes, rb_ff = layers_[0].w2.row_bytes;
     int slot = std::max(2 * rb_e, 2 * rb_ff);

@@ -132,6 +132,42 @@ __device__ __forceinline__ void dot2_q4_slot(const unsigned char *row0, const un
 // op_rms_norm_mul, same as k::stage_act); a 32-weight quant block is covered by 8 consecutive lanes, so amax / sum need 3
 // shuffle steps.  Quantisation is order-free (max, integer sums): identical bytes to k::stage_act.
 constexpr int kStageMaxK = 7;  // up to 14336 columns
+// quantise the float4 at elements i..i+3 (8 consecutive lanes cover one 32-weight block) into the split-plane Q8 layout
+template <int ACT>
+__device__ __forceinline__ void quant_item(const float4 a, int i, int cols, unsigned char *sm) {
+    unsigned char *qs = sm; float *d = (float *)(sm + cols); float *s = d + cols / 32;
+    const int j8 = threadIdx.x & 7, b = i >> 5;
+    float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    const float dd = amax / 127.f;
+    const float id = amax != 0.0f ? 127.f / amax : 0.0f;
+    const int q0 = __float2int_rn(a.x * id), q1 = __float2int_rn(a.y * id), q2 = __float2int_rn(a.z * id), q3 = __float2int_rn(a.w * id);
+    *(unsigned *)(qs + (j8 < 4 ? 0 : cols / 2) + b * 16 + (j8 & 3) * 4) = (unsigned)(q0 & 0xff) | ((unsigned)(q1 & 0xff) << 8) | ((unsigned)(q2 & 0xff) << 16) | ((unsigned)(q3 & 0xff) << 24);
+    int sum = (q0 + q1) + (q2 + q3);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    if (j8 == 0) {
+        if (ACT == ACT_Q8_0) { d[b] = __half2float(__float2half_rn(dd)); s[b] = 0.f; }
+        else { d[b] = dd; s[b] = dd * (float)sum; }
+    }
+}
+// un-normed inputs (wo, down): the vector streams L2 -> shared window `xs` (xs_items float4 per thread, cp.async.cg) ->
+// quantiser, window by window; nothing is kept in registers.
+template <int ACT>
+__device__ __forceinline__ void stage_plain_mega(const float *__restrict__ x, int cols, float *xs, int xs_items, unsigned char *sm) {
+    const int tid = threadIdx.x;  // tid < 256
+    for (int it0 = 0; 1024 * it0 < cols; it0 += xs_items) {
+        for (int u = 0; u < xs_items; ++u) {
+            const int i = 1024 * (it0 + u) + 4 * tid;
+            if (i < cols) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(xs + 1024 * u + 4 * tid)), "l"(x + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#pragma unroll 1
+        for (int u = 0; u < xs_items; ++u) {
+            const int i = 1024 * (it0 + u) + 4 * tid;
+            if (i < cols) quant_item<ACT>(*(const float4 *)(xs + 1024 * u + 4 * tid), i, cols, sm);  // warp-uniform predicate; own copy only
+        }
+    }
+}
 template <int ACT>
 __device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, const float *__restrict__ nw, int cols, float *xs, unsigned char *sm, double *red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // tid < 256
@@ -163,29 +199,21 @@ __device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, cons
         const float mean = (float)(tot / (double)cols);
         scale = 1.0f / sqrtf(mean + 1e-6f);
     }
-    unsigned char *qs = sm; float *d = (float *)(sm + cols); float *s = d + cols / 32;
-    const int j8 = tid & 7;
 #pragma unroll 2
     for (int it = 0; it <= nitem; ++it) {
         const int i = 1024 * it + 4 * tid;
         if (i < cols) {  // warp-uniform: cols is a multiple of 128
             float4 a = *(const float4 *)(xs + i);
             if (nw) { const float4 w4 = *(const float4 *)(nw + i); a = make_float4((a.x * scale) * w4.x, (a.y * scale) * w4.y, (a.z * scale) * w4.z, (a.w * scale) * w4.w); }
-            const int b = i >> 5;
-            float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            const float dd = amax / 127.f;
-            const float id = amax != 0.0f ? 127.f / amax : 0.0f;
-            const int q0 = __float2int_rn(a.x * id), q1 = __float2int_rn(a.y * id), q2 = __float2int_rn(a.z * id), q3 = __float2int_rn(a.w * id);
-            *(unsigned *)(qs + (j8 < 4 ? 0 : cols / 2) + b * 16 + (j8 & 3) * 4) = (unsigned)(q0 & 0xff) | ((unsigned)(q1 & 0xff) << 8) | ((unsigned)(q2 & 0xff) << 16) | ((unsigned)(q3 & 0xff) << 24);
-            int sum = (q0 + q1) + (q2 + q3);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 4); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            if (j8 == 0) {
-                if (ACT == ACT_Q8_0) { d[b] = __half2float(__float2half_rn(dd)); s[b] = 0.f; }
-                else { d[b] = dd; s[b] = dd * (float)sum; }
-            }
+            quant_item<ACT>(a, i, cols, sm);
         }
     }
+}
+
+// out-of-line so that the attention code gets its own register allocation (it runs on n_head CTAs only)
+__device__ __noinline__ void attention_mega(const float *q, const __half *kc, const __half *vc, float *out, int pos, int h, int E, int n_ctx, float kq_scale,
+                                            const __half *tab_exp, unsigned char *dyn, double *red, float *redf, __half *qh, float *part) {
+    attention_head<true>(q, kc, vc, out, pos, h, 0, E, n_ctx, kq_scale, tab_exp, dyn, red, redf, qh, part);
 }
 
 template <int WT>
@@ -247,7 +275,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         if (op.kind == OP_ATTN) {
             if (cta < P.n_head && tid < 256) {  // one head per CTA, 256 threads (named barrier 1)
                 const size_t lo = (size_t)op.layer * P.n_ctx * P.E;
-                attention_head<true>(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, 0, P.E, P.n_ctx, P.kq_scale, P.tab_exp, xsb, red, redf, qh, part);
+                attention_mega(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, P.E, P.n_ctx, P.kq_scale, P.tab_exp, xsb, red, redf, qh, part);
             }
             continue;
         }
@@ -264,13 +292,19 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
 
         // ---- matvec ops -------------------------------------------------------------------------------------
         const float *src = op.kind == OP_WO ? P.att : op.kind == OP_DOWN ? P.act : P.x;
-        if (tid < 256) stage_act_mega<ACT>(src, op.norm_w, op.cols, (float *)xsb, actb, red);
+        if (tid < 256) {
+            if (op.norm_w) stage_act_mega<ACT>(src, op.norm_w, op.cols, (float *)xsb, actb, red);
+            else stage_plain_mega<ACT>(src, op.cols, (float *)xsb, P.xs_bytes >> 12, actb);
+        }
         consumer_sync();
         if (tr) tr[2] = clock64();
         const int nb = op.cols / 32;
         const int lo = (int)((long long)cta * op.n_su / G), hi = (int)((long long)(cta + 1) * op.n_su / G);
         unsigned long long best = 0ull;
-        for (int su = lo + warp; su < hi; su += kConsumerWarps) {
+        // W = min(15, n_slots) warps consume.  With W <= n_slots a warp can never wait on a slot that is two fills behind:
+        // it consumed slot n - W itself, so fill n - n_slots (<= n - W) has happened and the mbarrier parity is unambiguous.
+        const int W = min(kConsumerWarps, P.n_slots);
+        for (int su = lo + warp; warp < W && su < hi; su += W) {
             const unsigned n = n_base + (unsigned)(su - lo);
             const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
             float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};  // residual rows of this slot, fetched before the wait
