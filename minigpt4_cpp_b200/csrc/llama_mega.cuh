@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         const float *src = op.kind == OP_WO ? P.att : op.kind == OP_DOWN ? P.act : P.x;
         if (tid < 256) {
             if (op.norm_w) stage_act_mega<ACT>(src, op.norm_w, op.cols, (float *)xsb, actb, red);
-            else stage_plain_mega<ACT>(src, op.cols, (float *)xsb, P.xs_bytes >> 12, actb);
+            else stage_plain_mega<ACT>(src, op.cols, (float *)xsb, max(1, P.xs_bytes >> 12), actb);
         }
         consumer_sync();
         if (tr) tr[2] = clock64();
