@@ -529,20 +529,28 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
     float *sc = (float *)dyn; __half *ph = (__half *)(dyn + (size_t)n_ctx * 4);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nkv = pos + 1;
-    if (tid < 128) qh[tid] = __float2half_rn(ld_act<MEGA>(q + (size_t)t * E + h * 128 + tid));
-    cta_sync<MEGA>();
-    // scores: each half-warp takes one key (16 lanes x 8 halves = 128)
+    // scores: each half-warp takes one key (16 lanes x 8 halves = 128).  Every lane fetches its own 8 q values together with
+    // its first batch of K rows (one memory round trip instead of two); q is rounded to F16 as ggml does.
     {
         const int sub = lane >> 4, l16 = lane & 15;
-        const uint4 qv = *(const uint4 *)(qh + l16 * 8);
-        const __half2 *q2 = (const __half2 *)&qv;
         constexpr int B = 8;  // keys in flight per half-warp: all loads of a batch are issued before the first use
-        for (int kb0 = warp * 2; kb0 < nkv; kb0 += 16 * B) {  // warp-uniform trip counts (both half-warps shuffle together)
+        __half2 q2[4];
+        bool have_q = false;
+        for (int kb0 = warp * 2; kb0 < nkv || !have_q; kb0 += 16 * B) {  // warp-uniform trip counts (both half-warps shuffle together)
             uint4 kv[B];
 #pragma unroll
             for (int u = 0; u < B; ++u) {
                 const int key = kb0 + u * 16 + sub;
                 if (key < nkv) kv[u] = ld_kv16<MEGA>(kc + (size_t)key * E + h * 128 + l16 * 8);
+            }
+            if (!have_q) {
+                const float *qp = q + (size_t)t * E + h * 128 + l16 * 8;
+                float qf[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) qf[e] = ld_act<MEGA>(qp + e);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) q2[j] = __floats2half2_rn(qf[2 * j], qf[2 * j + 1]);
+                have_q = true;
             }
 #pragma unroll
             for (int u = 0; u < B; ++u) {

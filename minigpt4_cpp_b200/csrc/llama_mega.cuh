@@ -68,14 +68,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 // all consumer threads of all CTAs; `target` = number of arrivals that complete this barrier (monotonic counter)
 __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
-    __threadfence();
-    consumer_sync();
+    consumer_sync();  // all consumer warps of this CTA have issued their global writes (CTA-scope ordering)
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        __threadfence();  // cumulative: publishes the CTA's writes at gpu scope before the arrival below
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         unsigned v;
         do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
-        __threadfence();
     }
     consumer_sync();
 }
@@ -150,36 +148,51 @@ __device__ __forceinline__ void quant_item(const float4 a, int i, int cols, unsi
         else { d[b] = dd; s[b] = dd * (float)sum; }
     }
 }
-// un-normed inputs (wo, down): the vector streams L2 -> shared window `xs` (xs_items float4 per thread, cp.async.cg) ->
-// quantiser, window by window; nothing is kept in registers.
+// un-normed inputs (wo, down): the vector streams L2 -> shared window `xs` -> quantiser.  The window is split into two
+// halves of `half_items` float4 per thread, filled by alternating cp.async groups, so copy latency is paid once.
 template <int ACT>
-__device__ __forceinline__ void stage_plain_mega(const float *__restrict__ x, int cols, float *xs, int xs_items, unsigned char *sm) {
+__device__ __forceinline__ void stage_plain_mega(const float *__restrict__ x, int cols, float *xs, int half_items, unsigned char *sm) {
     const int tid = threadIdx.x;  // tid < 256
-    for (int it0 = 0; 1024 * it0 < cols; it0 += xs_items) {
-        for (int u = 0; u < xs_items; ++u) {
-            const int i = 1024 * (it0 + u) + 4 * tid;
-            if (i < cols) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(xs + 1024 * u + 4 * tid)), "l"(x + i) : "memory");
+    const int n_items = (cols + 1023) >> 10, n_groups = (n_items + half_items - 1) / half_items;
+    auto issue = [&](int g) {
+        if (g < n_groups) {
+            float *dst = xs + (g & 1) * half_items * 1024;
+            for (int u = 0; u < half_items; ++u) {
+                const int i = 1024 * (g * half_items + u) + 4 * tid;
+                if (i < cols) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + 1024 * u + 4 * tid)), "l"(x + i) : "memory");
+            }
         }
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");  // (possibly empty) group keeps the wait_group accounting uniform
+    };
+    issue(0); issue(1);
+    for (int g = 0; g < n_groups; ++g) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // group g has landed (each thread reads only its own copies)
+        const float *src = xs + (g & 1) * half_items * 1024;
 #pragma unroll 1
-        for (int u = 0; u < xs_items; ++u) {
-            const int i = 1024 * (it0 + u) + 4 * tid;
-            if (i < cols) quant_item<ACT>(*(const float4 *)(xs + 1024 * u + 4 * tid), i, cols, sm);  // warp-uniform predicate; own copy only
+        for (int u = 0; u < half_items; ++u) {
+            const int i = 1024 * (g * half_items + u) + 4 * tid;
+            if (i < cols) quant_item<ACT>(*(const float4 *)(src + 1024 * u + 4 * tid), i, cols, sm);  // warp-uniform predicate
         }
+        issue(g + 2);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 template <int ACT>
 __device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, const float *__restrict__ nw, int cols, float *xs, unsigned char *sm, double *red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // tid < 256
-    const int nitem = cols >> 10;  // float4 items per thread (cols is a multiple of 1024? no: of 128 -> tail handled by i < cols)
+    const int nitem = cols >> 10;  // float4 items per thread (tail handled by i < cols); this routine serves cols = n_embd <= 5120
     for (int it = 0; it <= nitem; ++it) {
         const int i = 1024 * it + 4 * tid;
         if (i < cols) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(xs + i)), "l"(x + i) : "memory");
-            if (nw) asm volatile("prefetch.global.L1 [%0];" ::"l"(nw + i));
         }
     }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // norm weights (constant data): issued now, consumed after the block reduction; n_embd <= 5120 -> at most 5 float4
+    float4 w4[5];
+#pragma unroll
+    for (int it = 0; it < 5; ++it) { const int i = 1024 * it + 4 * tid; if (nw && i < cols) w4[it] = __ldg((const float4 *)(nw + i)); }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // each thread reads back only what it copied itself, so no barrier is needed before the passes below
     float scale = 1.0f;
     if (nw) {
@@ -199,12 +212,12 @@ __device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, cons
         const float mean = (float)(tot / (double)cols);
         scale = 1.0f / sqrtf(mean + 1e-6f);
     }
-#pragma unroll 2
-    for (int it = 0; it <= nitem; ++it) {
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
         const int i = 1024 * it + 4 * tid;
         if (i < cols) {  // warp-uniform: cols is a multiple of 128
             float4 a = *(const float4 *)(xs + i);
-            if (nw) { const float4 w4 = *(const float4 *)(nw + i); a = make_float4((a.x * scale) * w4.x, (a.y * scale) * w4.y, (a.z * scale) * w4.z, (a.w * scale) * w4.w); }
+            if (nw) a = make_float4((a.x * scale) * w4[it].x, (a.y * scale) * w4[it].y, (a.z * scale) * w4[it].z, (a.w * scale) * w4[it].w);
             quant_item<ACT>(a, i, cols, sm);
         }
     }
@@ -294,7 +307,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         const float *src = op.kind == OP_WO ? P.att : op.kind == OP_DOWN ? P.act : P.x;
         if (tid < 256) {
             if (op.norm_w) stage_act_mega<ACT>(src, op.norm_w, op.cols, (float *)xsb, actb, red);
-            else stage_plain_mega<ACT>(src, op.cols, (float *)xsb, max(1, P.xs_bytes >> 12), actb);
+            else stage_plain_mega<ACT>(src, op.cols, (float *)xsb, max(1, P.xs_bytes >> 13), actb);
         }
         consumer_sync();
         if (tr) tr[2] = clock64();

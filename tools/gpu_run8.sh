@@ -7,4 +7,4 @@ run canary 150 python -m pytest tests/test_e2e_gpu.py -q -p no:cacheprovider -x 
 run canary2 240 python -m pytest tests/test_e2e_gpu.py -q -p no:cacheprovider -x -k "chat_flow or batch_invariance" || { echo "CANARY2 FAILED - aborting"; exit 1; }
 run pytest_gpu 420 python -m pytest tests -m gpu -q -p no:cacheprovider
 TAILN=30 run trace 420 python tools/mega_trace.py || exit 1
-TAILN=30 run bench 600 python bench.py --steps 2 --warmup 3
+TAILN=30 run bench 600 python bench.py --steps 2 --warmup 3 --no-cpu

@@ -6,7 +6,11 @@ import numpy as np
 import minigpt4_cpp_b200 as m
 import bench
 lib = m.load_library(); ext = m.B200(lib)
-vis, llm, _ = bench.ensure_models("7b", "q4_1", 39)
+from minigpt4_cpp_b200 import modelgen as mg
+NL = int(os.environ.get("TRACE_LAYERS", "4"))  # per-layer numbers do not depend on depth; 4 layers keep generation fast
+llm = str(bench.model_dir() / f"llama-7bwide-{NL}l-q4_1.bin")
+if not os.path.exists(llm):
+    mg.write_llama_ggjt(llm, mg.LlamaSpec(wtype="q4_1", n_embd=4096, n_head=32, n_layer=NL))
 ctx = ext.llm_load(llm, n_ctx=2048)
 rows = np.random.default_rng(0).standard_normal((32, 4096)).astype(np.float32)
 ext.eval_embd(ctx, rows)
@@ -14,7 +18,7 @@ ids, ms = ext.decode_chain(ctx, 128)
 print("chain ms/token", ms / 128)
 tr = ext.mega_trace(ctx).astype(np.float64)  # last launch
 names = {0: "embed", 1: "qkv", 2: "attn", 3: "wo", 4: "gate_up", 5: "down", 6: "output", 7: "final"}
-kinds = [0] + [1, 2, 3, 4, 5] * 32 + [6, 7]
+kinds = [0] + [1, 2, 3, 4, 5] * NL + [6, 7]
 mhz = 1965.0
 for c in range(2):
     t = tr[c]
