@@ -40,6 +40,7 @@ struct MegaParams {
     const float2 *rope; const __half *tab_exp, *tab_silu;
     const unsigned char *tok; int tok_type; size_t tok_row_bytes;
     DeviceState *state; unsigned *barrier;
+    int l2_ahead;      // producer: slots requested into L2 ahead of the ring (0 = off)
     long long *trace;  // optional [2 CTAs][n_ops][4] clock64 stamps: op start, barrier passed, activations staged, op done
 };
 
@@ -251,19 +252,37 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
 
     if (warp == kConsumerWarps) {  // ------------------------------ producer ------------------------------
         if (lane == 0) {
-            unsigned n = 0;
-            for (int oi = 0; oi < P.n_ops; ++oi) {
-                const MegaOp op = P.ops[oi];
-                if (!op.w) continue;
-                const int lo = (int)((long long)cta * op.n_su / G), hi = (int)((long long)(cta + 1) * op.n_su / G);
-                for (int su = lo; su < hi; ++su, ++n) {
-                    const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
-                    mb_wait(&empty[s], ph ^ 1u);
-                    const int r0 = su * op.su_rows, nr = min(op.su_rows, op.rows - r0);
-                    const unsigned bytes = (unsigned)nr * (unsigned)op.row_bytes;
-                    mb_expect_tx(&full[s], bytes);
-                    bulk_g2s(ring + (size_t)s * P.slot_bytes, op.w + (size_t)r0 * op.row_bytes, bytes, &full[s]);
+            // Two cursors walk this CTA's slot sequence over the whole op program: `fl` fills the shared-memory ring (blocks
+            // when the ring is full), `pf` runs kL2Ahead slots further and only asks L2 to fetch (cp.async.bulk.prefetch.L2),
+            // so HBM keeps streaming while the consumers sit in a grid barrier / staging / the attention op.
+            struct Cur { int oi, su, hi; };
+            auto seek = [&](Cur &c) {  // position on the first slot of the next op that has weights; false at the end
+                while (c.oi < P.n_ops) {
+                    const MegaOp *o = P.ops + c.oi;
+                    if (o->w) { const int n_su = o->n_su; c.su = (int)((long long)cta * n_su / G); c.hi = (int)((long long)(cta + 1) * n_su / G); if (c.su < c.hi) return true; }
+                    ++c.oi;
                 }
+                return false;
+            };
+            auto step = [&](Cur &c) { if (++c.su >= c.hi) { ++c.oi; return seek(c); } return true; };
+            Cur fl{0, 0, 0}, pf{0, 0, 0};
+            bool fl_ok = seek(fl), pf_ok = seek(pf);
+            int ahead = 0; unsigned n = 0;
+            while (fl_ok) {
+                while (pf_ok && ahead < P.l2_ahead) {
+                    const MegaOp *o = P.ops + pf.oi;
+                    const int r0 = pf.su * o->su_rows, nr = min(o->su_rows, o->rows - r0);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(o->w + (size_t)r0 * o->row_bytes), "r"((unsigned)nr * (unsigned)o->row_bytes) : "memory");
+                    pf_ok = step(pf); ++ahead;
+                }
+                const MegaOp *o = P.ops + fl.oi;
+                const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
+                mb_wait(&empty[s], ph ^ 1u);
+                const int r0 = fl.su * o->su_rows, nr = min(o->su_rows, o->rows - r0);
+                const unsigned bytes = (unsigned)nr * (unsigned)o->row_bytes;
+                mb_expect_tx(&full[s], bytes);
+                bulk_g2s(ring + (size_t)s * P.slot_bytes, o->w + (size_t)r0 * o->row_bytes, bytes, &full[s]);
+                fl_ok = step(fl); ++n; --ahead;
             }
         }
         return;

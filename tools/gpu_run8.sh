@@ -6,5 +6,7 @@ run build 300 python __graft_entry__.py || exit 1
 run canary 150 python -m pytest tests/test_e2e_gpu.py -q -p no:cacheprovider -x -k "megakernel" || { echo "CANARY FAILED - aborting"; exit 1; }
 run canary2 240 python -m pytest tests/test_e2e_gpu.py -q -p no:cacheprovider -x -k "chat_flow or batch_invariance" || { echo "CANARY2 FAILED - aborting"; exit 1; }
 run pytest_gpu 420 python -m pytest tests -m gpu -q -p no:cacheprovider
-TAILN=30 run trace 420 python tools/mega_trace.py || exit 1
+TAILN=22 run trace_nol2 420 env MINIGPT4_B200_L2_AHEAD=0 python tools/mega_trace.py || exit 1
+TAILN=22 run trace 300 python tools/mega_trace.py || exit 1
+TAILN=22 run trace_l2_48 300 env MINIGPT4_B200_L2_AHEAD=48 python tools/mega_trace.py
 TAILN=30 run bench 600 python bench.py --steps 2 --warmup 3 --no-cpu
