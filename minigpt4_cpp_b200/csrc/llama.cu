@@ -389,7 +389,7 @@ bool LlamaDevice::build_mega() {
     size_t act_b = std::max(act_bytes(act, FF), act_bytes(act, E));
     act_b = (act_b + 127) & ~(size_t)127;
     size_t xs_b = std::max((size_t)E * 4, (size_t)d_.n_ctx * 6);  // F32 copy of the RMS-normed input (n_embd wide) / attention scratch
-    xs_b = std::max<size_t>(xs_b, 4096);                           // at least one 1024-float window for the un-normed inputs
+    xs_b = std::max<size_t>(xs_b, 8192);                           // two 1024-float half-windows (double buffer) for the un-normed inputs
     xs_b = (xs_b + 127) & ~(size_t)127;
     const int rb_e = layers_[0].qkv.row_bytes, rb_ff = layers_[0].w2.row_bytes;
     int slot = std::max(2 * rb_e, 2 * rb_ff);
