@@ -46,8 +46,8 @@ extern int g_verbosity;  // 0 none, 1 error, 2 info, 3 debug
 // Fatal: there is NO CPU fallback.  A CUDA failure aborts loudly (reference PANIC -> exit(-1), minigpt4.cpp:230-232).
 #define CUDA_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
     fprintf(stderr, "[minigpt4-b200][fatal] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \
-    abort(); } } while (0)
-#define MG4_PANIC(...) do { fprintf(stderr, "[minigpt4-b200][fatal] " __VA_ARGS__); fputc('\n', stderr); abort(); } while (0)
+    fflush(stderr); abort(); } } while (0)
+#define MG4_PANIC(...) do { fprintf(stderr, "[minigpt4-b200][fatal] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); abort(); } while (0)
 
 // ggml tensor type ids as stored in ggjt files (llama.cpp@master-31cfbb1 ggml.h)
 enum GGType : int { GG_F32 = 0, GG_F16 = 1, GG_Q4_0 = 2, GG_Q4_1 = 3, GG_Q5_0 = 6, GG_Q5_1 = 7, GG_Q8_0 = 8, GG_Q8_1 = 9,

@@ -392,18 +392,23 @@ bool LlamaDevice::build_mega() {
     xs_b = std::max<size_t>(xs_b, 8192);                           // two 1024-float half-windows (double buffer) for the un-normed inputs
     xs_b = (xs_b + 127) & ~(size_t)127;
     const int rb_e = layers_[0].qkv.row_bytes, rb_ff = layers_[0].w2.row_bytes;
-    int slot = std::max(2 * rb_e, 2 * rb_ff);
-    slot = std::max(slot, 4 * rb_e);
+    // one ring slot holds a row pair of an n_embd-wide matrix or ONE row of an n_ff-wide matrix (its pair uses two slots)
+    int slot = std::max(2 * rb_e, rb_ff);
     slot = (slot + 127) & ~127;
     cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-    const size_t budget = prop.sharedMemPerBlockOptin - 2048;  // static shared + slack
-    const int n_slots = (int)std::min<size_t>(24, (budget - 9216 - act_b - xs_b - 512) / (size_t)slot);  // 9 KB of static shared memory
-    if (n_slots < 4) return false;
-    auto su_rows_for = [&](int row_bytes) { int r = (slot / row_bytes) & ~1; return std::max(2, std::min(r, 4)); };
+    const size_t budget = prop.sharedMemPerBlockOptin - 2048;  // slack
+    const int n_slots = (int)std::min<size_t>(48, (budget - 9216 - act_b - xs_b - 1024) / (size_t)slot);  // 9 KB of static shared memory
+    if (n_slots < 12) return false;
+    const int inflight = 10;  // slots kept free of consumers so that ~bandwidth x latency worth of fills is always in flight
     std::vector<MegaOp> ops;
     auto add = [&](int kind, int layer, const QMat *m, const float *norm) {
         MegaOp o{}; o.kind = kind; o.layer = layer; o.norm_w = norm;
-        if (m) { o.rows = m->rows; o.cols = m->cols; o.row_bytes = m->row_bytes; o.su_rows = su_rows_for(m->row_bytes); o.n_su = (m->rows + o.su_rows - 1) / o.su_rows; o.w = (const unsigned char *)m->p0; }
+        if (m) {
+            o.rows = m->rows; o.cols = m->cols; o.row_bytes = m->row_bytes; o.w = (const unsigned char *)m->p0;
+            o.sps = 2 * m->row_bytes <= slot ? 1 : 2;
+            o.n_su = m->rows / 2;
+            o.n_warps = std::max(1, std::min(kConsumerWarps, (n_slots - inflight) / o.sps));
+        }
         ops.push_back(o);
     };
     add(OP_EMBED, 0, nullptr, nullptr);

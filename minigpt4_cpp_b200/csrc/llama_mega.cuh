@@ -25,7 +25,8 @@ enum OpKind : int { OP_EMBED = 0, OP_QKV = 1, OP_ATTN = 2, OP_WO = 3, OP_GATEUP 
 
 struct MegaOp {
     int kind, layer, rows, cols;
-    int row_bytes, su_rows, n_su, pad;   // su = "super-unit": su_rows consecutive rows = one ring slot, consumed by one warp
+    int row_bytes, sps, n_su, n_warps;   // su = one ROW PAIR, the unit a consumer warp works on; it occupies sps ring slots (1 slot of two
+                                         // rows for n_embd-wide matrices, 2 slots of one row for n_ff-wide ones); n_warps = active consumers
     const unsigned char *w;              // row-packed Q4 weights (null for non-matvec ops)
     const float *norm_w;
 };
@@ -186,14 +187,10 @@ __device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, cons
         const int i = 1024 * it + 4 * tid;
         if (i < cols) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(xs + i)), "l"(x + i) : "memory");
+            if (nw) asm volatile("prefetch.global.L1 [%0];" ::"l"(nw + i));
         }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    // norm weights (constant data): issued now, consumed after the block reduction; n_embd <= 5120 -> at most 5 float4
-    float4 w4[5];
-#pragma unroll
-    for (int it = 0; it < 5; ++it) { const int i = 1024 * it + 4 * tid; if (nw && i < cols) w4[it] = __ldg((const float4 *)(nw + i)); }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     // each thread reads back only what it copied itself, so no barrier is needed before the passes below
     float scale = 1.0f;
     if (nw) {
@@ -213,12 +210,12 @@ __device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, cons
         const float mean = (float)(tot / (double)cols);
         scale = 1.0f / sqrtf(mean + 1e-6f);
     }
-#pragma unroll
-    for (int it = 0; it < 5; ++it) {
+#pragma unroll 2
+    for (int it = 0; it <= nitem; ++it) {
         const int i = 1024 * it + 4 * tid;
         if (i < cols) {  // warp-uniform: cols is a multiple of 128
             float4 a = *(const float4 *)(xs + i);
-            if (nw) a = make_float4((a.x * scale) * w4[it].x, (a.y * scale) * w4[it].y, (a.z * scale) * w4[it].z, (a.w * scale) * w4[it].w);
+            if (nw) { const float4 w4 = __ldg((const float4 *)(nw + i)); a = make_float4((a.x * scale) * w4.x, (a.y * scale) * w4.y, (a.z * scale) * w4.z, (a.w * scale) * w4.w); }
             quant_item<ACT>(a, i, cols, sm);
         }
     }
@@ -271,18 +268,18 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
             while (fl_ok) {
                 while (pf_ok && ahead < P.l2_ahead) {
                     const MegaOp *o = P.ops + pf.oi;
-                    const int r0 = pf.su * o->su_rows, nr = min(o->su_rows, o->rows - r0);
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(o->w + (size_t)r0 * o->row_bytes), "r"((unsigned)nr * (unsigned)o->row_bytes) : "memory");
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(o->w + (size_t)pf.su * 2 * o->row_bytes), "r"(2u * (unsigned)o->row_bytes) : "memory");
                     pf_ok = step(pf); ++ahead;
                 }
                 const MegaOp *o = P.ops + fl.oi;
-                const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
-                mb_wait(&empty[s], ph ^ 1u);
-                const int r0 = fl.su * o->su_rows, nr = min(o->su_rows, o->rows - r0);
-                const unsigned bytes = (unsigned)nr * (unsigned)o->row_bytes;
-                mb_expect_tx(&full[s], bytes);
-                bulk_g2s(ring + (size_t)s * P.slot_bytes, o->w + (size_t)r0 * o->row_bytes, bytes, &full[s]);
-                fl_ok = step(fl); ++n; --ahead;
+                const unsigned bytes = (unsigned)o->row_bytes * (o->sps == 1 ? 2u : 1u);
+                for (int j = 0; j < o->sps; ++j, ++n) {
+                    const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
+                    mb_wait(&empty[s], ph ^ 1u);
+                    mb_expect_tx(&full[s], bytes);
+                    bulk_g2s(ring + (size_t)s * P.slot_bytes, o->w + ((size_t)fl.su * 2 + j) * o->row_bytes, bytes, &full[s]);
+                }
+                fl_ok = step(fl); --ahead;
             }
         }
         return;
@@ -333,25 +330,26 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         const int nb = op.cols / 32;
         const int lo = (int)((long long)cta * op.n_su / G), hi = (int)((long long)(cta + 1) * op.n_su / G);
         unsigned long long best = 0ull;
-        // W = min(15, n_slots) warps consume.  With W <= n_slots a warp can never wait on a slot that is two fills behind:
-        // it consumed slot n - W itself, so fill n - n_slots (<= n - W) has happened and the mbarrier parity is unambiguous.
-        const int W = min(kConsumerWarps, P.n_slots);
+        // op.n_warps consumer warps work on this op (the rest of the ring must stay free for fills in flight).  With
+        // n_warps * sps <= n_slots a warp can never wait on a slot that is two fills behind: it consumed unit su - n_warps
+        // itself, so the previous fill of its slot has happened and the mbarrier parity is unambiguous.
+        const int W = op.n_warps;
         for (int su = lo + warp; warp < W && su < hi; su += W) {
-            const unsigned n = n_base + (unsigned)(su - lo);
-            const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
-            float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};  // residual rows of this slot, fetched before the wait
-            if (op.kind == OP_WO || op.kind == OP_DOWN) {
-                rs[0] = __ldcg((const float2 *)(P.x + su * op.su_rows));
-                if (op.su_rows > 2) rs[1] = __ldcg((const float2 *)(P.x + su * op.su_rows + 2));
-            }
-            mb_wait(&full[s], ph);
-            const unsigned char *slot = ring + (size_t)s * P.slot_bytes;
-            for (int rp = 0; rp < op.su_rows; rp += 2) {
-                const int r0 = su * op.su_rows + rp;
-                if (r0 >= op.rows) break;
-                float v0, v1;
-                dot2_q4_slot<Q41>(slot + (size_t)rp * op.row_bytes, slot + (size_t)(rp + 1) * op.row_bytes, nb, op.cols, actb, lane, v0, v1);
-                if (lane == 0) switch (op.kind) {
+            const unsigned n = n_base + (unsigned)(su - lo) * (unsigned)op.sps;
+            const int s0 = (int)(n % (unsigned)P.n_slots), s1 = (int)((n + 1) % (unsigned)P.n_slots);
+            const int r0 = su * 2;
+            float2 rs = make_float2(0.f, 0.f);  // residual rows of this pair, fetched before the wait
+            if (op.kind == OP_WO || op.kind == OP_DOWN) rs = __ldcg((const float2 *)(P.x + r0));
+            mb_wait(&full[s0], (n / (unsigned)P.n_slots) & 1u);
+            if (op.sps == 2) mb_wait(&full[s1], ((n + 1) / (unsigned)P.n_slots) & 1u);
+            const unsigned char *row0 = ring + (size_t)s0 * P.slot_bytes;
+            const unsigned char *row1 = op.sps == 2 ? ring + (size_t)s1 * P.slot_bytes : row0 + op.row_bytes;
+            float v0, v1;
+            dot2_q4_slot<Q41>(row0, row1, nb, op.cols, actb, lane, v0, v1);
+            if (lane == 0) {
+                mb_arrive(&empty[s0]);
+                if (op.sps == 2) mb_arrive(&empty[s1]);
+                switch (op.kind) {
                     case OP_QKV: {
                         const int E = P.E, partn = r0 / E, rr = r0 % E;
                         const size_t kvo = ((size_t)op.layer * P.n_ctx + pos) * E + rr;
@@ -363,10 +361,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
                             else *(__half2 *)(P.kcache + kvo) = __floats2half2_rn(o0, o1);
                         }
                     } break;
-                    case OP_WO: case OP_DOWN: {
-                        const float2 r2 = rp == 0 ? rs[0] : rs[1];
-                        *(float2 *)(P.x + r0) = make_float2(v0 + r2.x, v1 + r2.y);
-                    } break;
+                    case OP_WO: case OP_DOWN: *(float2 *)(P.x + r0) = make_float2(v0 + rs.x, v1 + rs.y); break;
                     case OP_GATEUP: P.act[r0 >> 1] = lut_f16(P.tab_silu, v0) * v1; break;
                     default: {  // OP_OUTPUT
                         P.logits[r0] = v0;
@@ -376,11 +371,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
                     } break;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mb_arrive(&empty[s]);
         }
         if (op.kind == OP_OUTPUT && lane == 0 && best) atomicMax(&P.state->argmax_key, best);
-        n_base += (unsigned)(hi - lo);
+        n_base += (unsigned)(hi - lo) * (unsigned)op.sps;
         if (tr) tr[3] = clock64();  // (thread 0 = warp 0 only; other warps may still be consuming)
     }
 }
