@@ -397,7 +397,8 @@ bool LlamaDevice::build_mega() {
     slot = (slot + 127) & ~127;
     cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     const size_t budget = prop.sharedMemPerBlockOptin - 2048;  // slack
-    const int n_slots = (int)std::min<size_t>(48, (budget - 9216 - act_b - xs_b - 1024) / (size_t)slot);  // 9 KB of static shared memory
+    const size_t ops_b = (size_t)(5 * d_.n_layer + 3) * sizeof(MegaOp);  // the op program lives in shared memory too
+    const int n_slots = (int)std::min<size_t>(48, (budget - 9216 - act_b - xs_b - ops_b - 1024) / (size_t)slot);  // 9 KB of static shared memory
     if (n_slots < 12) return false;
     const int inflight = 10;  // slots kept free of consumers so that ~bandwidth x latency worth of fills is always in flight
     std::vector<MegaOp> ops;
@@ -435,11 +436,11 @@ bool LlamaDevice::build_mega() {
     P->tok = (const unsigned char *)tok_raw_; P->tok_type = tok_type_; P->tok_row_bytes = gg_row_bytes(tok_type_, (size_t)E);
     P->state = state_; P->barrier = mega_barrier_;
     P->trace = nullptr;
-    P->l2_ahead = getenv("MINIGPT4_B200_L2_AHEAD") ? atoi(getenv("MINIGPT4_B200_L2_AHEAD")) : 24;
+    P->l2_ahead = getenv("MINIGPT4_B200_L2_AHEAD") ? atoi(getenv("MINIGPT4_B200_L2_AHEAD")) : 48;
     if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, ops.size() * 8 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, ops.size() * 8 * sizeof(long long))); P->trace = mega_trace_; }
     mega_n_ops_ = (int)ops.size();
     mega_params_ = P;
-    mega_smem_ = (size_t)n_slots * slot + xs_b + act_b + (size_t)n_slots * 16 + 64;
+    mega_smem_ = (size_t)n_slots * slot + xs_b + act_b + (size_t)n_slots * 16 + ops.size() * sizeof(MegaOp) + 64;
     mega_type_ = wt;
     mega_stk_ = (std::max(E, FF) + 2047) / 2048;
     const void *fn = mega_fn();

@@ -533,7 +533,7 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
     // its first batch of K rows (one memory round trip instead of two); q is rounded to F16 as ggml does.
     {
         const int sub = lane >> 4, l16 = lane & 15;
-        constexpr int B = 8;  // keys in flight per half-warp: all loads of a batch are issued before the first use
+        constexpr int B = 12;  // keys in flight per half-warp (192 keys per pass): all loads of a batch are issued before the first use
         __half2 q2[4];
         bool have_q = false;
         for (int kb0 = warp * 2; kb0 < nkv || !have_q; kb0 += 16 * B) {  // warp-uniform trip counts (both half-warps shuffle together)
@@ -584,8 +584,8 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        constexpr int B = 8;
-        for (int key0 = g; key0 < nkv; key0 += 16 * B) {  // batch the V loads; the FMA order over keys stays sequential
+        constexpr int B = 12;
+        for (int key0 = g; key0 < nkv; key0 += 16 * B) {  // batch the V loads (192 keys per pass); the FMA order over keys stays sequential
             uint4 vv[B];
 #pragma unroll
             for (int u = 0; u < B; ++u) { const int key = key0 + 16 * u; if (key < nkv) vv[u] = ld_kv16<MEGA>(vc + (size_t)key * E + h * 128 + o * 8); }

@@ -41,7 +41,7 @@ struct MegaParams {
     const float2 *rope; const __half *tab_exp, *tab_silu;
     const unsigned char *tok; int tok_type; size_t tok_row_bytes;
     DeviceState *state; unsigned *barrier;
-    int l2_ahead;      // producer: slots requested into L2 ahead of the ring (0 = off)
+    int l2_ahead;      // producer: ring slots requested into L2 ahead of the fill cursor (0 = off)
     long long *trace;  // optional [2 CTAs][n_ops][4] clock64 stamps: op start, barrier passed, activations staged, op done
 };
 
@@ -238,48 +238,53 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
     constexpr bool Q41 = WT == GG_Q4_1;
     unsigned char *ring = smem, *xsb = smem + (size_t)P.n_slots * P.slot_bytes, *actb = xsb + P.xs_bytes;
     uint64_t *full = (uint64_t *)(actb + P.act_bytes), *empty = full + P.n_slots;
+    MegaOp *ops = (MegaOp *)(empty + P.n_slots);                 // the op program, copied once from global memory
+    volatile unsigned *fill_count = (volatile unsigned *)(ops + P.n_ops);  // slots issued so far (read by the L2-prefetch lane)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
 
     if (tid == 0) {
         for (int s = 0; s < P.n_slots; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
+        *fill_count = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = tid; i < P.n_ops * (int)(sizeof(MegaOp) / 16); i += kMegaThreads) ((uint4 *)ops)[i] = ((const uint4 *)P.ops)[i];
     __syncthreads();  // the only CTA-wide barrier; afterwards consumers use named barriers 2 (512 thr) and 1 (256 thr, attention)
 
     if (warp == kConsumerWarps) {  // ------------------------------ producer ------------------------------
+        // lane 0 fills the shared-memory ring with cp.async.bulk (blocks when the ring is full); lane 1 walks the same slot
+        // sequence kL2Ahead units further and only asks L2 to fetch (cp.async.bulk.prefetch.L2), so HBM keeps streaming while
+        // the consumers sit in a grid barrier / staging / the attention op.  Per-op fields are held in registers.
         if (lane == 0) {
-            // Two cursors walk this CTA's slot sequence over the whole op program: `fl` fills the shared-memory ring (blocks
-            // when the ring is full), `pf` runs kL2Ahead slots further and only asks L2 to fetch (cp.async.bulk.prefetch.L2),
-            // so HBM keeps streaming while the consumers sit in a grid barrier / staging / the attention op.
-            struct Cur { int oi, su, hi; };
-            auto seek = [&](Cur &c) {  // position on the first slot of the next op that has weights; false at the end
-                while (c.oi < P.n_ops) {
-                    const MegaOp *o = P.ops + c.oi;
-                    if (o->w) { const int n_su = o->n_su; c.su = (int)((long long)cta * n_su / G); c.hi = (int)((long long)(cta + 1) * n_su / G); if (c.su < c.hi) return true; }
-                    ++c.oi;
-                }
-                return false;
-            };
-            auto step = [&](Cur &c) { if (++c.su >= c.hi) { ++c.oi; return seek(c); } return true; };
-            Cur fl{0, 0, 0}, pf{0, 0, 0};
-            bool fl_ok = seek(fl), pf_ok = seek(pf);
-            int ahead = 0; unsigned n = 0;
-            while (fl_ok) {
-                while (pf_ok && ahead < P.l2_ahead) {
-                    const MegaOp *o = P.ops + pf.oi;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(o->w + (size_t)pf.su * 2 * o->row_bytes), "r"(2u * (unsigned)o->row_bytes) : "memory");
-                    pf_ok = step(pf); ++ahead;
-                }
-                const MegaOp *o = P.ops + fl.oi;
-                const unsigned bytes = (unsigned)o->row_bytes * (o->sps == 1 ? 2u : 1u);
-                for (int j = 0; j < o->sps; ++j, ++n) {
-                    const int s = (int)(n % (unsigned)P.n_slots); const unsigned ph = (n / (unsigned)P.n_slots) & 1u;
+            unsigned n = 0, s = 0, ph = 0;  // fill number, its ring slot and phase parity (running counters: no div/mod per slot)
+            for (int oi = 0; oi < P.n_ops; ++oi) {
+                const unsigned char *w = ops[oi].w;
+                if (!w) continue;
+                const int n_su = ops[oi].n_su, sps = ops[oi].sps;
+                const unsigned rb = (unsigned)ops[oi].row_bytes, bytes = sps == 1 ? 2u * rb : rb;
+                const int lo = (int)((long long)cta * n_su / G), hi = (int)((long long)(cta + 1) * n_su / G);
+                const unsigned char *src = w + (size_t)lo * 2 * rb;
+                for (int c = (hi - lo) * sps; c > 0; --c, src += bytes) {
                     mb_wait(&empty[s], ph ^ 1u);
                     mb_expect_tx(&full[s], bytes);
-                    bulk_g2s(ring + (size_t)s * P.slot_bytes, o->w + ((size_t)fl.su * 2 + j) * o->row_bytes, bytes, &full[s]);
+                    bulk_g2s(ring + (size_t)s * P.slot_bytes, src, bytes, &full[s]);
+                    *fill_count = ++n;
+                    if (++s == (unsigned)P.n_slots) { s = 0; ph ^= 1u; }
                 }
-                fl_ok = step(fl); --ahead;
+            }
+        } else if (lane == 1 && P.l2_ahead > 0) {
+            unsigned n = 0;
+            for (int oi = 0; oi < P.n_ops; ++oi) {
+                const unsigned char *w = ops[oi].w;
+                if (!w) continue;
+                const int n_su = ops[oi].n_su, sps = ops[oi].sps;
+                const unsigned rb = (unsigned)ops[oi].row_bytes;
+                const int lo = (int)((long long)cta * n_su / G), hi = (int)((long long)(cta + 1) * n_su / G);
+                const unsigned char *src = w + (size_t)lo * 2 * rb;
+                for (int su = lo; su < hi; ++su, n += (unsigned)sps, src += 2 * rb) {
+                    while ((int)(n - *fill_count) >= P.l2_ahead) __nanosleep(200);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(2u * rb) : "memory");
+                }
             }
         }
         return;
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
     unsigned n_base = 0, bar_target = 0;
     const int pos = __ldcg(&P.state->n_past);  // position of the token being decoded (state only changes in OP_FINAL)
     for (int oi = 0; oi < P.n_ops; ++oi) {
-        const MegaOp op = P.ops[oi];
+        const MegaOp op = ops[oi];
         long long *tr = (P.trace && tid == 0 && (cta == 0 || cta == G - 1)) ? P.trace + ((size_t)(cta == 0 ? 0 : 1) * P.n_ops + oi) * 4 : nullptr;
         if (tr) { tr[0] = clock64(); tr[2] = 0; }
         if (oi > 0) { bar_target += (unsigned)G; grid_barrier(P.barrier, bar_target); }
