@@ -437,7 +437,7 @@ bool LlamaDevice::build_mega() {
     P->state = state_; P->barrier = mega_barrier_;
     P->trace = nullptr;
     P->l2_ahead = getenv("MINIGPT4_B200_L2_AHEAD") ? atoi(getenv("MINIGPT4_B200_L2_AHEAD")) : 48;
-    if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, ops.size() * 8 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, ops.size() * 8 * sizeof(long long))); P->trace = mega_trace_; }
+    if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, ops.size() * 16 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, ops.size() * 16 * sizeof(long long))); P->trace = mega_trace_; }
     mega_n_ops_ = (int)ops.size();
     mega_params_ = P;
     mega_smem_ = (size_t)n_slots * slot + xs_b + act_b + (size_t)n_slots * 16 + ops.size() * sizeof(MegaOp) + 64;
@@ -516,7 +516,7 @@ float LlamaDevice::decode_chain(int steps, int n_past, int32_t *ids_out) {
 
 int LlamaDevice::mega_trace(long long *out, int max_values) {
     if (!mega_trace_) return 0;
-    const int n = std::min(max_values, mega_n_ops_ * 8);
+    const int n = std::min(max_values, mega_n_ops_ * 16);
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaMemcpy(out, mega_trace_, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
     return n;

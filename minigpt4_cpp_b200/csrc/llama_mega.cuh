@@ -42,7 +42,8 @@ struct MegaParams {
     const unsigned char *tok; int tok_type; size_t tok_row_bytes;
     DeviceState *state; unsigned *barrier;
     int l2_ahead;      // producer: ring slots requested into L2 ahead of the fill cursor (0 = off)
-    long long *trace;  // optional [2 CTAs][n_ops][4] clock64 stamps: op start, barrier passed, activations staged, op done
+    long long *trace;  // optional [2 CTAs][n_ops][8]: clock64 at op start, barrier passed, activations staged, op done; then (warp 0)
+                       // cycles spent waiting for ring fills, cycles in the dot products, units processed, unused
 };
 
 constexpr int kConsumerWarps = 15, kConsumerThreads = 480;
@@ -295,8 +296,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
     const int pos = __ldcg(&P.state->n_past);  // position of the token being decoded (state only changes in OP_FINAL)
     for (int oi = 0; oi < P.n_ops; ++oi) {
         const MegaOp op = ops[oi];
-        long long *tr = (P.trace && tid == 0 && (cta == 0 || cta == G - 1)) ? P.trace + ((size_t)(cta == 0 ? 0 : 1) * P.n_ops + oi) * 4 : nullptr;
-        if (tr) { tr[0] = clock64(); tr[2] = 0; }
+        long long *tr = (P.trace && tid == 0 && (cta == 0 || cta == G - 1)) ? P.trace + ((size_t)(cta == 0 ? 0 : 1) * P.n_ops + oi) * 8 : nullptr;
+        if (tr) { tr[0] = clock64(); tr[2] = 0; tr[4] = 0; tr[5] = 0; tr[6] = 0; }
         if (oi > 0) { bar_target += (unsigned)G; grid_barrier(P.barrier, bar_target); }
         if (tr) tr[1] = clock64();
 
@@ -339,18 +340,24 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         // n_warps * sps <= n_slots a warp can never wait on a slot that is two fills behind: it consumed unit su - n_warps
         // itself, so the previous fill of its slot has happened and the mbarrier parity is unambiguous.
         const int W = op.n_warps;
+        const int S = P.n_slots, stepn = W * op.sps;
+        int s0 = (int)((n_base + (unsigned)(warp * op.sps)) % (unsigned)S);              // ring slot of this warp's current unit ...
+        unsigned ph0 = ((n_base + (unsigned)(warp * op.sps)) / (unsigned)S) & 1u;        // ... and its fill parity (advanced incrementally)
         for (int su = lo + warp; warp < W && su < hi; su += W) {
-            const unsigned n = n_base + (unsigned)(su - lo) * (unsigned)op.sps;
-            const int s0 = (int)(n % (unsigned)P.n_slots), s1 = (int)((n + 1) % (unsigned)P.n_slots);
+            int s1 = s0 + 1; unsigned ph1 = ph0;
+            if (s1 == S) { s1 = 0; ph1 ^= 1u; }
             const int r0 = su * 2;
             float2 rs = make_float2(0.f, 0.f);  // residual rows of this pair, fetched before the wait
             if (op.kind == OP_WO || op.kind == OP_DOWN) rs = __ldcg((const float2 *)(P.x + r0));
-            mb_wait(&full[s0], (n / (unsigned)P.n_slots) & 1u);
-            if (op.sps == 2) mb_wait(&full[s1], ((n + 1) / (unsigned)P.n_slots) & 1u);
+            const long long tw0 = tr ? clock64() : 0;
+            mb_wait(&full[s0], ph0);
+            if (op.sps == 2) mb_wait(&full[s1], ph1);
+            const long long tw1 = tr ? clock64() : 0;
             const unsigned char *row0 = ring + (size_t)s0 * P.slot_bytes;
             const unsigned char *row1 = op.sps == 2 ? ring + (size_t)s1 * P.slot_bytes : row0 + op.row_bytes;
             float v0, v1;
             dot2_q4_slot<Q41>(row0, row1, nb, op.cols, actb, lane, v0, v1);
+            if (tr) { const long long tw2 = clock64(); tr[4] += tw1 - tw0; tr[5] += tw2 - tw1; tr[6] += 1; }
             if (lane == 0) {
                 mb_arrive(&empty[s0]);
                 if (op.sps == 2) mb_arrive(&empty[s1]);
@@ -376,6 +383,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
                     } break;
                 }
             }
+            s0 += stepn; while (s0 >= S) { s0 -= S; ph0 ^= 1u; }
         }
         if (op.kind == OP_OUTPUT && lane == 0 && best) atomicMax(&P.state->argmax_key, best);
         n_base += (unsigned)(hi - lo) * (unsigned)op.sps;

@@ -293,9 +293,9 @@ class B200:
         return ms.value, nb.value
 
     def mega_trace(self, ctx) -> np.ndarray:
-        buf = np.zeros(2 * 400 * 4, np.int64)
+        buf = np.zeros(2 * 400 * 8, np.int64)
         n = self.L.minigpt4_b200_mega_trace(ctx.ptr, _ptr(buf), buf.size)
-        return buf[:n].reshape(2, -1, 4) if n else buf[:0]
+        return buf[:n].reshape(2, -1, 8) if n else buf[:0]
 
     def stats(self, ctx) -> Stats:
         s = Stats()
