@@ -380,17 +380,16 @@ bool LlamaDevice::build_mega() {
     const int wt = output_.type;
     if (wt != GG_Q4_0 && wt != GG_Q4_1) return false;
     for (auto &L : layers_) if (!L.fused_qkv || L.qkv.type != wt || L.wo.type != wt || L.w13.type != wt || L.w2.type != wt) return false;
-    if (d_.n_embd % 256 || d_.n_ff % 256 || std::max(d_.n_embd, d_.n_ff) > 2048 * mk::kStageMaxK || d_.n_embd % 128 || d_.n_ff % 128) return false;
+    if (d_.n_embd % 256 || d_.n_ff % 256 || d_.n_embd > 1024 * mk::kNormItems || d_.n_ff > 4 * mk::kConsumerThreads * mk::kPlainItems) return false;
     int coop = 0, dev = 0; CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     if (!coop) return false;
     const int E = d_.n_embd, FF = d_.n_ff;
     const int act = act_of(wt);
     size_t act_b = std::max(act_bytes(act, FF), act_bytes(act, E));
+    act_b = std::max(act_b, (size_t)d_.n_ctx * 6);  // the attention op (which stages no activations) uses the region as its scratch
     act_b = (act_b + 127) & ~(size_t)127;
-    size_t xs_b = std::max((size_t)E * 4, (size_t)d_.n_ctx * 6);  // F32 copy of the RMS-normed input (n_embd wide) / attention scratch
-    xs_b = std::max<size_t>(xs_b, 8192);                           // two 1024-float half-windows (double buffer) for the un-normed inputs
-    xs_b = (xs_b + 127) & ~(size_t)127;
+    const size_t xs_b = 0;
     const int rb_e = layers_[0].qkv.row_bytes, rb_ff = layers_[0].w2.row_bytes;
     // one ring slot holds a row pair of an n_embd-wide matrix or ONE row of an n_ff-wide matrix (its pair uses two slots)
     int slot = std::max(2 * rb_e, rb_ff);
@@ -400,7 +399,7 @@ bool LlamaDevice::build_mega() {
     const size_t ops_b = (size_t)(5 * d_.n_layer + 3) * sizeof(MegaOp);  // the op program lives in shared memory too
     const int n_slots = (int)std::min<size_t>(48, (budget - 9216 - act_b - xs_b - ops_b - 1024) / (size_t)slot);  // 9 KB of static shared memory
     if (n_slots < 12) return false;
-    const int inflight = 10;  // slots kept free of consumers so that ~bandwidth x latency worth of fills is always in flight
+    const int inflight = getenv("MINIGPT4_B200_INFLIGHT") ? atoi(getenv("MINIGPT4_B200_INFLIGHT")) : 10;  // slots kept free of consumers so that ~bandwidth x latency worth of fills is always in flight
     std::vector<MegaOp> ops;
     auto add = [&](int kind, int layer, const QMat *m, const float *norm) {
         MegaOp o{}; o.kind = kind; o.layer = layer; o.norm_w = norm;

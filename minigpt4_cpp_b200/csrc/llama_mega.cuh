@@ -33,7 +33,7 @@ struct MegaOp {
 
 struct MegaParams {
     const MegaOp *ops; int n_ops;
-    int n_slots, slot_bytes, act_bytes, xs_bytes;   // shared memory: [ring][xs: F32 input / attention scratch][act: staged Q8][mbarriers]
+    int n_slots, slot_bytes, act_bytes, xs_bytes;   // shared memory: [ring][act: staged Q8 activations / attention scratch][mbarriers][ops]
     int E, FF, n_head, n_ctx, n_vocab;
     float kq_scale;
     float *x, *q, *att, *act, *logits;
@@ -81,61 +81,73 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
     consumer_sync();
 }
 
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {  // unsigned bytes x signed bytes
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// sum_j q_j a_j of one 32-weight Q4 block (16 B of nibbles, q in 0..15) with its Q8 block (two 16-byte planes).  The high nibbles
+// stay in place (w & 0xF0F0F0F0 = 16 q): their dp4a sum is an exact multiple of 16, so one shift replaces four - and the two
+// 4-deep dp4a chains are independent.  Integer arithmetic: same value as the nibble-by-nibble form of k::dot2_q4.
+__device__ __forceinline__ int q4_block_idot(const uint4 q, const int4 lo, const int4 hi) {
+    int sl = dp4a_us(q.x & 0x0F0F0F0Fu, lo.x, 0), sh = dp4a_us(q.x & 0xF0F0F0F0u, hi.x, 0);
+    sl = dp4a_us(q.y & 0x0F0F0F0Fu, lo.y, sl); sh = dp4a_us(q.y & 0xF0F0F0F0u, hi.y, sh);
+    sl = dp4a_us(q.z & 0x0F0F0F0Fu, lo.z, sl); sh = dp4a_us(q.z & 0xF0F0F0F0u, hi.z, sh);
+    sl = dp4a_us(q.w & 0x0F0F0F0Fu, lo.w, sl); sh = dp4a_us(q.w & 0xF0F0F0F0u, hi.w, sh);
+    return sl + (sh >> 4);
+}
+
 // Two rows of a shared-memory ring slot against the staged activation vector.  Same per-lane block order and the same
-// arithmetic as k::dot2_q4 (lane l: blocks l, l+32, ... increasing; butterfly reductions), but one block at a time: shared
-// memory latency is short, so there is no need to keep 8 blocks in registers, and the megakernel stays free of spills.
+// float arithmetic as k::dot2_q4 (lane l: blocks l, l+32, ... increasing; butterfly reductions).  Two blocks per row are in
+// flight per iteration (8 independent dp4a chains); Q4_0's "-8" is applied as  sum (q-8) a = sum q a - 8 sum a  with the
+// integer activation sum the staging pass leaves in the `s` plane.
 template <bool Q41>
 __device__ __forceinline__ void dot2_q4_slot(const unsigned char *row0, const unsigned char *row1, int nb, int cols, const unsigned char *act, int lane, float &r0, float &r1) {
     const uint4 *qs0 = (const uint4 *)row0, *qs1 = (const uint4 *)row1;
     const unsigned char *sc0 = row0 + (size_t)nb * 16, *sc1 = row1 + (size_t)nb * 16;
+    const int4 *alo = (const int4 *)act, *ahi = (const int4 *)(act + cols / 2);
     const float *ad = (const float *)(act + cols), *as = ad + nb;
     float accd0 = 0.f, accd1 = 0.f, accm0 = 0.f, accm1 = 0.f;
-#pragma unroll 2
-    for (int b = lane; b < nb; b += 32) {
-        const uint4 q0 = qs0[b], q1 = qs1[b];
-        const int4 a0 = *(const int4 *)(act + b * 16), a1 = *(const int4 *)(act + cols / 2 + b * 16);
-        const float adv = ad[b];
-        float d0, m0 = 0.f, d1, m1 = 0.f;
+#pragma unroll 1
+    for (int b = lane; b < nb; b += 64) {
+        const bool two = b + 32 < nb;
+        const int c = two ? b + 32 : b;  // (clamped: the second block's loads stay in bounds, its contribution is dropped)
+        const uint4 qa0 = qs0[b], qa1 = qs1[b], qb0 = qs0[c], qb1 = qs1[c];
+        const int4 la = alo[b], ha = ahi[b], lb = alo[c], hb = ahi[c];
+        const float adva = ad[b], advb = ad[c], asva = as[b], asvb = as[c];
+        int sa0 = q4_block_idot(qa0, la, ha), sa1 = q4_block_idot(qa1, la, ha);
+        int sb0 = q4_block_idot(qb0, lb, hb), sb1 = q4_block_idot(qb1, lb, hb);
         if (Q41) {
-            const float2 f0 = __half22float2(((const __half2 *)sc0)[b]), f1 = __half22float2(((const __half2 *)sc1)[b]);
-            d0 = f0.x; m0 = f0.y; d1 = f1.x; m1 = f1.y;
-        } else { d0 = __half2float(((const __half *)sc0)[b]); d1 = __half2float(((const __half *)sc1)[b]); }
-        const unsigned w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w};
-        const int av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        int s0 = 0, s1 = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int l0 = (int)(w0[j] & 0x0F0F0F0Fu), l1 = (int)(w1[j] & 0x0F0F0F0Fu);
-            if (!Q41) { l0 = (int)__vsub4((unsigned)l0, 0x08080808u); l1 = (int)__vsub4((unsigned)l1, 0x08080808u); }
-            s0 = __dp4a(l0, av[j], s0); s1 = __dp4a(l1, av[j], s1);
+            const float2 fa0 = __half22float2(((const __half2 *)sc0)[b]), fa1 = __half22float2(((const __half2 *)sc1)[b]);
+            const float2 fb0 = __half22float2(((const __half2 *)sc0)[c]), fb1 = __half22float2(((const __half2 *)sc1)[c]);
+            accd0 = fmaf(fa0.x * adva, (float)sa0, accd0); accm0 = fmaf(fa0.y, asva, accm0);
+            accd1 = fmaf(fa1.x * adva, (float)sa1, accd1); accm1 = fmaf(fa1.y, asva, accm1);
+            if (two) {
+                accd0 = fmaf(fb0.x * advb, (float)sb0, accd0); accm0 = fmaf(fb0.y, asvb, accm0);
+                accd1 = fmaf(fb1.x * advb, (float)sb1, accd1); accm1 = fmaf(fb1.y, asvb, accm1);
+            }
+        } else {
+            const float da0 = __half2float(((const __half *)sc0)[b]), da1 = __half2float(((const __half *)sc1)[b]);
+            const float db0 = __half2float(((const __half *)sc0)[c]), db1 = __half2float(((const __half *)sc1)[c]);
+            const int ia = 8 * (int)asva, ib = 8 * (int)asvb;
+            sa0 -= ia; sa1 -= ia; sb0 -= ib; sb1 -= ib;
+            accd0 += ((float)sa0 * da0) * adva; accd1 += ((float)sa1 * da1) * adva;
+            if (two) { accd0 += ((float)sb0 * db0) * advb; accd1 += ((float)sb1 * db1) * advb; }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int h0 = (int)((w0[j] >> 4) & 0x0F0F0F0Fu), h1 = (int)((w1[j] >> 4) & 0x0F0F0F0Fu);
-            if (!Q41) { h0 = (int)__vsub4((unsigned)h0, 0x08080808u); h1 = (int)__vsub4((unsigned)h1, 0x08080808u); }
-            s0 = __dp4a(h0, av[4 + j], s0); s1 = __dp4a(h1, av[4 + j], s1);
-        }
-        if (Q41) {
-            const float asv = as[b];
-            accd0 = fmaf(d0 * adv, (float)s0, accd0); accm0 = fmaf(m0, asv, accm0);
-            accd1 = fmaf(d1 * adv, (float)s1, accd1); accm1 = fmaf(m1, asv, accm1);
-        } else { accd0 += ((float)s0 * d0) * adv; accd1 += ((float)s1 * d1) * adv; }
     }
     r0 = warp_sum(accd0) + warp_sum(accm0);
     r1 = warp_sum(accd1) + warp_sum(accm1);
 }
 
-// Activation staging for the megakernel (Q8_0 / Q8_1 targets), executed by warps 0-7 (256 threads).
-// The F32 input vector is copied L2 -> shared memory with cp.async.cg (no registers held, all chunks in flight, L1
-// bypassed because other CTAs wrote it earlier in this launch); both passes (RMS partial sums, quantisation) then read
-// shared memory, so the routine is register-light and the megakernel has no spills.  Thread t owns the float4s at
-// elements 2048k + 4t and 2048k + 1024 + 4t: its RMS partials are canonical partials t and t + 256 (oracle.cpp
-// op_rms_norm_mul, same as k::stage_act); a 32-weight quant block is covered by 8 consecutive lanes, so amax / sum need 3
-// shuffle steps.  Quantisation is order-free (max, integer sums): identical bytes to k::stage_act.
-constexpr int kStageMaxK = 7;  // up to 14336 columns
-// quantise the float4 at elements i..i+3 (8 consecutive lanes cover one 32-weight block) into the split-plane Q8 layout
+// Activation staging for the megakernel (Q8_0 / Q8_1 targets).  The F32 input vector is read straight from L2 into registers
+// (ld.global.cg: other CTAs wrote it earlier in this launch), all loads of a thread in flight at once, and quantised from there
+// into the split-plane Q8 layout in shared memory.  A 32-weight quant block is covered by 8 consecutive lanes, so amax / sum need
+// 3 shuffle steps; quantisation is order-free (max, integer sums): identical bytes to k::stage_act.
+constexpr int kNormItems = 5;   // RMS-normed inputs (warps 0-7): n_embd <= 256 threads x 4 floats x 5 = 5120
+constexpr int kPlainItems = 8;  // un-normed inputs (all 15 consumer warps): cols <= 480 x 4 x 8 = 15360
+// quantise the float4 at elements i..i+3; `valid` is shared by the 8 lanes of a block (all lanes run the shuffles)
 template <int ACT>
-__device__ __forceinline__ void quant_item(const float4 a, int i, int cols, unsigned char *sm) {
+__device__ __forceinline__ void quant_item(const float4 a, int i, bool valid, int cols, unsigned char *sm) {
     unsigned char *qs = sm; float *d = (float *)(sm + cols); float *s = d + cols / 32;
     const int j8 = threadIdx.x & 7, b = i >> 5;
     float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
@@ -143,81 +155,74 @@ __device__ __forceinline__ void quant_item(const float4 a, int i, int cols, unsi
     const float dd = amax / 127.f;
     const float id = amax != 0.0f ? 127.f / amax : 0.0f;
     const int q0 = __float2int_rn(a.x * id), q1 = __float2int_rn(a.y * id), q2 = __float2int_rn(a.z * id), q3 = __float2int_rn(a.w * id);
-    *(unsigned *)(qs + (j8 < 4 ? 0 : cols / 2) + b * 16 + (j8 & 3) * 4) = (unsigned)(q0 & 0xff) | ((unsigned)(q1 & 0xff) << 8) | ((unsigned)(q2 & 0xff) << 16) | ((unsigned)(q3 & 0xff) << 24);
     int sum = (q0 + q1) + (q2 + q3);
     sum += __shfl_xor_sync(0xffffffffu, sum, 4); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    if (j8 == 0) {
-        if (ACT == ACT_Q8_0) { d[b] = __half2float(__float2half_rn(dd)); s[b] = 0.f; }
-        else { d[b] = dd; s[b] = dd * (float)sum; }
+    if (valid) {
+        *(unsigned *)(qs + (j8 < 4 ? 0 : cols / 2) + b * 16 + (j8 & 3) * 4) = (unsigned)(q0 & 0xff) | ((unsigned)(q1 & 0xff) << 8) | ((unsigned)(q2 & 0xff) << 16) | ((unsigned)(q3 & 0xff) << 24);
+        if (j8 == 0) {
+            if (ACT == ACT_Q8_0) { d[b] = __half2float(__float2half_rn(dd)); s[b] = (float)sum; }  // integer sum of the block (exact), see dot2_q4_slot
+            else { d[b] = dd; s[b] = dd * (float)sum; }
+        }
     }
 }
-// un-normed inputs (wo, down): the vector streams L2 -> shared window `xs` -> quantiser.  The window is split into two
-// halves of `half_items` float4 per thread, filled by alternating cp.async groups, so copy latency is paid once.
+// un-normed inputs (wo, down), all 480 consumer threads: thread t owns the float4s 480 k + t
 template <int ACT>
-__device__ __forceinline__ void stage_plain_mega(const float *__restrict__ x, int cols, float *xs, int half_items, unsigned char *sm) {
-    const int tid = threadIdx.x;  // tid < 256
-    const int n_items = (cols + 1023) >> 10, n_groups = (n_items + half_items - 1) / half_items;
-    auto issue = [&](int g) {
-        if (g < n_groups) {
-            float *dst = xs + (g & 1) * half_items * 1024;
-            for (int u = 0; u < half_items; ++u) {
-                const int i = 1024 * (g * half_items + u) + 4 * tid;
-                if (i < cols) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + 1024 * u + 4 * tid)), "l"(x + i) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");  // (possibly empty) group keeps the wait_group accounting uniform
-    };
-    issue(0); issue(1);
-    for (int g = 0; g < n_groups; ++g) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");  // group g has landed (each thread reads only its own copies)
-        const float *src = xs + (g & 1) * half_items * 1024;
-#pragma unroll 1
-        for (int u = 0; u < half_items; ++u) {
-            const int i = 1024 * (g * half_items + u) + 4 * tid;
-            if (i < cols) quant_item<ACT>(*(const float4 *)(src + 1024 * u + 4 * tid), i, cols, sm);  // warp-uniform predicate
-        }
-        issue(g + 2);
+__device__ __forceinline__ void stage_plain_mega(const float *__restrict__ x, int cols, unsigned char *sm) {
+    const int tid = threadIdx.x;  // tid < 480
+    float4 xv[kPlainItems];
+#pragma unroll
+    for (int it = 0; it < kPlainItems; ++it) {
+        const int i = 4 * (tid + kConsumerThreads * it);
+        xv[it] = i < cols ? __ldcg((const float4 *)(x + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int it = 0; it < kPlainItems; ++it) {
+        const int i = 4 * (tid + kConsumerThreads * it);
+        if (4 * kConsumerThreads * it < cols) quant_item<ACT>(xv[it], i, i < cols, cols, sm);  // (CTA-uniform predicate)
+    }
+}
+// RMS-normed inputs (n_embd wide), warps 0-7.  Thread t owns the float4s at elements 1024 it + 4 t: its RMS partials are the
+// canonical partials t (even it) and t + 256 (odd it) of oracle.cpp op_rms_norm_mul, same as k::stage_act.  The norm weights
+// `nw` were fetched into registers BEFORE the grid barrier (they are static), so only the activations are on the critical path.
+__device__ __forceinline__ void load_norm_weights(const float *__restrict__ nw, int cols, float4 (&w)[kNormItems]) {
+#pragma unroll
+    for (int it = 0; it < kNormItems; ++it) {
+        const int i = 1024 * it + 4 * (int)threadIdx.x;
+        w[it] = i < cols ? __ldg((const float4 *)(nw + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 template <int ACT>
-__device__ __forceinline__ void stage_act_mega(const float *__restrict__ x, const float *__restrict__ nw, int cols, float *xs, unsigned char *sm, double *red) {
+__device__ __forceinline__ void stage_norm_mega(const float *__restrict__ x, const float4 (&w)[kNormItems], int cols, unsigned char *sm, double *red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // tid < 256
-    const int nitem = cols >> 10;  // float4 items per thread (tail handled by i < cols); this routine serves cols = n_embd <= 5120
-    for (int it = 0; it <= nitem; ++it) {
+    float4 xv[kNormItems];
+#pragma unroll
+    for (int it = 0; it < kNormItems; ++it) {
         const int i = 1024 * it + 4 * tid;
-        if (i < cols) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(xs + i)), "l"(x + i) : "memory");
-            if (nw) asm volatile("prefetch.global.L1 [%0];" ::"l"(nw + i));
+        xv[it] = i < cols ? __ldcg((const float4 *)(x + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double ssa = 0.0, ssb = 0.0;
+#pragma unroll
+    for (int it = 0; it < kNormItems; ++it) {
+        if (1024 * it + 4 * tid < cols) {
+            const float4 a = xv[it];
+            if (it & 1) { ssb += (double)(a.x * a.x); ssb += (double)(a.y * a.y); ssb += (double)(a.z * a.z); ssb += (double)(a.w * a.w); }
+            else        { ssa += (double)(a.x * a.x); ssa += (double)(a.y * a.y); ssa += (double)(a.z * a.z); ssa += (double)(a.w * a.w); }
         }
     }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    // each thread reads back only what it copied itself, so no barrier is needed before the passes below
-    float scale = 1.0f;
-    if (nw) {
-        double ssa = 0.0, ssb = 0.0;
-        for (int k = 0; 2048 * k < cols; ++k) {
-            const int ia = 2048 * k + 4 * tid, ib = ia + 1024;
-            if (ia < cols) { const float4 a = *(const float4 *)(xs + ia); ssa += (double)(a.x * a.x); ssa += (double)(a.y * a.y); ssa += (double)(a.z * a.z); ssa += (double)(a.w * a.w); }
-            if (ib < cols) { const float4 b = *(const float4 *)(xs + ib); ssb += (double)(b.x * b.x); ssb += (double)(b.y * b.y); ssb += (double)(b.z * b.z); ssb += (double)(b.w * b.w); }
-        }
-        ssa = warp_sum(ssa); ssb = warp_sum(ssb);
-        cta_sync<true>();
-        if (lane == 0) { red[warp] = ssa; red[warp + 8] = ssb; }
-        cta_sync<true>();
-        if (warp == 0) { double t = lane < 16 ? red[lane] : 0.0; t = warp_sum(t); if (lane == 0) red[32] = t; }
-        cta_sync<true>();
-        const double tot = red[32];
-        const float mean = (float)(tot / (double)cols);
-        scale = 1.0f / sqrtf(mean + 1e-6f);
-    }
-#pragma unroll 2
-    for (int it = 0; it <= nitem; ++it) {
+    ssa = warp_sum(ssa); ssb = warp_sum(ssb);
+    if (lane == 0) { red[warp] = ssa; red[warp + 8] = ssb; }
+    cta_sync<true>();
+    if (warp == 0) { double t = lane < 16 ? red[lane] : 0.0; t = warp_sum(t); if (lane == 0) red[32] = t; }
+    cta_sync<true>();
+    const double tot = red[32];
+    const float mean = (float)(tot / (double)cols);
+    const float scale = 1.0f / sqrtf(mean + 1e-6f);
+#pragma unroll
+    for (int it = 0; it < kNormItems; ++it) {
         const int i = 1024 * it + 4 * tid;
-        if (i < cols) {  // warp-uniform: cols is a multiple of 128
-            float4 a = *(const float4 *)(xs + i);
-            if (nw) { const float4 w4 = __ldg((const float4 *)(nw + i)); a = make_float4((a.x * scale) * w4.x, (a.y * scale) * w4.y, (a.z * scale) * w4.z, (a.w * scale) * w4.w); }
-            quant_item<ACT>(a, i, cols, sm);
+        if (1024 * it < cols) {  // (CTA-uniform predicate)
+            const float4 a = xv[it], w4 = w[it];
+            quant_item<ACT>(make_float4((a.x * scale) * w4.x, (a.y * scale) * w4.y, (a.z * scale) * w4.z, (a.w * scale) * w4.w), i, i < cols, cols, sm);
         }
     }
 }
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
     __shared__ float part[16 * 128];
     constexpr int ACT = act_of(WT);
     constexpr bool Q41 = WT == GG_Q4_1;
-    unsigned char *ring = smem, *xsb = smem + (size_t)P.n_slots * P.slot_bytes, *actb = xsb + P.xs_bytes;
+    unsigned char *ring = smem, *actb = smem + (size_t)P.n_slots * P.slot_bytes;  // actb doubles as the attention op's scratch
     uint64_t *full = (uint64_t *)(actb + P.act_bytes), *empty = full + P.n_slots;
     MegaOp *ops = (MegaOp *)(empty + P.n_slots);                 // the op program, copied once from global memory
     volatile unsigned *fill_count = (volatile unsigned *)(ops + P.n_ops);  // slots issued so far (read by the L2-prefetch lane)
@@ -298,6 +303,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         const MegaOp op = ops[oi];
         long long *tr = (P.trace && tid == 0 && (cta == 0 || cta == G - 1)) ? P.trace + ((size_t)(cta == 0 ? 0 : 1) * P.n_ops + oi) * 8 : nullptr;
         if (tr) { tr[0] = clock64(); tr[2] = 0; tr[4] = 0; tr[5] = 0; tr[6] = 0; }
+        float4 nwr[kNormItems];  // RMSNorm weights of this op: static data, fetched before the barrier wait
+        if (op.norm_w && tid < 256) load_norm_weights(op.norm_w, op.cols, nwr);
         if (oi > 0) { bar_target += (unsigned)G; grid_barrier(P.barrier, bar_target); }
         if (tr) tr[1] = clock64();
 
@@ -310,7 +317,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
         if (op.kind == OP_ATTN) {
             if (cta < P.n_head && tid < 256) {  // one head per CTA, 256 threads (named barrier 1)
                 const size_t lo = (size_t)op.layer * P.n_ctx * P.E;
-                attention_mega(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, P.E, P.n_ctx, P.kq_scale, P.tab_exp, xsb, red, redf, qh, part);
+                attention_mega(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, P.E, P.n_ctx, P.kq_scale, P.tab_exp, actb, red, redf, qh, part);
             }
             continue;
         }
@@ -327,15 +334,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
 
         // ---- matvec ops -------------------------------------------------------------------------------------
         const float *src = op.kind == OP_WO ? P.att : op.kind == OP_DOWN ? P.act : P.x;
-        if (tid < 256) {
-            if (op.norm_w) stage_act_mega<ACT>(src, op.norm_w, op.cols, (float *)xsb, actb, red);
-            else stage_plain_mega<ACT>(src, op.cols, (float *)xsb, max(1, P.xs_bytes >> 13), actb);
-        }
+        if (op.norm_w) { if (tid < 256) stage_norm_mega<ACT>(src, nwr, op.cols, actb, red); }
+        else stage_plain_mega<ACT>(src, op.cols, actb);
         consumer_sync();
         if (tr) tr[2] = clock64();
         const int nb = op.cols / 32;
         const int lo = (int)((long long)cta * op.n_su / G), hi = (int)((long long)(cta + 1) * op.n_su / G);
         unsigned long long best = 0ull;
+        // gate/up epilogue (lane 0): the SiLU table lookup of a unit is issued after its dot product and consumed after the NEXT
+        // unit's, so its L2 latency is off the warp's critical path
+        __half pend_h = __ushort_as_half((unsigned short)0); float pend_up = 0.f; int pend_i = -1;
         // op.n_warps consumer warps work on this op (the rest of the ring must stay free for fills in flight).  With
         // n_warps * sps <= n_slots a warp can never wait on a slot that is two fills behind: it consumed unit su - n_warps
         // itself, so the previous fill of its slot has happened and the mbarrier parity is unambiguous.
@@ -347,8 +355,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
             int s1 = s0 + 1; unsigned ph1 = ph0;
             if (s1 == S) { s1 = 0; ph1 ^= 1u; }
             const int r0 = su * 2;
-            float2 rs = make_float2(0.f, 0.f);  // residual rows of this pair, fetched before the wait
+            float2 rs = make_float2(0.f, 0.f);  // residual rows of this pair / RoPE (cos, sin) of this pair: fetched before the wait
             if (op.kind == OP_WO || op.kind == OP_DOWN) rs = __ldcg((const float2 *)(P.x + r0));
+            else if (op.kind == OP_QKV && r0 < 2 * P.E) rs = __ldg(&P.rope[(size_t)pos * 64 + ((r0 % P.E) % 128) / 2]);
             const long long tw0 = tr ? clock64() : 0;
             mb_wait(&full[s0], ph0);
             if (op.sps == 2) mb_wait(&full[s1], ph1);
@@ -367,14 +376,17 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
                         const size_t kvo = ((size_t)op.layer * P.n_ctx + pos) * E + rr;
                         if (partn == 2) { *(__half2 *)(P.vcache + kvo) = __floats2half2_rn(v0, v1); }
                         else {
-                            const float2 cs = P.rope[(size_t)pos * 64 + (rr % 128) / 2];
+                            const float2 cs = rs;
                             const float o0 = v0 * cs.x - v1 * cs.y, o1 = v0 * cs.y + v1 * cs.x;
                             if (partn == 0) *(float2 *)(P.q + rr) = make_float2(o0, o1);
                             else *(__half2 *)(P.kcache + kvo) = __floats2half2_rn(o0, o1);
                         }
                     } break;
                     case OP_WO: case OP_DOWN: *(float2 *)(P.x + r0) = make_float2(v0 + rs.x, v1 + rs.y); break;
-                    case OP_GATEUP: P.act[r0 >> 1] = lut_f16(P.tab_silu, v0) * v1; break;
+                    case OP_GATEUP:
+                        if (pend_i >= 0) P.act[pend_i] = __half2float(pend_h) * pend_up;
+                        pend_h = P.tab_silu[__half_as_ushort(__float2half_rn(v0))]; pend_up = v1; pend_i = r0 >> 1;
+                        break;
                     default: {  // OP_OUTPUT
                         P.logits[r0] = v0;
                         const unsigned long long k0 = argmax_key(v0, r0);
@@ -385,6 +397,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
             }
             s0 += stepn; while (s0 >= S) { s0 -= S; ph0 ^= 1u; }
         }
+        if (lane == 0 && pend_i >= 0) P.act[pend_i] = __half2float(pend_h) * pend_up;
         if (op.kind == OP_OUTPUT && lane == 0 && best) atomicMax(&P.state->argmax_key, best);
         n_base += (unsigned)(hi - lo) * (unsigned)op.sps;
         if (tr) tr[3] = clock64();  // (thread 0 = warp 0 only; other warps may still be consuming)

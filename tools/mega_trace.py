@@ -1,6 +1,7 @@
 """Per-op timeline of the decode megakernel (needs MINIGPT4_B200_MEGA_TRACE=1): prints where a token's time goes."""
 import os, sys, json
-os.environ["MINIGPT4_B200_MEGA_TRACE"] = "1"
+NOTRACE = bool(os.environ.get("NOTRACE"))
+if not NOTRACE: os.environ["MINIGPT4_B200_MEGA_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import minigpt4_cpp_b200 as m
@@ -15,7 +16,8 @@ ctx = ext.llm_load(llm, n_ctx=2048)
 rows = np.random.default_rng(0).standard_normal((32, 4096)).astype(np.float32)
 ext.eval_embd(ctx, rows)
 ids, ms = ext.decode_chain(ctx, 128)
-print("chain ms/token", ms / 128)
+print("chain ms/token", ms / 128, "(trace off)" if NOTRACE else "(trace on)")
+if NOTRACE: sys.exit(0)
 tr = ext.mega_trace(ctx).astype(np.float64)  # last launch
 names = {0: "embed", 1: "qkv", 2: "attn", 3: "wo", 4: "gate_up", 5: "down", 6: "output", 7: "final"}
 kinds = [0] + [1, 2, 3, 4, 5] * NL + [6, 7]
