@@ -452,7 +452,8 @@ bool LlamaDevice::build_mega() {
 }
 const void *LlamaDevice::mega_fn() const {
     using namespace mk;
-    return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1> : (const void *)decode_megakernel<GG_Q4_0>;
+    if (mega_trace_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1, true> : (const void *)decode_megakernel<GG_Q4_0, true>;
+    return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1, false> : (const void *)decode_megakernel<GG_Q4_0, false>;
 }
 void LlamaDevice::launch_mega() {
     using namespace mk;

@@ -69,6 +69,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
+// first unit (row pair) of CTA `cta`: units are split evenly over the grid (n_su * G < 2^31: host-checked)
+__device__ __forceinline__ int unit_begin(int cta, int n_su, int G) { return (int)((unsigned)cta * (unsigned)n_su / (unsigned)G); }
+
 // all consumer threads of all CTAs; `target` = number of arrivals that complete this barrier (monotonic counter)
 __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
     consumer_sync();  // all consumer warps of this CTA have issued their global writes (CTA-scope ordering)
@@ -98,9 +101,10 @@ __device__ __forceinline__ int q4_block_idot(const uint4 q, const int4 lo, const
 }
 
 // Two rows of a shared-memory ring slot against the staged activation vector.  Same per-lane block order and the same
-// float arithmetic as k::dot2_q4 (lane l: blocks l, l+32, ... increasing; butterfly reductions).  Two blocks per row are in
-// flight per iteration (8 independent dp4a chains); Q4_0's "-8" is applied as  sum (q-8) a = sum q a - 8 sum a  with the
-// integer activation sum the staging pass leaves in the `s` plane.
+// float arithmetic as k::dot2_q4 (lane l: blocks l, l+32, ... increasing; butterfly reductions), one block per iteration
+// (4 independent dp4a chains; shared-memory latency is short and the other warps of the sub-partition fill the gaps, so deeper
+// unrolling buys nothing and costs registers).  Q4_0's "-8" is applied as  sum (q-8) a = sum q a - 8 sum a  with the integer
+// activation sum the staging pass leaves in the `s` plane.
 template <bool Q41>
 __device__ __forceinline__ void dot2_q4_slot(const unsigned char *row0, const unsigned char *row1, int nb, int cols, const unsigned char *act, int lane, float &r0, float &r1) {
     const uint4 *qs0 = (const uint4 *)row0, *qs1 = (const uint4 *)row1;
@@ -109,30 +113,20 @@ __device__ __forceinline__ void dot2_q4_slot(const unsigned char *row0, const un
     const float *ad = (const float *)(act + cols), *as = ad + nb;
     float accd0 = 0.f, accd1 = 0.f, accm0 = 0.f, accm1 = 0.f;
 #pragma unroll 1
-    for (int b = lane; b < nb; b += 64) {
-        const bool two = b + 32 < nb;
-        const int c = two ? b + 32 : b;  // (clamped: the second block's loads stay in bounds, its contribution is dropped)
-        const uint4 qa0 = qs0[b], qa1 = qs1[b], qb0 = qs0[c], qb1 = qs1[c];
-        const int4 la = alo[b], ha = ahi[b], lb = alo[c], hb = ahi[c];
-        const float adva = ad[b], advb = ad[c], asva = as[b], asvb = as[c];
-        int sa0 = q4_block_idot(qa0, la, ha), sa1 = q4_block_idot(qa1, la, ha);
-        int sb0 = q4_block_idot(qb0, lb, hb), sb1 = q4_block_idot(qb1, lb, hb);
+    for (int b = lane; b < nb; b += 32) {
+        const uint4 q0 = qs0[b], q1 = qs1[b];
+        const int4 la = alo[b], ha = ahi[b];
+        const float adv = ad[b], asv = as[b];
+        int s0 = q4_block_idot(q0, la, ha), s1 = q4_block_idot(q1, la, ha);
         if (Q41) {
-            const float2 fa0 = __half22float2(((const __half2 *)sc0)[b]), fa1 = __half22float2(((const __half2 *)sc1)[b]);
-            const float2 fb0 = __half22float2(((const __half2 *)sc0)[c]), fb1 = __half22float2(((const __half2 *)sc1)[c]);
-            accd0 = fmaf(fa0.x * adva, (float)sa0, accd0); accm0 = fmaf(fa0.y, asva, accm0);
-            accd1 = fmaf(fa1.x * adva, (float)sa1, accd1); accm1 = fmaf(fa1.y, asva, accm1);
-            if (two) {
-                accd0 = fmaf(fb0.x * advb, (float)sb0, accd0); accm0 = fmaf(fb0.y, asvb, accm0);
-                accd1 = fmaf(fb1.x * advb, (float)sb1, accd1); accm1 = fmaf(fb1.y, asvb, accm1);
-            }
+            const float2 f0 = __half22float2(((const __half2 *)sc0)[b]), f1 = __half22float2(((const __half2 *)sc1)[b]);
+            accd0 = fmaf(f0.x * adv, (float)s0, accd0); accm0 = fmaf(f0.y, asv, accm0);
+            accd1 = fmaf(f1.x * adv, (float)s1, accd1); accm1 = fmaf(f1.y, asv, accm1);
         } else {
-            const float da0 = __half2float(((const __half *)sc0)[b]), da1 = __half2float(((const __half *)sc1)[b]);
-            const float db0 = __half2float(((const __half *)sc0)[c]), db1 = __half2float(((const __half *)sc1)[c]);
-            const int ia = 8 * (int)asva, ib = 8 * (int)asvb;
-            sa0 -= ia; sa1 -= ia; sb0 -= ib; sb1 -= ib;
-            accd0 += ((float)sa0 * da0) * adva; accd1 += ((float)sa1 * da1) * adva;
-            if (two) { accd0 += ((float)sb0 * db0) * advb; accd1 += ((float)sb1 * db1) * advb; }
+            const float d0 = __half2float(((const __half *)sc0)[b]), d1 = __half2float(((const __half *)sc1)[b]);
+            const int i8 = 8 * (int)asv;
+            s0 -= i8; s1 -= i8;
+            accd0 += ((float)s0 * d0) * adv; accd1 += ((float)s1 * d1) * adv;
         }
     }
     r0 = warp_sum(accd0) + warp_sum(accm0);
@@ -233,19 +227,175 @@ __device__ __noinline__ void attention_mega(const float *q, const __half *kc, co
     attention_head<true>(q, kc, vc, out, pos, h, 0, E, n_ctx, kq_scale, tab_exp, dyn, red, redf, qh, part);
 }
 
-template <int WT>
-__global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaParams P) {
+// shared memory carve-up (dynamic): [ring][act: staged Q8 activations / attention scratch][full mbarriers][empty mbarriers][ops][fill_count]
+struct MegaSmem { unsigned char *ring, *actb; uint64_t *full, *empty; MegaOp *ops; volatile unsigned *fill_count; };
+__device__ __forceinline__ MegaSmem carve_smem(const MegaParams &P) {
     extern __shared__ __align__(128) unsigned char smem[];
+    MegaSmem m;
+    m.ring = smem; m.actb = smem + (size_t)P.n_slots * P.slot_bytes;
+    m.full = (uint64_t *)(m.actb + P.act_bytes); m.empty = m.full + P.n_slots;
+    m.ops = (MegaOp *)(m.empty + P.n_slots);                       // the op program, copied once from global memory
+    m.fill_count = (volatile unsigned *)(m.ops + P.n_ops);         // slots issued so far (read by the L2-prefetch lane)
+    return m;
+}
+
+// The matvec phase of one op for one consumer warp: for each of its row pairs wait for the ring slot(s), dot, release, epilogue.
+// One out-of-line instance per op kind: each gets its own register allocation (the unit loop must not spill - with ~215 KB of
+// shared memory the L1 is a few KB, so a spill is an L2 round trip) and only its own epilogue.
+//   n_base = ring fill number of this CTA's first unit of the op.  With n_warps * sps <= n_slots a warp can never wait on a slot
+//   that is two fills behind (it consumed unit su - n_warps itself), so the mbarrier parity is unambiguous.
+template <bool Q41, int KIND, bool TRACE>
+__device__ __forceinline__ unsigned consume_units(const MegaParams &P, int oi, unsigned n_base, int pos, long long *tr) {
+    const MegaSmem m = carve_smem(P);
+    const MegaOp &op = m.ops[oi];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int W = op.n_warps, sps = op.sps;
+    const int lo = unit_begin(cta, op.n_su, G), hi = unit_begin(cta + 1, op.n_su, G);
+    const unsigned n_next = n_base + (unsigned)(hi - lo) * (unsigned)sps;  // fill number of the next op's first unit
+    if (warp >= W) return n_next;
+    const int cols = op.cols, nb = cols >> 5, S = P.n_slots, stepn = W * sps;
+    const unsigned rb = (unsigned)op.row_bytes, slot_bytes = (unsigned)P.slot_bytes;
+    const unsigned n0 = n_base + (unsigned)(warp * sps);
+    int s0 = (int)(n0 % (unsigned)S);          // ring slot of this warp's current unit ...
+    unsigned ph0 = (n0 / (unsigned)S) & 1u;    // ... and its fill parity (advanced incrementally)
+    unsigned long long best = 0ull;
+    // gate/up epilogue (lane 0): the SiLU table lookup of a unit is issued after its dot product and consumed after the NEXT
+    // unit's, so its L2 latency is off the warp's critical path
+    __half pend_h = __ushort_as_half((unsigned short)0); float pend_up = 0.f; int pend_i = -1;
+    for (int su = lo + warp; su < hi; su += W) {
+        int s1 = s0 + 1; unsigned ph1 = ph0;
+        if (s1 == S) { s1 = 0; ph1 ^= 1u; }
+        const int r0 = su * 2;
+        float2 rs = make_float2(0.f, 0.f);  // residual rows of this pair / RoPE (cos, sin) of this pair: fetched before the wait
+        if (KIND == OP_WO || KIND == OP_DOWN) rs = __ldcg((const float2 *)(P.x + r0));
+        if (KIND == OP_QKV) { if (r0 < 2 * P.E) rs = __ldg(&P.rope[(size_t)pos * 64 + ((r0 % P.E) % 128) / 2]); }
+        long long tw0 = 0, tw1 = 0, tw2 = 0;
+        if (TRACE && tr) tw0 = clock64();
+        mb_wait(&m.full[s0], ph0);
+        if (sps == 2) mb_wait(&m.full[s1], ph1);
+        if (TRACE && tr) tw1 = clock64();
+        const unsigned char *row0 = m.ring + (size_t)s0 * slot_bytes;
+        const unsigned char *row1 = sps == 2 ? m.ring + (size_t)s1 * slot_bytes : row0 + rb;
+        float v0, v1;
+        dot2_q4_slot<Q41>(row0, row1, nb, cols, m.actb, lane, v0, v1);
+        if (TRACE && tr) { tw2 = clock64(); tr[4] += tw1 - tw0; tr[5] += tw2 - tw1; tr[6] += 1; }
+        if (lane == 0) {
+            mb_arrive(&m.empty[s0]);
+            if (sps == 2) mb_arrive(&m.empty[s1]);
+            if (KIND == OP_QKV) {
+                const int E = P.E, partn = r0 / E, rr = r0 % E;
+                const size_t kvo = ((size_t)op.layer * P.n_ctx + pos) * E + rr;
+                if (partn == 2) { *(__half2 *)(P.vcache + kvo) = __floats2half2_rn(v0, v1); }
+                else {
+                    const float2 cs = rs;
+                    const float o0 = v0 * cs.x - v1 * cs.y, o1 = v0 * cs.y + v1 * cs.x;
+                    if (partn == 0) *(float2 *)(P.q + rr) = make_float2(o0, o1);
+                    else *(__half2 *)(P.kcache + kvo) = __floats2half2_rn(o0, o1);
+                }
+            } else if (KIND == OP_WO || KIND == OP_DOWN) {
+                *(float2 *)(P.x + r0) = make_float2(v0 + rs.x, v1 + rs.y);
+            } else if (KIND == OP_GATEUP) {
+                if (pend_i >= 0) P.act[pend_i] = __half2float(pend_h) * pend_up;
+                pend_h = P.tab_silu[__half_as_ushort(__float2half_rn(v0))]; pend_up = v1; pend_i = r0 >> 1;
+            } else {  // OP_OUTPUT
+                P.logits[r0] = v0;
+                const unsigned long long k0 = argmax_key(v0, r0);
+                best = best > k0 ? best : k0;
+                if (r0 + 1 < P.n_vocab) { P.logits[r0 + 1] = v1; const unsigned long long k1 = argmax_key(v1, r0 + 1); best = best > k1 ? best : k1; }
+            }
+        }
+        s0 += stepn; while (s0 >= S) { s0 -= S; ph0 ^= 1u; }
+        if (TRACE && tr) tr[7] += clock64() - tw2;
+    }
+    if (KIND == OP_GATEUP) { if (lane == 0 && pend_i >= 0) P.act[pend_i] = __half2float(pend_h) * pend_up; }
+    if (KIND == OP_OUTPUT) { if (lane == 0 && best) atomicMax(&P.state->argmax_key, best); }
+    return n_next;
+}
+
+// The front half of a matvec op for the consumer warps: fetch the (static) RMSNorm weights, pass the grid barrier that makes the
+// previous op's output visible, stage the input vector as Q8 blocks in shared memory.
+template <int ACT, bool TRACE>
+__device__ __forceinline__ void stage_op(const MegaParams &P, int oi, unsigned bar_target, long long *tr) {
+    __shared__ double red[34];
+    const MegaSmem m = carve_smem(P);
+    const MegaOp &op = m.ops[oi];
+    const int tid = threadIdx.x, cols = op.cols, kind = op.kind;
+    const float *nw = op.norm_w;
+    float4 nwr[kNormItems];
+    if (nw && tid < 256) load_norm_weights(nw, cols, nwr);
+    grid_barrier(P.barrier, bar_target);
+    if (TRACE && tr) tr[1] = clock64();
+    const float *src = kind == OP_WO ? P.att : kind == OP_DOWN ? P.act : P.x;
+    if (nw) { if (tid < 256) stage_norm_mega<ACT>(src, nwr, cols, m.actb, red); }
+    else stage_plain_mega<ACT>(src, cols, m.actb);
+    consumer_sync();
+    if (TRACE && tr) tr[2] = clock64();
+}
+
+// The producer warp: lane 0 fills the shared-memory ring with cp.async.bulk (blocks when the ring is full); lane 1 walks the same
+// slot sequence up to l2_ahead slots further and only asks L2 to fetch (cp.async.bulk.prefetch.L2), so HBM keeps streaming while
+// the consumers sit in a grid barrier / staging / the attention op.  Per-op fields are held in registers.
+__device__ __noinline__ void producer_loop(const MegaParams &P) {
+    const MegaSmem m = carve_smem(P);
+    unsigned char *const ring = m.ring;
+    uint64_t *const full = m.full, *const empty = m.empty;
+    const MegaOp *const ops = m.ops;
+    volatile unsigned *const fill_count = m.fill_count;
+    const int lane = threadIdx.x & 31, G = (int)gridDim.x, cta = (int)blockIdx.x;
+    if (lane == 0) {
+        unsigned n = 0, s = 0, ph = 0;  // fill number, its ring slot and phase parity (running counters: no div/mod per slot)
+        for (int oi = 0; oi < P.n_ops; ++oi) {
+            const unsigned char *w = ops[oi].w;
+            if (!w) continue;
+            const int n_su = ops[oi].n_su, sps = ops[oi].sps;
+            const unsigned rb = (unsigned)ops[oi].row_bytes, bytes = sps == 1 ? 2u * rb : rb;
+            const int lo = unit_begin(cta, n_su, G), hi = unit_begin(cta + 1, n_su, G);
+            const unsigned char *src = w + (size_t)lo * 2 * rb;
+            for (int c = (hi - lo) * sps; c > 0; --c, src += bytes) {
+                mb_wait(&empty[s], ph ^ 1u);
+                mb_expect_tx(&full[s], bytes);
+                bulk_g2s(ring + (size_t)s * P.slot_bytes, src, bytes, &full[s]);
+                *fill_count = ++n;
+                if (++s == (unsigned)P.n_slots) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (lane == 1 && P.l2_ahead > 0) {
+        unsigned n = 0;
+        for (int oi = 0; oi < P.n_ops; ++oi) {
+            const unsigned char *w = ops[oi].w;
+            if (!w) continue;
+            const int n_su = ops[oi].n_su, sps = ops[oi].sps;
+            const unsigned rb = (unsigned)ops[oi].row_bytes;
+            const int lo = unit_begin(cta, n_su, G), hi = unit_begin(cta + 1, n_su, G);
+            const unsigned char *src = w + (size_t)lo * 2 * rb;
+            for (int su = lo; su < hi; ++su, n += (unsigned)sps, src += 2 * rb) {
+                while ((int)(n - *fill_count) >= P.l2_ahead) __nanosleep(200);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(2u * rb) : "memory");
+            }
+        }
+    }
+}
+
+// token embedding row -> x (dequantised on the fly), spread over the grid
+__device__ __noinline__ void embed_op(const MegaParams &P) {
+    const int token = __ldcg(&P.state->tokens[0]);
+    const unsigned char *row = P.tok + (size_t)token * P.tok_row_bytes;
+    for (int i = (int)blockIdx.x * kConsumerThreads + (int)threadIdx.x; i < P.E; i += (int)gridDim.x * kConsumerThreads) P.x[i] = dequant_elem(P.tok_type, row, i);
+}
+
+template <int WT, bool TRACE>
+__global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __grid_constant__ MegaParams P) {
     __shared__ double red[34];
     __shared__ float redf[34];
     __shared__ __align__(16) __half qh[128];
     __shared__ float part[16 * 128];
     constexpr int ACT = act_of(WT);
     constexpr bool Q41 = WT == GG_Q4_1;
-    unsigned char *ring = smem, *actb = smem + (size_t)P.n_slots * P.slot_bytes;  // actb doubles as the attention op's scratch
-    uint64_t *full = (uint64_t *)(actb + P.act_bytes), *empty = full + P.n_slots;
-    MegaOp *ops = (MegaOp *)(empty + P.n_slots);                 // the op program, copied once from global memory
-    volatile unsigned *fill_count = (volatile unsigned *)(ops + P.n_ops);  // slots issued so far (read by the L2-prefetch lane)
+    const MegaSmem m = carve_smem(P);
+    unsigned char *const ring = m.ring, *const actb = m.actb;
+    uint64_t *const full = m.full, *const empty = m.empty;
+    MegaOp *const ops = m.ops;
+    volatile unsigned *const fill_count = m.fill_count;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
 
@@ -257,72 +407,29 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
     for (int i = tid; i < P.n_ops * (int)(sizeof(MegaOp) / 16); i += kMegaThreads) ((uint4 *)ops)[i] = ((const uint4 *)P.ops)[i];
     __syncthreads();  // the only CTA-wide barrier; afterwards consumers use named barriers 2 (512 thr) and 1 (256 thr, attention)
 
-    if (warp == kConsumerWarps) {  // ------------------------------ producer ------------------------------
-        // lane 0 fills the shared-memory ring with cp.async.bulk (blocks when the ring is full); lane 1 walks the same slot
-        // sequence kL2Ahead units further and only asks L2 to fetch (cp.async.bulk.prefetch.L2), so HBM keeps streaming while
-        // the consumers sit in a grid barrier / staging / the attention op.  Per-op fields are held in registers.
-        if (lane == 0) {
-            unsigned n = 0, s = 0, ph = 0;  // fill number, its ring slot and phase parity (running counters: no div/mod per slot)
-            for (int oi = 0; oi < P.n_ops; ++oi) {
-                const unsigned char *w = ops[oi].w;
-                if (!w) continue;
-                const int n_su = ops[oi].n_su, sps = ops[oi].sps;
-                const unsigned rb = (unsigned)ops[oi].row_bytes, bytes = sps == 1 ? 2u * rb : rb;
-                const int lo = (int)((long long)cta * n_su / G), hi = (int)((long long)(cta + 1) * n_su / G);
-                const unsigned char *src = w + (size_t)lo * 2 * rb;
-                for (int c = (hi - lo) * sps; c > 0; --c, src += bytes) {
-                    mb_wait(&empty[s], ph ^ 1u);
-                    mb_expect_tx(&full[s], bytes);
-                    bulk_g2s(ring + (size_t)s * P.slot_bytes, src, bytes, &full[s]);
-                    *fill_count = ++n;
-                    if (++s == (unsigned)P.n_slots) { s = 0; ph ^= 1u; }
-                }
-            }
-        } else if (lane == 1 && P.l2_ahead > 0) {
-            unsigned n = 0;
-            for (int oi = 0; oi < P.n_ops; ++oi) {
-                const unsigned char *w = ops[oi].w;
-                if (!w) continue;
-                const int n_su = ops[oi].n_su, sps = ops[oi].sps;
-                const unsigned rb = (unsigned)ops[oi].row_bytes;
-                const int lo = (int)((long long)cta * n_su / G), hi = (int)((long long)(cta + 1) * n_su / G);
-                const unsigned char *src = w + (size_t)lo * 2 * rb;
-                for (int su = lo; su < hi; ++su, n += (unsigned)sps, src += 2 * rb) {
-                    while ((int)(n - *fill_count) >= P.l2_ahead) __nanosleep(200);
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(2u * rb) : "memory");
-                }
-            }
-        }
-        return;
-    }
+    if (warp == kConsumerWarps) { producer_loop(P); return; }
 
     // ------------------------------------ consumers ------------------------------------
+    // The op loop keeps almost nothing live: the phases are out-of-line functions (stage_op, consume_units, attention_mega) that
+    // ptxas gives the registers above the caller's live set - the smaller this loop's state, the more the hot loops get.
     unsigned n_base = 0, bar_target = 0;
     const int pos = __ldcg(&P.state->n_past);  // position of the token being decoded (state only changes in OP_FINAL)
     for (int oi = 0; oi < P.n_ops; ++oi) {
-        const MegaOp op = ops[oi];
-        long long *tr = (P.trace && tid == 0 && (cta == 0 || cta == G - 1)) ? P.trace + ((size_t)(cta == 0 ? 0 : 1) * P.n_ops + oi) * 8 : nullptr;
-        if (tr) { tr[0] = clock64(); tr[2] = 0; tr[4] = 0; tr[5] = 0; tr[6] = 0; }
-        float4 nwr[kNormItems];  // RMSNorm weights of this op: static data, fetched before the barrier wait
-        if (op.norm_w && tid < 256) load_norm_weights(op.norm_w, op.cols, nwr);
-        if (oi > 0) { bar_target += (unsigned)G; grid_barrier(P.barrier, bar_target); }
-        if (tr) tr[1] = clock64();
-
-        if (op.kind == OP_EMBED) {
-            const int token = __ldcg(&P.state->tokens[0]);
-            const unsigned char *row = P.tok + (size_t)token * P.tok_row_bytes;
-            for (int i = cta * kConsumerThreads + tid; i < P.E; i += G * kConsumerThreads) P.x[i] = dequant_elem(P.tok_type, row, i);
-            continue;
-        }
-        if (op.kind == OP_ATTN) {
-            if (cta < P.n_head && tid < 256) {  // one head per CTA, 256 threads (named barrier 1)
-                const size_t lo = (size_t)op.layer * P.n_ctx * P.E;
-                attention_mega(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, P.E, P.n_ctx, P.kq_scale, P.tab_exp, actb, red, redf, qh, part);
-            }
-            continue;
-        }
-        if (op.kind == OP_FINAL) {
-            if (cta == 0 && tid == 0) {
+        const int kind = ops[oi].kind;
+        long long *tr = nullptr;
+        if (TRACE) { if (P.trace && tid == 0 && (cta == 0 || cta == G - 1)) tr = P.trace + ((size_t)(cta == 0 ? 0 : 1) * P.n_ops + oi) * 8; }
+        if (TRACE && tr) { tr[0] = clock64(); tr[2] = 0; tr[4] = 0; tr[5] = 0; tr[6] = 0; tr[7] = 0; }
+        if (oi > 0) bar_target += (unsigned)G;
+        if (kind == OP_EMBED || kind == OP_ATTN || kind == OP_FINAL) {
+            if (oi > 0) grid_barrier(P.barrier, bar_target);
+            if (TRACE && tr) tr[1] = clock64();
+            if (kind == OP_EMBED) embed_op(P);
+            else if (kind == OP_ATTN) {
+                if (cta < P.n_head && tid < 256) {  // one head per CTA, 256 threads (named barrier 1)
+                    const size_t lo = (size_t)ops[oi].layer * P.n_ctx * P.E;
+                    attention_mega(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, P.E, P.n_ctx, P.kq_scale, P.tab_exp, actb, red, redf, qh, part);
+                }
+            } else if (cta == 0 && tid == 0) {
                 DeviceState *st = P.state;
                 const unsigned long long key = __ldcg((const unsigned long long *)&st->argmax_key);
                 const int id = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
@@ -331,76 +438,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const MegaP
             }
             continue;
         }
-
-        // ---- matvec ops -------------------------------------------------------------------------------------
-        const float *src = op.kind == OP_WO ? P.att : op.kind == OP_DOWN ? P.act : P.x;
-        if (op.norm_w) { if (tid < 256) stage_norm_mega<ACT>(src, nwr, op.cols, actb, red); }
-        else stage_plain_mega<ACT>(src, op.cols, actb);
-        consumer_sync();
-        if (tr) tr[2] = clock64();
-        const int nb = op.cols / 32;
-        const int lo = (int)((long long)cta * op.n_su / G), hi = (int)((long long)(cta + 1) * op.n_su / G);
-        unsigned long long best = 0ull;
-        // gate/up epilogue (lane 0): the SiLU table lookup of a unit is issued after its dot product and consumed after the NEXT
-        // unit's, so its L2 latency is off the warp's critical path
-        __half pend_h = __ushort_as_half((unsigned short)0); float pend_up = 0.f; int pend_i = -1;
-        // op.n_warps consumer warps work on this op (the rest of the ring must stay free for fills in flight).  With
-        // n_warps * sps <= n_slots a warp can never wait on a slot that is two fills behind: it consumed unit su - n_warps
-        // itself, so the previous fill of its slot has happened and the mbarrier parity is unambiguous.
-        const int W = op.n_warps;
-        const int S = P.n_slots, stepn = W * op.sps;
-        int s0 = (int)((n_base + (unsigned)(warp * op.sps)) % (unsigned)S);              // ring slot of this warp's current unit ...
-        unsigned ph0 = ((n_base + (unsigned)(warp * op.sps)) / (unsigned)S) & 1u;        // ... and its fill parity (advanced incrementally)
-        for (int su = lo + warp; warp < W && su < hi; su += W) {
-            int s1 = s0 + 1; unsigned ph1 = ph0;
-            if (s1 == S) { s1 = 0; ph1 ^= 1u; }
-            const int r0 = su * 2;
-            float2 rs = make_float2(0.f, 0.f);  // residual rows of this pair / RoPE (cos, sin) of this pair: fetched before the wait
-            if (op.kind == OP_WO || op.kind == OP_DOWN) rs = __ldcg((const float2 *)(P.x + r0));
-            else if (op.kind == OP_QKV && r0 < 2 * P.E) rs = __ldg(&P.rope[(size_t)pos * 64 + ((r0 % P.E) % 128) / 2]);
-            const long long tw0 = tr ? clock64() : 0;
-            mb_wait(&full[s0], ph0);
-            if (op.sps == 2) mb_wait(&full[s1], ph1);
-            const long long tw1 = tr ? clock64() : 0;
-            const unsigned char *row0 = ring + (size_t)s0 * P.slot_bytes;
-            const unsigned char *row1 = op.sps == 2 ? ring + (size_t)s1 * P.slot_bytes : row0 + op.row_bytes;
-            float v0, v1;
-            dot2_q4_slot<Q41>(row0, row1, nb, op.cols, actb, lane, v0, v1);
-            if (tr) { const long long tw2 = clock64(); tr[4] += tw1 - tw0; tr[5] += tw2 - tw1; tr[6] += 1; }
-            if (lane == 0) {
-                mb_arrive(&empty[s0]);
-                if (op.sps == 2) mb_arrive(&empty[s1]);
-                switch (op.kind) {
-                    case OP_QKV: {
-                        const int E = P.E, partn = r0 / E, rr = r0 % E;
-                        const size_t kvo = ((size_t)op.layer * P.n_ctx + pos) * E + rr;
-                        if (partn == 2) { *(__half2 *)(P.vcache + kvo) = __floats2half2_rn(v0, v1); }
-                        else {
-                            const float2 cs = rs;
-                            const float o0 = v0 * cs.x - v1 * cs.y, o1 = v0 * cs.y + v1 * cs.x;
-                            if (partn == 0) *(float2 *)(P.q + rr) = make_float2(o0, o1);
-                            else *(__half2 *)(P.kcache + kvo) = __floats2half2_rn(o0, o1);
-                        }
-                    } break;
-                    case OP_WO: case OP_DOWN: *(float2 *)(P.x + r0) = make_float2(v0 + rs.x, v1 + rs.y); break;
-                    case OP_GATEUP:
-                        if (pend_i >= 0) P.act[pend_i] = __half2float(pend_h) * pend_up;
-                        pend_h = P.tab_silu[__half_as_ushort(__float2half_rn(v0))]; pend_up = v1; pend_i = r0 >> 1;
-                        break;
-                    default: {  // OP_OUTPUT
-                        P.logits[r0] = v0;
-                        const unsigned long long k0 = argmax_key(v0, r0);
-                        best = best > k0 ? best : k0;
-                        if (r0 + 1 < P.n_vocab) { P.logits[r0 + 1] = v1; const unsigned long long k1 = argmax_key(v1, r0 + 1); best = best > k1 ? best : k1; }
-                    } break;
-                }
-            }
-            s0 += stepn; while (s0 >= S) { s0 -= S; ph0 ^= 1u; }
+        // ---- matvec ops: [norm weights -> grid barrier -> stage activations] then [ring slots -> dot -> epilogue] ----
+        stage_op<ACT, TRACE>(P, oi, bar_target, tr);
+        switch (kind) {
+            case OP_QKV:    n_base = consume_units<Q41, OP_QKV, TRACE>(P, oi, n_base, pos, tr); break;
+            case OP_WO:     n_base = consume_units<Q41, OP_WO, TRACE>(P, oi, n_base, pos, tr); break;
+            case OP_GATEUP: n_base = consume_units<Q41, OP_GATEUP, TRACE>(P, oi, n_base, pos, tr); break;
+            case OP_DOWN:   n_base = consume_units<Q41, OP_DOWN, TRACE>(P, oi, n_base, pos, tr); break;
+            default:        n_base = consume_units<Q41, OP_OUTPUT, TRACE>(P, oi, n_base, pos, tr); break;
         }
-        if (lane == 0 && pend_i >= 0) P.act[pend_i] = __half2float(pend_h) * pend_up;
-        if (op.kind == OP_OUTPUT && lane == 0 && best) atomicMax(&P.state->argmax_key, best);
-        n_base += (unsigned)(hi - lo) * (unsigned)op.sps;
-        if (tr) tr[3] = clock64();  // (thread 0 = warp 0 only; other warps may still be consuming)
+        if (TRACE && tr) tr[3] = clock64();  // (thread 0 = warp 0 only; other warps may still be consuming)
     }
 }
 

@@ -28,12 +28,12 @@ for c in range(2):
     print(f"CTA {'0' if c == 0 else 'G-1'}: total {tot:.1f} us")
     agg = {}
     for i, k in enumerate(kinds):
-        start, bar, staged, done, wwait, wdot, wunits, _ = t[i]
+        start, bar, staged, done, wwait, wdot, wunits, wepi = t[i]
         nxt = t[i + 1, 0] if i + 1 < len(kinds) else t[i, 1]
-        a = agg.setdefault(names[k], [0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0])
+        a = agg.setdefault(names[k], [0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0])
         a[0] += 1; a[1] += (bar - start) / mhz
         if staged: a[2] += (staged - bar) / mhz; a[3] += (done - staged) / mhz
-        a[4] += (nxt - start) / mhz; a[5] += wwait / mhz; a[6] += wdot / mhz; a[7] += wunits
+        a[4] += (nxt - start) / mhz; a[5] += wwait / mhz; a[6] += wdot / mhz; a[7] += wunits; a[8] += wepi / mhz
     for k, a in agg.items():
         print(f"  {k:8s} n={a[0]:3d} barrier {a[1]/a[0]:6.2f} us  stage {a[2]/a[0]:6.2f} us  consume {a[3]/a[0]:6.2f} us  total/op {a[4]/a[0]:6.2f} us  sum {a[4]:8.1f} us"
-              f" | warp0: fill-wait {a[5]/a[0]:5.2f} us, dot {a[6]/a[0]:5.2f} us, {a[7]/a[0]:4.1f} units/op")
+              f" | warp0: fill-wait {a[5]/a[0]:5.2f} us, dot {a[6]/a[0]:5.2f} us, epilogue {a[8]/a[0]:5.2f} us, {a[7]/a[0]:4.1f} units/op")
