@@ -400,6 +400,9 @@ bool LlamaDevice::build_mega() {
     const int n_slots = (int)std::min<size_t>(48, (budget - 9216 - act_b - xs_b - ops_b - 1024) / (size_t)slot);  // 9 KB of static shared memory
     if (n_slots < 12) return false;
     const int inflight = getenv("MINIGPT4_B200_INFLIGHT") ? atoi(getenv("MINIGPT4_B200_INFLIGHT")) : 10;  // slots kept free of consumers so that ~bandwidth x latency worth of fills is always in flight
+    // n_ff-wide matrices (down): a CTA's whole share (rows/2/grid row pairs x 2 slots) fits the ring, so every pair can have its own warp and
+    // the op is ONE round of dot products instead of two; the fills behind it come out of L2 (the look-ahead lane keeps running)
+    const int inflight2 = getenv("MINIGPT4_B200_INFLIGHT2") ? atoi(getenv("MINIGPT4_B200_INFLIGHT2")) : 0;
     std::vector<MegaOp> ops;
     auto add = [&](int kind, int layer, const QMat *m, const float *norm) {
         MegaOp o{}; o.kind = kind; o.layer = layer; o.norm_w = norm;
@@ -407,7 +410,7 @@ bool LlamaDevice::build_mega() {
             o.rows = m->rows; o.cols = m->cols; o.row_bytes = m->row_bytes; o.w = (const unsigned char *)m->p0;
             o.sps = 2 * m->row_bytes <= slot ? 1 : 2;
             o.n_su = m->rows / 2;
-            o.n_warps = std::max(1, std::min(kConsumerWarps, (n_slots - inflight) / o.sps));
+            o.n_warps = std::max(1, std::min(kConsumerWarps, (n_slots - (o.sps == 2 ? inflight2 : inflight)) / o.sps));
         }
         ops.push_back(o);
     };
@@ -436,6 +439,7 @@ bool LlamaDevice::build_mega() {
     P->state = state_; P->barrier = mega_barrier_;
     P->trace = nullptr;
     P->l2_ahead = getenv("MINIGPT4_B200_L2_AHEAD") ? atoi(getenv("MINIGPT4_B200_L2_AHEAD")) : 48;
+    P->flags = getenv("MINIGPT4_B200_MEGA_FLAGS") ? atoi(getenv("MINIGPT4_B200_MEGA_FLAGS")) : 1;
     if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, ops.size() * 16 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, ops.size() * 16 * sizeof(long long))); P->trace = mega_trace_; }
     mega_n_ops_ = (int)ops.size();
     mega_params_ = P;

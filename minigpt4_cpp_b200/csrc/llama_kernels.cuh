@@ -522,7 +522,7 @@ template <bool MEGA> __device__ __forceinline__ __half2 ld_kv4(const __half *p) 
     return *(const __half2 *)p;
 }
 // one (head h, token t) of decode/prefill attention; 256 threads; dyn = n_ctx * 6 bytes of shared scratch
-template <bool MEGA>
+template <bool MEGA, int EARLY_V = 12>
 __device__ __forceinline__ void attention_head(const float *__restrict__ q, const __half *__restrict__ kc, const __half *__restrict__ vc, float *__restrict__ out,
                                                int pos, int h, int t, int E, int n_ctx, float kq_scale, const __half *__restrict__ tab_exp,
                                                unsigned char *dyn, double *red, float *redf, __half *qh, float *part /*[16*128]*/) {
@@ -540,8 +540,8 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
             uint4 kv[B];
 #pragma unroll
             for (int u = 0; u < B; ++u) {
-                const int key = kb0 + u * 16 + sub;
-                if (key < nkv) kv[u] = ld_kv16<MEGA>(kc + (size_t)key * E + h * 128 + l16 * 8);
+                const int key = min(kb0 + u * 16 + sub, nkv - 1);  // clamped, unconditional: a predicated load would demote kv[] to local memory
+                kv[u] = ld_kv16<MEGA>(kc + (size_t)key * E + h * 128 + l16 * 8);
             }
             if (!have_q) {
                 const float *qp = q + (size_t)t * E + h * 128 + l16 * 8;
@@ -568,6 +568,14 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
             }
         }
     }
+    // megakernel: the first batch of V rows does not depend on the scores - request it now, so its HBM round trip runs under the
+    // soft-max (three block reductions and a table lookup) instead of after it
+    constexpr int BV = MEGA ? EARLY_V : 1;
+    uint4 vv0[BV];
+    if (MEGA) {
+#pragma unroll
+        for (int u = 0; u < BV; ++u) { const int key = min((tid >> 4) + 16 * u, nkv - 1); vv0[u] = ld_kv16<MEGA>(vc + (size_t)key * E + h * 128 + (tid & 15) * 8); }
+    }
     cta_sync<MEGA>();
     float mx = -INFINITY;
     for (int i = tid; i < nkv; i += 256) mx = fmaxf(mx, sc[i]);
@@ -585,10 +593,24 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
         constexpr int B = 12;
-        for (int key0 = g; key0 < nkv; key0 += 16 * B) {  // batch the V loads (192 keys per pass); the FMA order over keys stays sequential
+        int key0 = g;
+        if (MEGA) {  // the batch requested before the soft-max (keys g, g+16, ...: same sequential FMA order)
+#pragma unroll
+            for (int u = 0; u < BV; ++u) {
+                const int key = g + 16 * u;
+                if (key < nkv) {
+                    const float p = __half2float(ph[key]);
+                    const __half2 *v2 = (const __half2 *)&vv0[u];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float2 v = __half22float2(v2[j]); acc[2 * j] = fmaf(v.x, p, acc[2 * j]); acc[2 * j + 1] = fmaf(v.y, p, acc[2 * j + 1]); }
+                }
+            }
+            key0 += 16 * BV;
+        }
+        for (; key0 < nkv; key0 += 16 * B) {  // batch the V loads (192 keys per pass); the FMA order over keys stays sequential
             uint4 vv[B];
 #pragma unroll
-            for (int u = 0; u < B; ++u) { const int key = key0 + 16 * u; if (key < nkv) vv[u] = ld_kv16<MEGA>(vc + (size_t)key * E + h * 128 + o * 8); }
+            for (int u = 0; u < B; ++u) { const int key = min(key0 + 16 * u, nkv - 1); vv[u] = ld_kv16<MEGA>(vc + (size_t)key * E + h * 128 + o * 8); }
 #pragma unroll
             for (int u = 0; u < B; ++u) {
                 const int key = key0 + 16 * u;

@@ -42,6 +42,7 @@ struct MegaParams {
     const unsigned char *tok; int tok_type; size_t tok_row_bytes;
     DeviceState *state; unsigned *barrier;
     int l2_ahead;      // producer: ring slots requested into L2 ahead of the fill cursor (0 = off)
+    int flags;         // bit 0: request the head's K/V history into L2 (evict_last) while the qkv weights are consumed
     long long *trace;  // optional [2 CTAs][n_ops][8]: clock64 at op start, barrier passed, activations staged, op done; then (warp 0)
                        // cycles spent waiting for ring fills, cycles in the dot products, units processed, unused
 };
@@ -69,6 +70,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2_keep(const void *p) { asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p)); }
+// The attention op of this layer will read K/V rows 0..pos-1 of head h (256 B per key and tensor, written by earlier tokens, long
+// since evicted by the weight stream).  Asking L2 for them one op early turns the two HBM round trips on the attention critical path
+// into L2 hits; evict_last keeps the weight stream from pushing them out again before they are used.
+__device__ __forceinline__ void prefetch_kv_head(const __half *kc, const __half *vc, int pos, int h, int E) {
+    for (int i = (int)threadIdx.x; i < 2 * pos; i += 256) {  // (key, 128-byte half of the 256-byte head row)
+        const size_t off = (size_t)(i >> 1) * E + h * 128 + (i & 1) * 64;
+        prefetch_l2_keep(kc + off); prefetch_l2_keep(vc + off);
+    }
+}
+
 // first unit (row pair) of CTA `cta`: units are split evenly over the grid (n_su * G < 2^31: host-checked)
 __device__ __forceinline__ int unit_begin(int cta, int n_su, int G) { return (int)((unsigned)cta * (unsigned)n_su / (unsigned)G); }
 
@@ -76,7 +89,9 @@ __device__ __forceinline__ int unit_begin(int cta, int n_su, int G) { return (in
 __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
     consumer_sync();  // all consumer warps of this CTA have issued their global writes (CTA-scope ordering)
     if (threadIdx.x == 0) {
-        __threadfence();  // cumulative: publishes the CTA's writes at gpu scope before the arrival below
+        // release: a cumulative acq_rel fence publishes the CTA's writes (ordered before it by the bar.sync above) at gpu scope before the
+        // arrival.  (__threadfence() is the sequentially-consistent MEMBAR.SC.GPU - stronger, and slower, than this pattern needs.)
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         unsigned v;
         do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
@@ -321,12 +336,13 @@ __device__ __forceinline__ void stage_op(const MegaParams &P, int oi, unsigned b
     const MegaOp &op = m.ops[oi];
     const int tid = threadIdx.x, cols = op.cols, kind = op.kind;
     const float *nw = op.norm_w;
-    float4 nwr[kNormItems];
-    if (nw && tid < 256) load_norm_weights(nw, cols, nwr);
+    // the (static) norm weights are only ASKED into L2 before the barrier and loaded together with the activations after it: holding
+    // them in registers across the barrier cost 20 registers that ptxas spilled to local memory (an L2 round trip on this path)
+    if (nw && tid * 32 < cols) prefetch_l2(nw + tid * 32);
     grid_barrier(P.barrier, bar_target);
     if (TRACE && tr) tr[1] = clock64();
     const float *src = kind == OP_WO ? P.att : kind == OP_DOWN ? P.act : P.x;
-    if (nw) { if (tid < 256) stage_norm_mega<ACT>(src, nwr, cols, m.actb, red); }
+    if (nw) { if (tid < 256) { float4 nwr[kNormItems]; load_norm_weights(nw, cols, nwr); stage_norm_mega<ACT>(src, nwr, cols, m.actb, red); } }
     else stage_plain_mega<ACT>(src, cols, m.actb);
     consumer_sync();
     if (TRACE && tr) tr[2] = clock64();
@@ -440,6 +456,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         }
         // ---- matvec ops: [norm weights -> grid barrier -> stage activations] then [ring slots -> dot -> epilogue] ----
         stage_op<ACT, TRACE>(P, oi, bar_target, tr);
+        if (kind == OP_QKV && (P.flags & 1) && cta < P.n_head && tid < 256) {
+            const size_t lo = (size_t)ops[oi].layer * P.n_ctx * P.E;
+            prefetch_kv_head(P.kcache + lo, P.vcache + lo, pos, cta, P.E);
+        }
         switch (kind) {
             case OP_QKV:    n_base = consume_units<Q41, OP_QKV, TRACE>(P, oi, n_base, pos, tr); break;
             case OP_WO:     n_base = consume_units<Q41, OP_WO, TRACE>(P, oi, n_base, pos, tr); break;
