@@ -75,12 +75,19 @@ MINIGPT4_API int minigpt4_b200_op_layernorm(const float *x, int rows, int n, con
 /* q,k,v: [n][heads*dh]; out [nq][heads*dh] rounded to F16 precision */
 MINIGPT4_API int minigpt4_b200_op_attention(const float *q, const float *k, const float *v, int nq, int nk, int heads, int dh, float score_div, float *out);
 
+/* out_f16[n] = the F16 operand the vision graph builds at load time from a non-F16 matrix: `raw` holds n elements as ggml blocks of
+ * `ggml_type` (0 F32, 2 Q4_0, 3 Q4_1, 6 Q5_0, 7 Q5_1, 8 Q8_0); values follow ggml's dequantize_row_* and are rounded to F16 */
+MINIGPT4_API int minigpt4_b200_op_dequant_f16(int ggml_type, const void *raw, long n, void *out_f16);
+
 /* host-only seams (no GPU touched): the tokenizer / sampler / file readers are host logic and are unit-tested on CPU */
 /* tokenise with the vocabulary stored in a ggjt file; returns count or -needed (llama_tokenize convention), -1000000 on read failure */
 MINIGPT4_API int minigpt4_b200_host_tokenize(const char *llm_model, const char *text, int add_bos, int32_t *out, int max_tokens);
 /* run the sampler chain of minigpt4_end_chat on caller-provided logits (reference minigpt4.cpp:2425-2483) */
 MINIGPT4_API int minigpt4_b200_host_sample(const float *logits, int n_vocab, int seed, float temp, int32_t top_k, float top_p, float tfs_z,
                                            float typical_p, int mirostat, float mirostat_tau, float mirostat_eta, int n_draws, int32_t *out_ids);
+/* block quantiser behind minigpt4_quantize_model (ggml quantize_row_*_reference): n floats (n % 32 == 0) -> ggml blocks of
+ * `ggml_type` (2 Q4_0, 3 Q4_1, 6 Q5_0, 7 Q5_1, 8 Q8_0); returns the bytes written, -1 for an unsupported type or ragged n */
+MINIGPT4_API long minigpt4_b200_host_quantize_row(int ggml_type, const float *x, long n, void *out_blocks);
 /* parse a MiniGPT-4 container (returns MiniGPT4Error) / ggjt file (0 ok) and report tensor counts */
 MINIGPT4_API int minigpt4_b200_host_inspect_container(const char *path, int *n_models, int *n_tensors, int *n_embd_llm);
 MINIGPT4_API int minigpt4_b200_host_inspect_ggjt(const char *path, int *n_vocab, int *n_embd, int *n_layer, int *n_tensors);

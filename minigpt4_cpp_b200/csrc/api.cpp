@@ -190,6 +190,10 @@ int minigpt4_b200_op_attention(const float *q, const float *k, const float *v, i
     VisionDevice::test_attention(q, k, v, nq, nk, heads, dh, score_div, out); return 0;
 }
 
+int minigpt4_b200_op_dequant_f16(int ggml_type, const void *raw, long n, void *out_f16) { return VisionDevice::test_dequant(ggml_type, raw, n, out_f16); }
+extern "C" long mg4_quantize_row(int gg_type, const float *x, long n, unsigned char *out);
+long minigpt4_b200_host_quantize_row(int ggml_type, const float *x, long n, void *out_blocks) { return mg4_quantize_row(ggml_type, x, n, (unsigned char *)out_blocks); }
+
 int minigpt4_b200_host_tokenize(const char *llm_model, const char *text, int add_bos, int32_t *out, int max_tokens) {
     LlamaFile f;
     if (!f.load(llm_model)) return -1000000;

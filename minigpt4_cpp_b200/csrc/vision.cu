@@ -90,14 +90,32 @@ VisionDevice::~VisionDevice() {
 void *VisionDevice::dalloc(size_t n) {
     void *p; CUDA_CHECK(cudaMalloc(&p, n)); CUDA_CHECK(cudaMemset(p, 0, n)); allocs_.push_back(p); return p;
 }
+// Every >= 2-D weight ends up as an F16 row-major operand of the tensor-core GEMMs.  F16 containers (the reference's convert.py
+// output) are copied as they are.  Quantised containers (minigpt4_quantize_model output: the README's pre-quantised downloads) and
+// F32 ones are expanded to F16 once, here, on the device.  NOTE (numerics): ggml would run such a matrix through its quantised
+// mul_mat (activations quantised to Q8_0/Q8_1, integer block dots); here the weight's dequantised value, rounded to F16, meets the
+// F16-rounded activation on the tensor cores.  Both are faithful to the stored weights to ~1e-3; the parity test bounds the
+// difference on the final embedding (tests/test_quantized_vision_gpu.py).
+static bool vision_type_ok(int gg) { return gg == GG_F16 || gg == GG_F32 || gg == GG_Q4_0 || gg == GG_Q4_1 || gg == GG_Q5_0 || gg == GG_Q5_1 || gg == GG_Q8_0; }
+void VisionDevice::put16(const HostTensor &t, __half *dst) {
+    if (!vision_type_ok(t.gg)) MG4_PANIC("tensor %s: ggml type %d is not supported by the vision graph (F16, F32, Q4_0, Q4_1, Q5_0, Q5_1, Q8_0)", t.name.c_str(), t.gg);
+    const size_t n = (size_t)t.nelements();
+    if (t.gg == GG_F16) { CUDA_CHECK(cudaMemcpy(dst, t.data, n * 2, cudaMemcpyHostToDevice)); return; }
+    unsigned char *raw = nullptr;
+    CUDA_CHECK(cudaMalloc((void **)&raw, t.nbytes));
+    CUDA_CHECK(cudaMemcpy(raw, t.data, t.nbytes, cudaMemcpyHostToDevice));
+    dequant_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256>>>(t.gg, raw, n, dst);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());
+    cudaFree(raw);
+}
 const __half *VisionDevice::w16(const VisionFile &f, const std::string &model, const std::string &name, int rows, int cols) {
     const HostTensor &t = f.get(model, name);
-    if (t.gg != GG_F16) MG4_PANIC("tensor %s.%s: only F16 matrices are supported by the tensor-core path (type %d)", model.c_str(), name.c_str(), t.gg);
     if (t.nelements() != (int64_t)rows * cols) MG4_PANIC("tensor %s.%s: expected %d x %d", model.c_str(), name.c_str(), rows, cols);
-    void *d = dalloc(t.nbytes);
-    CUDA_CHECK(cudaMemcpy(d, t.data, t.nbytes, cudaMemcpyHostToDevice));
-    weight_bytes_ += t.nbytes;
-    return (const __half *)d;
+    __half *d = (__half *)dalloc((size_t)rows * cols * 2);
+    put16(t, d);
+    weight_bytes_ += (size_t)rows * cols * 2;
+    return d;
 }
 const float *VisionDevice::w32(const VisionFile &f, const std::string &model, const std::string &name, int n) {
     const HostTensor &t = f.get(model, name);
@@ -157,12 +175,12 @@ Error VisionDevice::load(const VisionFile &f) {
     pos_ = w32(f, VE, "pos_embed", T * D);
     {   // patch embedding: [D][3*14*14] -> [D][640]
         const HostTensor &pw = f.get(VE, "patch_embed.proj.weight");
-        if (pw.gg != GG_F16 || pw.nelements() != (int64_t)D * 588) MG4_PANIC("patch_embed.proj.weight must be F16 [14,14,3,%d]", D);
-        __half *raw = (__half *)dalloc(pw.nbytes); CUDA_CHECK(cudaMemcpy(raw, pw.data, pw.nbytes, cudaMemcpyHostToDevice));
+        if (pw.nelements() != (int64_t)D * 588) MG4_PANIC("patch_embed.proj.weight must be [14,14,3,%d]", D);
+        __half *raw = (__half *)dalloc((size_t)D * 588 * 2); put16(pw, raw);
         __half *padded = (__half *)dalloc((size_t)D * 640 * 2);
         pad_rows_f16_kernel<<<(unsigned)(((size_t)D * 640 + 255) / 256), 256>>>(raw, D, 588, padded, 640);
         CUDA_CHECK(cudaDeviceSynchronize());
-        weight_bytes_ += pw.nbytes;
+        weight_bytes_ += (size_t)D * 588 * 2;
         patch_ = add_plan(make_plan(padded, D, 640, patches_, 256, GE_PATCH));
         patch_->a.bias = w32(f, VE, "patch_embed.proj.bias", D); patch_->a.out_f32 = x_; patch_->a.ld_out = D; patch_->a.pos = pos_;
     }
@@ -193,10 +211,10 @@ Error VisionDevice::load(const VisionFile &f) {
     qtok_ = w32(f, "query_tokens", "weight", NQ * QH);
     const std::string QF = "Qformer";
     qln_w_ = w32(f, QF, "bert.embeddings.LayerNorm.weight", QH); qln_b_ = w32(f, QF, "bert.embeddings.LayerNorm.bias", QH);
-    auto cat16 = [&](std::initializer_list<const HostTensor *> ts, int cols) {  // row-concatenate F16 matrices
-        size_t total = 0; for (auto t : ts) { if (t->gg != GG_F16 || t->ne[0] != cols) MG4_PANIC("Q-Former matrix %s must be F16 with %d columns", t->name.c_str(), cols); total += t->nbytes; }
+    auto cat16 = [&](std::initializer_list<const HostTensor *> ts, int cols) {  // row-concatenate matrices as F16
+        size_t total = 0; for (auto t : ts) { if (t->ne[0] != cols) MG4_PANIC("Q-Former matrix %s must have %d columns", t->name.c_str(), cols); total += (size_t)t->nelements() * 2; }
         unsigned char *d = (unsigned char *)dalloc(total); size_t off = 0;
-        for (auto t : ts) { CUDA_CHECK(cudaMemcpy(d + off, t->data, t->nbytes, cudaMemcpyHostToDevice)); off += t->nbytes; }
+        for (auto t : ts) { put16(*t, (__half *)(d + off)); off += (size_t)t->nelements() * 2; }
         weight_bytes_ += total;
         return (const __half *)d;
     };
@@ -357,6 +375,16 @@ void VisionDevice::test_gemm(int M, int T, int K, const void *w_f16, const void 
         for (size_t i = 0; i < h.size(); ++i) out_f32[i] = __half2float(h[i]);
     } else CUDA_CHECK(cudaMemcpy(out_f32, O, (size_t)T * M * 4, cudaMemcpyDeviceToHost));
     delete p; cudaFree(W); cudaFree(X); cudaFree(O); if (B) cudaFree(B); if (O16) cudaFree(O16); if (tab) cudaFree(tab);
+}
+int VisionDevice::test_dequant(int gg_type, const void *raw, long n, void *out_f16) {
+    if (!vision_type_ok(gg_type) || n <= 0 || (gg_type != GG_F32 && gg_type != GG_F16 && n % 32)) return ErrLoadModelMiniGPT4DataType;
+    HostTensor t; t.gg = gg_type; t.n_dims = 1; t.ne[0] = n; t.data = (const uint8_t *)raw;
+    t.nbytes = (size_t)n / gg_block_elems(gg_type) * gg_block_bytes(gg_type);
+    __half *d; CUDA_CHECK(cudaMalloc((void **)&d, (size_t)n * 2));
+    put16(t, d);
+    CUDA_CHECK(cudaMemcpy(out_f16, d, (size_t)n * 2, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return ErrNone;
 }
 void VisionDevice::test_layernorm(const float *x, int rows, int n, const float *w, const float *b, float *out) {
     float *X, *W, *B, *O;

@@ -35,6 +35,7 @@ public:
 
     // kernel-level test hook: out[T][M] = bias + X[T][K] . W[M][K]^T through the tcgen05 GEMM (F16 operands on host)
     static void test_gemm(int M, int T, int K, const void *w_f16, const void *x_f16, const float *bias, int epi, float *out_f32);
+    static int test_dequant(int gg_type, const void *raw, long n, void *out_f16);
     static void test_layernorm(const float *x, int rows, int n, const float *w, const float *b, float *out);
     static void test_attention(const float *q, const float *k, const float *v, int nq, int nk, int heads, int dh, float div, float *out);
 
@@ -44,6 +45,7 @@ private:
     std::vector<GemmPlan *> plans_;
     std::vector<void *> allocs_;
     void *dalloc(size_t n);
+    static void put16(const HostTensor &t, __half *dst);  // any supported matrix type -> F16 on the device
     const __half *w16(const VisionFile &f, const std::string &model, const std::string &name, int rows, int cols);
     const float *w32(const VisionFile &f, const std::string &model, const std::string &name, int n);
     // weights

@@ -342,5 +342,27 @@ __global__ void pad_rows_f16_kernel(const __half *__restrict__ src, int rows, in
     dst[i] = c < cols ? src[(size_t)r * cols + c] : __float2half_rn(0.f);
 }
 
+// Load-time conversion of a non-F16 matrix to the F16 operand layout of the tensor-core path: F32, or ggml's 32-element block
+// types (what minigpt4_quantize_model can produce for a ViT-g / Q-Former matrix: reference minigpt4.cpp:2897-2935).  Values follow
+// ggml's dequantize_row_q4_0 / q4_1 / q5_0 / q5_1 / q8_0 in F32 and are then rounded to F16 (RNE).
+__device__ __forceinline__ float h16_at(const unsigned char *p) { return __half2float(__ushort_as_half((unsigned short)(p[0] | (p[1] << 8)))); }
+__global__ void dequant_to_f16_kernel(int gg_type, const unsigned char *__restrict__ raw, size_t n, __half *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t b = i >> 5; const int j = (int)(i & 31), jj = j & 15;
+    float v = 0.f;
+    switch (gg_type) {
+        case GG_F32: v = ((const float *)raw)[i]; break;
+        case GG_Q4_0: { const unsigned char *p = raw + b * 18; const int q = j < 16 ? (p[2 + jj] & 0xF) : (p[2 + jj] >> 4); v = (float)(q - 8) * h16_at(p); break; }
+        case GG_Q4_1: { const unsigned char *p = raw + b * 20; const int q = j < 16 ? (p[4 + jj] & 0xF) : (p[4 + jj] >> 4); v = (float)q * h16_at(p) + h16_at(p + 2); break; }
+        case GG_Q5_0: { const unsigned char *p = raw + b * 22; const unsigned qh = p[2] | (p[3] << 8) | (p[4] << 16) | ((unsigned)p[5] << 24);
+            const int q = (j < 16 ? (p[6 + jj] & 0xF) : (p[6 + jj] >> 4)) | (int)(((qh >> j) & 1u) << 4); v = (float)(q - 16) * h16_at(p); break; }
+        case GG_Q5_1: { const unsigned char *p = raw + b * 24; const unsigned qh = p[4] | (p[5] << 8) | (p[6] << 16) | ((unsigned)p[7] << 24);
+            const int q = (j < 16 ? (p[8 + jj] & 0xF) : (p[8 + jj] >> 4)) | (int)(((qh >> j) & 1u) << 4); v = (float)q * h16_at(p) + h16_at(p + 2); break; }
+        case GG_Q8_0: { const unsigned char *p = raw + b * 34; v = (float)(signed char)p[2 + j] * h16_at(p); break; }
+    }
+    out[i] = __float2half_rn(v);
+}
+
 }  // namespace vk
 }  // namespace mg4

@@ -220,6 +220,8 @@ _EXT = {
     "minigpt4_b200_op_gemm_f16": ([_I, _I, _I, _VP, _VP, _VP, _I, _VP], _I),
     "minigpt4_b200_op_layernorm": ([_VP, _I, _I, _VP, _VP, _VP], _I),
     "minigpt4_b200_op_attention": ([_VP, _VP, _VP, _I, _I, _I, _I, _F, _VP], _I),
+    "minigpt4_b200_op_dequant_f16": ([_I, _VP, C.c_long, _VP], _I),
+    "minigpt4_b200_host_quantize_row": ([_I, _VP, C.c_long, _VP], C.c_long),
     "minigpt4_b200_host_tokenize": ([_S, _S, _I, _VP, _I], _I),
     "minigpt4_b200_host_sample": ([_VP, _I, _I, _F, _I, _F, _F, _F, _I, _F, _F, _I, _VP], _I),
     "minigpt4_b200_host_inspect_container": ([_S, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)], _I),
@@ -349,6 +351,19 @@ class B200:
         out = np.empty_like(x)
         self._chk(self.L.minigpt4_b200_op_layernorm(_ptr(x), x.shape[0], x.shape[1], _ptr(w), _ptr(b), _ptr(out)))
         return out
+
+    def op_dequant_f16(self, gtype: int, raw: np.ndarray, n: int) -> np.ndarray:
+        raw = np.ascontiguousarray(raw)
+        out = np.zeros(n, np.float16)
+        self._chk(self.L.minigpt4_b200_op_dequant_f16(gtype, _ptr(raw), n, _ptr(out)))
+        return out
+
+    def host_quantize_row(self, gtype: int, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32).reshape(-1)
+        out = np.zeros(x.size // 32 * 40, np.uint8)
+        nb = self.L.minigpt4_b200_host_quantize_row(gtype, _ptr(x), x.size, _ptr(out))
+        assert nb >= 0, "unsupported quantisation type"
+        return out[:nb].copy()
 
     def op_attention(self, q, k, v, heads: int, dh: int, div: float) -> np.ndarray:
         q = np.ascontiguousarray(q, np.float32); k = np.ascontiguousarray(k, np.float32); v = np.ascontiguousarray(v, np.float32)

@@ -390,22 +390,34 @@ def write_minigpt4(path: str | Path, spec: VisionSpec) -> None:
                                           "hidden_size": HID, "num_attention_heads": 12, "intermediate_size": 3072,
                                           "cross_attention_freq": spec.cross_attention_freq, "layer_norm_eps": 1e-12,
                                           "add_cross_attention": True, "vocab_size": 30523}}
+    write_container(path, config, models)
+
+
+def write_container(path: str | Path, config: dict, models: list[tuple[str, dict[str, np.ndarray]]], file_dtype: int = DT_F16,
+                    raw_types: dict[str, tuple[int, list[int]]] | None = None) -> None:
+    """Container writer (layout of reference convert.py:56-180 / loader minigpt4.cpp:1478-1596).  float16 / float32 arrays are written
+    as F16 / F32 tensors; raw_types["<model>.<tensor>"] = (container dtype, ne[]) marks a uint8 array as ready-made quantised blocks."""
+    raw_types = raw_types or {}
     with open(path, "wb") as f:
         f.write(b"ggml")
-        f.write(struct.pack("<ii", 1, DT_F16))
+        f.write(struct.pack("<ii", 1, file_dtype))
         _wstr(f, json.dumps(config))
         for name, tensors in models:
             _wstr(f, name)
             f.write(struct.pack("<i", len(tensors)))
             for tname, arr in tensors.items():
                 _wstr(f, tname)
-                shape = list(arr.shape)[::-1]
+                key = f"{name}.{tname}"
+                if key in raw_types:
+                    dt, shape = raw_types[key][0], list(raw_types[key][1])
+                else:
+                    dt, shape = (DT_F16 if arr.dtype == np.float16 else DT_F32), list(arr.shape)[::-1]
                 f.write(struct.pack("<i", len(shape)))
                 f.write(struct.pack(f"<{len(shape)}i", *shape))
-                f.write(struct.pack("<i", DT_F16 if arr.dtype == np.float16 else DT_F32))
+                f.write(struct.pack("<i", dt))
             for tname, arr in tensors.items():
                 f.seek((f.tell() + 4095) // 4096 * 4096 if f.tell() % 4096 else f.tell())
-                arr.tofile(f)
+                np.ascontiguousarray(arr).tofile(f)
 
 
 def synth_image(seed: int = 1234) -> np.ndarray:
