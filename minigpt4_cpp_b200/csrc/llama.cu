@@ -438,7 +438,11 @@ bool LlamaDevice::build_mega() {
     P->tok = (const unsigned char *)tok_raw_; P->tok_type = tok_type_; P->tok_row_bytes = gg_row_bytes(tok_type_, (size_t)E);
     P->state = state_; P->barrier = mega_barrier_;
     P->trace = nullptr;
-    P->l2_ahead = getenv("MINIGPT4_B200_L2_AHEAD") ? atoi(getenv("MINIGPT4_B200_L2_AHEAD")) : 48;
+    // L2 look-ahead lane of the producer warp: OFF by default.  Measured (profiles/r1_v3_summary.md): with the lane on, a 7B token took 1750 us
+    // and read 8.1 GB from DRAM for 4.13 GB of weights (requests landing behind the fill cursor); restricted to requests ahead of the
+    // cursor the traffic was right but the token still took 1750 us, because the lane shares a warp with the fill lane and its polling
+    // delays the fills; with the lane off: 1459 us.  The 28-slot ring alone keeps ~28 MB in flight chip-wide.
+    P->l2_ahead = getenv("MINIGPT4_B200_L2_AHEAD") ? atoi(getenv("MINIGPT4_B200_L2_AHEAD")) : 0;
     P->flags = getenv("MINIGPT4_B200_MEGA_FLAGS") ? atoi(getenv("MINIGPT4_B200_MEGA_FLAGS")) : 1;
     if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, ops.size() * 16 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, ops.size() * 16 * sizeof(long long))); P->trace = mega_trace_; }
     mega_n_ops_ = (int)ops.size();

@@ -275,7 +275,7 @@ Error VisionDevice::load(const VisionFile &f) {
     return ErrNone;
 }
 
-static size_t attn_smem(int nk, int dh) { return ((size_t)nk * (dh + 4) + (size_t)nk * dh + 16 * dh + 16 * (size_t)((nk + 31) & ~31)) * 4; }
+static size_t attn_smem(int nk, int dh) { const int nkp = (nk + 31) & ~31; return ((size_t)nk * (dh + 4) + (size_t)nk * dh + (size_t)8 * kAttnNQ * (nkp > dh ? nkp : dh)) * 4; }
 static void launch_attention(int dh, dim3 grid, cudaStream_t s, const float *q, int ldq, const float *k, const float *v, int ldkv, int nq, int nk, float div, int qpc,
                              __half *out, int ld_out, const __half *tab) {
     static bool cfg = false;
@@ -296,14 +296,14 @@ void VisionDevice::record() {
     const int D = d_.D, T = d_.T, QH = 768, NQ = 32;
     cudaStream_t s = stream_;
     auto ln = [&](const float *x, int rows, int n, const float *w, const float *b, __half *o16, float *o32) {
-        layernorm_kernel<<<(rows + 1) / 2, 64, 0, s>>>(x, rows, n, w, b, o16, o32, nullptr); ++launches_;
+        layernorm_kernel<<<rows, 128, 0, s>>>(x, rows, n, w, b, o16, o32, nullptr); ++launches_;
     };
     auto gemm = [&](GemmPlan *p) { launch_plan(p, s); ++launches_; };
 
     im2col_patch_kernel<<<256, 128, 0, s>>>(img_, patches_, 640); ++launches_;
     gemm(patch_);
     cls_row_kernel<<<(D + 255) / 256, 256, 0, s>>>(cls_, pos_, x_, D); ++launches_;
-    const int qpc = (T + 7) / 8;  // 8 query chunks per head -> 128 CTAs
+    const int qpc = (T + 8) / 9;  // 9 query chunks per head -> 144 CTAs (one wave); 29 queries = 8 warps x 4 queries in one pass
     for (Block &b : blocks_) {
         ln(x_, T, D, b.n1w, b.n1b, ln16_, nullptr);
         gemm(b.qkv);
@@ -391,7 +391,7 @@ void VisionDevice::test_layernorm(const float *x, int rows, int n, const float *
     CUDA_CHECK(cudaMalloc((void **)&X, (size_t)rows * n * 4)); CUDA_CHECK(cudaMalloc((void **)&O, (size_t)rows * n * 4));
     CUDA_CHECK(cudaMalloc((void **)&W, (size_t)n * 4)); CUDA_CHECK(cudaMalloc((void **)&B, (size_t)n * 4));
     CUDA_CHECK(cudaMemcpy(X, x, (size_t)rows * n * 4, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(W, w, (size_t)n * 4, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(B, b, (size_t)n * 4, cudaMemcpyHostToDevice));
-    layernorm_kernel<<<(rows + 1) / 2, 64>>>(X, rows, n, W, B, nullptr, O, nullptr);
+    layernorm_kernel<<<rows, 128>>>(X, rows, n, W, B, nullptr, O, nullptr);
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy(out, O, (size_t)rows * n * 4, cudaMemcpyDeviceToHost));
     cudaFree(X); cudaFree(W); cudaFree(B); cudaFree(O);

@@ -197,30 +197,44 @@ __device__ __forceinline__ float warp_max_f(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__global__ void layernorm_kernel(const float *__restrict__ x, int rows, int n, const float *__restrict__ w, const float *__restrict__ b,
-                                 __half *__restrict__ out16, float *__restrict__ out32, const float *__restrict__ add_in /* optional: x + add_in before the norm */) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+// one CTA of 128 threads per row (n <= 1536: 12 values per thread, in registers, one global pass).  A single warp per row made the
+// kernel a ~1900-instruction dependent chain with one warp per scheduler (24 us for 257 x 1408 under ncu, r1_v3); four warps per row
+// cut the chain by 4 and give every scheduler of every SM something to overlap.
+__global__ void __launch_bounds__(128) layernorm_kernel(const float *__restrict__ x, int rows, int n, const float *__restrict__ w, const float *__restrict__ b,
+                                                        __half *__restrict__ out16, float *__restrict__ out32, const float *__restrict__ add_in /* optional: x + add_in before the norm */) {
+    __shared__ double red[8];
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (row >= rows) return;
     const float *xr = x + (size_t)row * n;
     const float *ar = add_in ? add_in + (size_t)row * n : nullptr;
-    constexpr int MAXE = 48;  // n <= 1536: the row lives in registers, one global pass
+    constexpr int MAXE = 12;
     float v[MAXE];
 #pragma unroll
-    for (int k = 0; k < MAXE; ++k) { const int i = lane + 32 * k; if (i < n) v[k] = ar ? xr[i] + ar[i] : xr[i]; }
+    for (int k = 0; k < MAXE; ++k) {
+        const int i = tid + 128 * k, ic = min(i, n - 1);  // clamped, unconditional loads; out-of-range slots hold 0
+        const float t = ar ? xr[ic] + ar[ic] : xr[ic];
+        v[k] = i < n ? t : 0.f;
+    }
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < MAXE; ++k) if (lane + 32 * k < n) s += (double)v[k];
+    for (int k = 0; k < MAXE; ++k) s += (double)v[k];
     s = warp_sum_d(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = (red[0] + red[1]) + (red[2] + red[3]);
     const float mean = (float)(s / (double)n);
     double s2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < MAXE; ++k) if (lane + 32 * k < n) { v[k] = v[k] - mean; s2 += (double)(v[k] * v[k]); }
+    for (int k = 0; k < MAXE; ++k) { v[k] = v[k] - mean; if (tid + 128 * k < n) s2 += (double)(v[k] * v[k]); }
     s2 = warp_sum_d(s2);
+    if (lane == 0) red[4 + warp] = s2;
+    __syncthreads();
+    s2 = (red[4] + red[5]) + (red[6] + red[7]);
     const float variance = (float)(s2 / (double)n);
     const float scale = 1.0f / sqrtf(variance + 1e-5f);
 #pragma unroll
     for (int k = 0; k < MAXE; ++k) {
-        const int i = lane + 32 * k;
+        const int i = tid + 128 * k;
         if (i < n) {
             float y = w[i] * (v[k] * scale);
             if (b) y = y + b[i];
@@ -234,17 +248,21 @@ __global__ void layernorm_kernel(const float *__restrict__ x, int rows, int n, c
 // F32 multi-head attention (ViT MHSA and Q-Former self/cross attention; ggml F32xF32 mul_mat + soft_max with fp16 exp LUT)
 // q: [nq][ldq] (+ head*DH), k,v: [nk][ldkv] (+ head*DH).  grid (heads, ceil(nq / q_per_cta)), block 256.
 // K ([nk][DH+4], float4 rows, odd float4 pitch -> conflict-free 128-bit reads) and V ([nk][DH]) of the head live in shared
-// memory; each warp processes TWO queries at a time so every K/V shared-memory read feeds two FMAs (the kernel is
-// shared-memory-bandwidth bound).  out: F16 [nq][ld_out] (operand of the following projection GEMM).
+// memory.  The kernel is shared-memory-bandwidth bound, so each warp processes NQ = 4 queries at a time: every K / V value read from
+// shared memory feeds 4 FMAs (r1_v3 ncu: the two-query version ran at 6 % of the FP32 peak, 79 us per ViT block).  The per-warp
+// scratch holds the warp's q rows while the scores are formed and is then reused for its probability rows.  Per element the
+// arithmetic (FMA order over d and over keys, LUT exp, double sum) is unchanged.  out: F16 [nq][ld_out] (operand of the next GEMM).
 // ---------------------------------------------------------------------------------------------
+constexpr int kAttnNQ = 4;
 template <int DH>
 __global__ void __launch_bounds__(256) attention_f32_kernel(const float *__restrict__ q, int ldq, const float *__restrict__ k, const float *__restrict__ v, int ldkv,
                                                             int nq, int nk, float score_div, int q_per_cta, __half *__restrict__ out, int ld_out,
                                                             const __half *__restrict__ tab_exp) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int DH4 = DH / 4, KP = DH + 4, NKI = 9;  // nk <= 288
+    constexpr int DH4 = DH / 4, KP = DH + 4, NKI = 9, NQ = kAttnNQ;  // nk <= 288
     const int nk_pad = (nk + 31) & ~31;
-    float *Ks = (float *)smem; float *Vs = Ks + (size_t)nk * KP; float *Qs = Vs + (size_t)nk * DH; float *Ps = Qs + 8 * 2 * DH;
+    const int wstride = NQ * (nk_pad > DH ? nk_pad : DH);
+    float *Ks = (float *)smem; float *Vs = Ks + (size_t)nk * KP; float *Ws = Vs + (size_t)nk * DH;
     const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int t = warp; t < nk; t += 8) {
         if (lane < DH4) {
@@ -254,48 +272,60 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float *__restr
     }
     __syncthreads();
     const int q0 = blockIdx.y * q_per_cta, q1 = min(nq, q0 + q_per_cta);
-    float *qw = Qs + warp * 2 * DH, *pw = Ps + (size_t)warp * 2 * nk_pad;
-    for (int tq = q0 + 2 * warp; tq < q1; tq += 16) {
-        const bool two = tq + 1 < q1;
+    float *qw = Ws + (size_t)warp * wstride, *pw = qw;
+    for (int tq = q0 + NQ * warp; tq < q1; tq += 8 * NQ) {
+        const int nv = min(NQ, q1 - tq);  // valid queries of this pass (the others are computed on zeros and dropped)
         if (lane < DH4) {
-            *(float4 *)(qw + lane * 4) = *(const float4 *)(q + (size_t)tq * ldq + h * DH + lane * 4);
-            *(float4 *)(qw + DH + lane * 4) = two ? *(const float4 *)(q + (size_t)(tq + 1) * ldq + h * DH + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi)
+                *(float4 *)(qw + qi * DH + lane * 4) = qi < nv ? *(const float4 *)(q + (size_t)(tq + qi) * ldq + h * DH + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();
-        float sa[NKI], sb[NKI];
+        float sc[NQ][NKI];
 #pragma unroll
-        for (int i = 0; i < NKI; ++i) { sa[i] = 0.f; sb[i] = 0.f; }
+        for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+            for (int i = 0; i < NKI; ++i) sc[qi][i] = 0.f;
         for (int c = 0; c < DH4; ++c) {
-            const float4 qa = *(const float4 *)(qw + c * 4), qb = *(const float4 *)(qw + DH + c * 4);
+            float4 qv[NQ];
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) qv[qi] = *(const float4 *)(qw + qi * DH + c * 4);
 #pragma unroll
             for (int i = 0; i < NKI; ++i) {
-                const int j = lane + 32 * i;
-                if (j < nk) {
-                    const float4 kk = *(const float4 *)(Ks + (size_t)j * KP + c * 4);
-                    sa[i] = fmaf(kk.x, qa.x, sa[i]); sa[i] = fmaf(kk.y, qa.y, sa[i]); sa[i] = fmaf(kk.z, qa.z, sa[i]); sa[i] = fmaf(kk.w, qa.w, sa[i]);
-                    sb[i] = fmaf(kk.x, qb.x, sb[i]); sb[i] = fmaf(kk.y, qb.y, sb[i]); sb[i] = fmaf(kk.z, qb.z, sb[i]); sb[i] = fmaf(kk.w, qb.w, sb[i]);
+                const int j = min(lane + 32 * i, nk - 1);  // clamped: lanes past the last key compute a value that is never used
+                const float4 kk = *(const float4 *)(Ks + (size_t)j * KP + c * 4);
+#pragma unroll
+                for (int qi = 0; qi < NQ; ++qi) {
+                    sc[qi][i] = fmaf(kk.x, qv[qi].x, sc[qi][i]); sc[qi][i] = fmaf(kk.y, qv[qi].y, sc[qi][i]);
+                    sc[qi][i] = fmaf(kk.z, qv[qi].z, sc[qi][i]); sc[qi][i] = fmaf(kk.w, qv[qi].w, sc[qi][i]);
                 }
             }
         }
-        float mxa = -INFINITY, mxb = -INFINITY;
+        __syncwarp();  // every lane has finished reading the q rows: the scratch becomes the probability rows
 #pragma unroll
-        for (int i = 0; i < NKI; ++i) if (lane + 32 * i < nk) { sa[i] = sa[i] / score_div; sb[i] = sb[i] / score_div; mxa = fmaxf(mxa, sa[i]); mxb = fmaxf(mxb, sb[i]); }
-        mxa = warp_max_f(mxa); mxb = warp_max_f(mxb);
-        double suma = 0.0, sumb = 0.0;
+        for (int qi = 0; qi < NQ; ++qi) {
+            float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < NKI; ++i) if (lane + 32 * i < nk) {
-            sa[i] = __half2float(tab_exp[__half_as_ushort(__float2half_rn(sa[i] - mxa))]); suma += (double)sa[i];
-            sb[i] = __half2float(tab_exp[__half_as_ushort(__float2half_rn(sb[i] - mxb))]); sumb += (double)sb[i];
+            for (int i = 0; i < NKI; ++i) if (lane + 32 * i < nk) { sc[qi][i] = sc[qi][i] / score_div; mx = fmaxf(mx, sc[qi][i]); }
+            mx = warp_max_f(mx);
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < NKI; ++i) if (lane + 32 * i < nk) {
+                sc[qi][i] = __half2float(tab_exp[__half_as_ushort(__float2half_rn(sc[qi][i] - mx))]); sum += (double)sc[qi][i];
+            }
+            sum = warp_sum_d(sum);
+            const float inv = (float)(1.0 / sum);
+#pragma unroll
+            for (int i = 0; i < NKI; ++i) { const int j = lane + 32 * i; if (j < nk_pad) pw[qi * nk_pad + j] = j < nk ? sc[qi][i] * inv : 0.f; }
         }
-        suma = warp_sum_d(suma); sumb = warp_sum_d(sumb);
-        const float inva = (float)(1.0 / suma), invb = (float)(1.0 / sumb);
-#pragma unroll
-        for (int i = 0; i < NKI; ++i) { const int j = lane + 32 * i; if (j < nk_pad) { pw[j] = j < nk ? sa[i] * inva : 0.f; pw[nk_pad + j] = j < nk ? sb[i] * invb : 0.f; } }
         __syncwarp();
-        float oa[3] = {0.f, 0.f, 0.f}, ob[3] = {0.f, 0.f, 0.f};
+        float o[NQ][3];
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) { o[qi][0] = 0.f; o[qi][1] = 0.f; o[qi][2] = 0.f; }
         for (int j4 = 0; j4 < nk_pad; j4 += 4) {
-            const float4 pa = *(const float4 *)(pw + j4), pb = *(const float4 *)(pw + nk_pad + j4);
-            const float pav[4] = {pa.x, pa.y, pa.z, pa.w}, pbv[4] = {pb.x, pb.y, pb.z, pb.w};
+            float pv[NQ][4];
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) { const float4 p4 = *(const float4 *)(pw + qi * nk_pad + j4); pv[qi][0] = p4.x; pv[qi][1] = p4.y; pv[qi][2] = p4.z; pv[qi][3] = p4.w; }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = j4 + u;
@@ -303,15 +333,21 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float *__restr
 #pragma unroll
                     for (int e = 0; e < 3; ++e) {
                         const int d = lane + 32 * e;
-                        if (d < DH) { const float vv = Vs[(size_t)j * DH + d]; oa[e] = fmaf(vv, pav[u], oa[e]); ob[e] = fmaf(vv, pbv[u], ob[e]); }
+                        if (d < DH) {
+                            const float vv = Vs[(size_t)j * DH + d];
+#pragma unroll
+                            for (int qi = 0; qi < NQ; ++qi) o[qi][e] = fmaf(vv, pv[qi][u], o[qi][e]);
+                        }
                     }
                 }
             }
         }
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            const int d = lane + 32 * e;
-            if (d < DH) { out[(size_t)tq * ld_out + h * DH + d] = __float2half_rn(oa[e]); if (two) out[(size_t)(tq + 1) * ld_out + h * DH + d] = __float2half_rn(ob[e]); }
+        for (int qi = 0; qi < NQ; ++qi) {
+            if (qi < nv) {
+#pragma unroll
+                for (int e = 0; e < 3; ++e) { const int d = lane + 32 * e; if (d < DH) out[(size_t)(tq + qi) * ld_out + h * DH + d] = __float2half_rn(o[qi][e]); }
+            }
         }
         __syncwarp();
     }
