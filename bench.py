@@ -109,6 +109,16 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(kernel: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (dram__bytes_read.sum +
+    dram__bytes_write.sum; profiles/traffic.json, written from the .ncu-rep of the same build), or None."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return float(json.loads(p.read_text())[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def host_cpus() -> int:
     """CPUs this process may actually use: affinity mask capped by the cgroup quota (a container often sees 128 logical
     CPUs but is throttled to far fewer; oversubscribing OpenMP threads there is catastrophic)."""
@@ -310,7 +320,7 @@ def main():
         us = chain_ms * 1e3 / (args.steps * N_GEN)  # per launch on one GPU (max over ranks)
         ach = st.llm_weight_bytes_per_token / us * 1e-3
         roofline = {"bound": "hbm", "kernel": f"decode_megakernel<{args.wtype}> (1 launch per token: {st.n_layer} x [qkv, attention, wo, gate_up, down] + output/arg-max)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic(f"decode_megakernel_{args.size}_{args.wtype}"), "peak_source": peak_src,
                     "bytes_per_launch": st.llm_weight_bytes_per_token, "us_per_launch": us}
     else:
         kinds = ["qkv", "wo", "gate_up", "down", "output"]

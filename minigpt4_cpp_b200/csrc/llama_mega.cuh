@@ -43,6 +43,7 @@ struct MegaParams {
     DeviceState *state; unsigned *barrier;
     int l2_ahead;      // producer: ring slots requested into L2 ahead of the fill cursor (0 = off)
     int flags;         // bit 0: request the head's K/V history into L2 (evict_last) while the qkv weights are consumed
+                       // bit 1: threads that idle during the attention op request the rest of their gate/up share into L2
     long long *trace;  // optional [2 CTAs][n_ops][8]: clock64 at op start, barrier passed, activations staged, op done; then (warp 0)
                        // cycles spent waiting for ring fills, cycles in the dot products, units processed, unused
 };
@@ -447,6 +448,21 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 if (cta < P.n_head && tid < 256) {  // one head per CTA, 256 threads (named barrier 1)
                     const size_t lo = (size_t)ops[oi].layer * P.n_ctx * P.E;
                     attention_mega(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, P.E, P.n_ctx, P.kq_scale, P.tab_exp, actb, red, redf, qh, part);
+                } else if ((P.flags & 2) && oi + 2 < P.n_ops && ops[oi + 2].w) {
+                    // Everybody else idles until the heads are done, the ring is full and the producer is blocked, so HBM idles too.  These
+                    // threads ask L2 for the part of this CTA's gate/up share that the ring has not requested yet; the producer's later
+                    // fills then come out of L2.  (Requests strictly ahead of the fill cursor: nothing is read from DRAM twice.)
+                    const MegaOp &wo = ops[oi + 1], &gu = ops[oi + 2];
+                    const unsigned cnt_wo = (unsigned)(unit_begin(cta + 1, wo.n_su, G) - unit_begin(cta, wo.n_su, G)) * (unsigned)wo.sps;
+                    const int lo = unit_begin(cta, gu.n_su, G), hi = unit_begin(cta + 1, gu.n_su, G);
+                    const int issued = (int)(*fill_count - (n_base + cnt_wo)) / gu.sps;  // gate/up units the producer has already requested
+                    const int first = lo + (issued > 0 ? issued : 0);
+                    if (first < hi) {
+                        const unsigned char *base = gu.w + (size_t)first * 2 * gu.row_bytes;
+                        const size_t bytes = (size_t)(hi - first) * 2 * gu.row_bytes;
+                        const int t = cta < P.n_head ? tid - 256 : tid, nt = cta < P.n_head ? kConsumerThreads - 256 : kConsumerThreads;
+                        for (size_t off = (size_t)t * 128; off < bytes; off += (size_t)nt * 128) prefetch_l2(base + off);
+                    }
                 }
             } else if (cta == 0 && tid == 0) {
                 DeviceState *st = P.state;
