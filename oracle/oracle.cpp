@@ -47,7 +47,7 @@ static inline float h2f(f16_t h) { return _cvtsh_ss(h); }
 static inline f16_t f2h(float f) { return _cvtss_sh(f, 0); }  // round-to-nearest-even
 
 // ggml type ids (ggml.h enum ggml_type at master-31cfbb1)
-enum { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_K = 13, T_Q6_K = 14 };
+enum { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q5_K = 13, T_Q6_K = 14 };
 
 #define QK 32
 #define QK_K 256
@@ -55,6 +55,8 @@ enum { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_K = 13, T_Q6_K = 14 };
 #pragma pack(push, 1)
 struct block_q4_0 { f16_t d; uint8_t qs[16]; };                          // 18 B
 struct block_q4_1 { f16_t d; f16_t m; uint8_t qs[16]; };                 // 20 B
+struct block_q5_0 { f16_t d; uint8_t qh[4]; uint8_t qs[16]; };           // 22 B
+struct block_q5_1 { f16_t d; f16_t m; uint8_t qh[4]; uint8_t qs[16]; };  // 24 B
 struct block_q8_0 { f16_t d; int8_t qs[32]; };                           // 34 B
 struct block_q8_1 { float d; float s; int8_t qs[32]; };                  // 40 B (d,s are F32 at this revision)
 struct block_q5_K { f16_t d; f16_t dmin; uint8_t scales[12]; uint8_t qh[32]; uint8_t qs[128]; }; // 176 B
@@ -302,6 +304,34 @@ static float vec_dot_f32(int n, const float *x, const float *y) {
 #endif
 }
 
+// Q5_0 / Q5_1 / Q8_0 (ggml.c ggml_vec_dot_q5_0_q8_0 / q5_1_q8_1 / q8_0_q8_0): the fifth bit of weight j sits in bit j of qh (low half of the
+// block) and bit j+16 (high half).  Scalar statement of the block sums; the float accumulation is one running sum per row, as in ggml's
+// scalar path (these types are only reached through quantised MiniGPT-4 containers / llama files, never on the bit-exact decode path).
+static inline int dot_q5_block(const uint8_t *qs, const uint8_t *qh4, const int8_t *q8, int bias) {
+    uint32_t qh; memcpy(&qh, qh4, 4);
+    int sumi = 0;
+    for (int j = 0; j < 16; ++j) {
+        const int x0 = ((qs[j] & 0x0F) | (int)(((qh >> j) & 1u) << 4)) - bias;
+        const int x1 = ((qs[j] >> 4) | (int)(((qh >> (j + 16)) & 1u) << 4)) - bias;
+        sumi += x0 * q8[j] + x1 * q8[j + 16];
+    }
+    return sumi;
+}
+static float vec_dot_q5_0_q8_0(int n, const block_q5_0 *x, const block_q8_0 *y) {
+    float sumf = 0;
+    for (int i = 0; i < n / QK; ++i) sumf += (h2f(x[i].d) * h2f(y[i].d)) * dot_q5_block(x[i].qs, x[i].qh, y[i].qs, 16);
+    return sumf;
+}
+static float vec_dot_q5_1_q8_1(int n, const block_q5_1 *x, const block_q8_1 *y) {
+    float sumf = 0;
+    for (int i = 0; i < n / QK; ++i) sumf += (h2f(x[i].d) * y[i].d) * dot_q5_block(x[i].qs, x[i].qh, y[i].qs, 0) + h2f(x[i].m) * y[i].s;
+    return sumf;
+}
+static float vec_dot_q8_0_q8_0(int n, const block_q8_0 *x, const block_q8_0 *y) {
+    float sumf = 0;
+    for (int i = 0; i < n / QK; ++i) { int sumi = 0; for (int j = 0; j < 32; ++j) sumi += x[i].qs[j] * y[i].qs[j]; sumf += (h2f(x[i].d) * h2f(y[i].d)) * sumi; }
+    return sumf;
+}
 // ---------------------------------------------------------------------------------------------
 // canonical-order reductions (language path) — mirrored 1:1 by csrc/llama_kernels.cuh
 // ---------------------------------------------------------------------------------------------
@@ -432,6 +462,7 @@ static size_t row_bytes(int type, int64_t cols) {
     switch (type) {
         case T_F32: return cols * 4; case T_F16: return cols * 2;
         case T_Q4_0: return cols / 32 * 18; case T_Q4_1: return cols / 32 * 20;
+        case T_Q5_0: return cols / 32 * 22; case T_Q5_1: return cols / 32 * 24; case T_Q8_0: return cols / 32 * 34;
         case T_Q5_K: return cols / 256 * 176; case T_Q6_K: return cols / 256 * 210;
     }
     fprintf(stderr, "oracle: unsupported type %d\n", type); abort();
@@ -451,8 +482,8 @@ static void mul_mat(const Tensor &W, const float *X, int n, float *Y, bool canon
     size_t qrb;
     switch (W.type) {
         case T_F16: qrb = cols * 2; break;
-        case T_Q4_0: qrb = cols / 32 * sizeof(block_q8_0); break;
-        case T_Q4_1: qrb = cols / 32 * sizeof(block_q8_1); break;
+        case T_Q4_0: case T_Q5_0: case T_Q8_0: qrb = cols / 32 * sizeof(block_q8_0); break;
+        case T_Q4_1: case T_Q5_1: qrb = cols / 32 * sizeof(block_q8_1); break;
         default: qrb = cols / 256 * sizeof(block_q8_K); break;
     }
     std::vector<uint8_t> wdata(qrb * (size_t)n);
@@ -461,8 +492,8 @@ static void mul_mat(const Tensor &W, const float *X, int n, float *Y, bool canon
         const float *x = X + (size_t)i * cols; uint8_t *q = wdata.data() + qrb * i;
         switch (W.type) {
             case T_F16: for (int64_t c = 0; c < cols; ++c) ((f16_t *)q)[c] = f2h(x[c]); break;
-            case T_Q4_0: quantize_row_q8_0(x, (block_q8_0 *)q, (int)cols); break;
-            case T_Q4_1: quantize_row_q8_1(x, (block_q8_1 *)q, (int)cols); break;
+            case T_Q4_0: case T_Q5_0: case T_Q8_0: quantize_row_q8_0(x, (block_q8_0 *)q, (int)cols); break;
+            case T_Q4_1: case T_Q5_1: quantize_row_q8_1(x, (block_q8_1 *)q, (int)cols); break;
             default: quantize_row_q8_K(x, (block_q8_K *)q, (int)cols); break;
         }
     }
@@ -471,7 +502,10 @@ static void mul_mat(const Tensor &W, const float *X, int n, float *Y, bool canon
         const uint8_t *w = wd + r * rb;
         for (int i = 0; i < n; ++i) {
             const uint8_t *q = wdata.data() + qrb * i; float v;
-            if (canon) switch (W.type) {
+            if (W.type == T_Q5_0) v = vec_dot_q5_0_q8_0((int)cols, (const block_q5_0 *)w, (const block_q8_0 *)q);
+            else if (W.type == T_Q5_1) v = vec_dot_q5_1_q8_1((int)cols, (const block_q5_1 *)w, (const block_q8_1 *)q);
+            else if (W.type == T_Q8_0) v = vec_dot_q8_0_q8_0((int)cols, (const block_q8_0 *)w, (const block_q8_0 *)q);
+            else if (canon) switch (W.type) {
                 case T_F16: v = dot_canon_f16((int)cols, (const f16_t *)w, (const f16_t *)q); break;
                 case T_Q4_0: v = dot_canon_q4_0((int)cols, (const block_q4_0 *)w, (const block_q8_0 *)q); break;
                 case T_Q4_1: v = dot_canon_q4_1((int)cols, (const block_q4_1 *)w, (const block_q8_1 *)q); break;
@@ -502,6 +536,18 @@ static void dequant_row(const Tensor &W, int64_t r, float *y) {
         case T_Q4_1: { const block_q4_1 *b = (const block_q4_1 *)w;
             for (int i = 0; i < cols / 32; ++i) { float d = h2f(b[i].d), m = h2f(b[i].m);
                 for (int j = 0; j < 16; ++j) { y[i * 32 + j] = (b[i].qs[j] & 0xF) * d + m; y[i * 32 + j + 16] = (b[i].qs[j] >> 4) * d + m; } } } break;
+        case T_Q5_0: { const block_q5_0 *b = (const block_q5_0 *)w;
+            for (int i = 0; i < cols / 32; ++i) { const float d = h2f(b[i].d); uint32_t qh; memcpy(&qh, b[i].qh, 4);
+                for (int j = 0; j < 16; ++j) {
+                    y[i * 32 + j] = (((b[i].qs[j] & 0xF) | (int)(((qh >> j) & 1u) << 4)) - 16) * d;
+                    y[i * 32 + j + 16] = (((b[i].qs[j] >> 4) | (int)(((qh >> (j + 16)) & 1u) << 4)) - 16) * d; } } } break;
+        case T_Q5_1: { const block_q5_1 *b = (const block_q5_1 *)w;
+            for (int i = 0; i < cols / 32; ++i) { const float d = h2f(b[i].d), m = h2f(b[i].m); uint32_t qh; memcpy(&qh, b[i].qh, 4);
+                for (int j = 0; j < 16; ++j) {
+                    y[i * 32 + j] = ((b[i].qs[j] & 0xF) | (int)(((qh >> j) & 1u) << 4)) * d + m;
+                    y[i * 32 + j + 16] = ((b[i].qs[j] >> 4) | (int)(((qh >> (j + 16)) & 1u) << 4)) * d + m; } } } break;
+        case T_Q8_0: { const block_q8_0 *b = (const block_q8_0 *)w;
+            for (int i = 0; i < cols / 32; ++i) { const float d = h2f(b[i].d); for (int j = 0; j < 32; ++j) y[i * 32 + j] = b[i].qs[j] * d; } } break;
         case T_Q5_K: { const block_q5_K *b = (const block_q5_K *)w;
             for (int i = 0; i < cols / 256; ++i) {
                 const uint8_t *ql = b[i].qs, *qh = b[i].qh; const float d = h2f(b[i].d), min = h2f(b[i].dmin);

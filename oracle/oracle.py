@@ -30,7 +30,7 @@ SYSTEM_PROMPT = ("Give the following image: <Img>ImageContent</Img>. You will be
 
 GG_BLOCK = {0: (1, 4), 1: (1, 2), 2: (32, 18), 3: (32, 20), 6: (32, 22), 7: (32, 24), 8: (32, 34), 13: (256, 176), 14: (256, 210)}
 # MiniGPT4DataType -> ggml type (reference minigpt4.cpp:555-739)
-MG4_TO_GG = {0: 1, 1: 0, 4: 2, 5: 3, 6: 6, 7: 7, 8: 8, 13: 13, 14: 14}  # (the oracle reads Q5_0/Q5_1/Q8_0 containers; its mul_mat restates Q4_0/Q4_1/K-quants)
+MG4_TO_GG = {0: 1, 1: 0, 4: 2, 5: 3, 6: 6, 7: 7, 8: 8, 13: 13, 14: 14}
 
 
 def build(force: bool = False) -> Path:
