@@ -190,7 +190,10 @@ def run_reference(args):
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         e.reset_chat()
-        emb = e.encode_image(img) if (it == 0 or args.cpu_encode_every_step) else emb
+        # the image encode (1-2 s of CPU work) runs in the first warm-up step and in the first TIMED step (that one is the reported
+        # encode_ms); later steps reuse the embedding so that the bounded sample stays within minutes
+        encoded = it == 0 or it == args.warmup or args.cpu_encode_every_step
+        emb = e.encode_image(img) if encoded else emb
         t1 = time.perf_counter()
         e.eval_embd(emb)
         t2 = time.perf_counter()
@@ -198,7 +201,8 @@ def run_reference(args):
             e.end_chat_greedy()
         t3 = time.perf_counter()
         if it >= args.warmup:
-            enc_ms.append((t1 - t0) * 1e3); dec_s.append(t3 - t2); step_s.append(t3 - t0)
+            if encoded: enc_ms.append((t1 - t0) * 1e3)
+            dec_s.append(t3 - t2); step_s.append(t3 - t0)
     v = n_tok * len(dec_s) / sum(dec_s)
     line = {"impl": "reference", "metric": "decode tokens/s (Vicuna-7B q4_1) + image-encode ms", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(step_s) / len(step_s), "higher_is_better": True, "scaling": "weak",
