@@ -891,3 +891,4 @@ ORACLE_API int oracle_llama_eval(void *l, const int32_t *tokens, const float *em
 ORACLE_API int oracle_llama_n_vocab(void *l) { return ((Llama *)l)->n_vocab; }
 ORACLE_API int oracle_llama_n_embd(void *l) { return ((Llama *)l)->n_embd; }
 ORACLE_API int oracle_num_threads(void) { return omp_get_max_threads(); }
+ORACLE_API void oracle_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

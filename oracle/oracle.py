@@ -33,6 +33,24 @@ GG_BLOCK = {0: (1, 4), 1: (1, 2), 2: (32, 18), 3: (32, 20), 6: (32, 22), 7: (32,
 MG4_TO_GG = {0: 1, 1: 0, 4: 2, 5: 3, 6: 6, 7: 7, 8: 8, 13: 13, 14: 14}
 
 
+def usable_cpus() -> int:
+    """CPUs this process may actually use: the affinity mask capped by the cgroup CPU quota.  A GPU box shows 128 logical CPUs to a
+    container that is throttled to 16; an OpenMP team of 128 spinning threads on a 16-CPU quota is 10-30x slower than a team of 16
+    (this, not the arithmetic, made the GPU parity suite take 8 minutes)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
+# idle OpenMP workers sleep instead of spinning (must be in the environment before libgomp initialises)
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+
+
 def build(force: bool = False) -> Path:
     so = _HERE / "liboracle.so"
     src = _HERE / "oracle.cpp"
@@ -68,6 +86,7 @@ def lib() -> ctypes.CDLL:
         L.oracle_table.argtypes = [i32]
         L.oracle_table.restype = ctypes.POINTER(ctypes.c_uint16)
         L.oracle_init()
+        L.oracle_set_num_threads(usable_cpus())  # default team for the single-op entry points (mul_mat, ...)
         _LIB = L
     return _LIB
 
@@ -265,7 +284,7 @@ class Tokenizer:
 # ------------------------------------------------------------------------------------------------
 class OracleEngine:
     def __init__(self, minigpt4_path=None, llama_path=None, n_ctx: int = 2048, n_batch: int = 512, n_threads: int = 0):
-        self.n_threads = n_threads or (os.cpu_count() or 1)
+        self.n_threads = n_threads or usable_cpus()
         self.n_batch = n_batch
         self.n_past = 0
         self.vis = None
