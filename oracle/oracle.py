@@ -47,10 +47,6 @@ def usable_cpus() -> int:
     return n
 
 
-# idle OpenMP workers sleep instead of spinning (must be in the environment before libgomp initialises)
-os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
-
-
 def build(force: bool = False) -> Path:
     so = _HERE / "liboracle.so"
     src = _HERE / "oracle.cpp"
