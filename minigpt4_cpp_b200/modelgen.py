@@ -210,6 +210,7 @@ class LlamaSpec:
     tok_type: str | None = None
     overrides: dict = field(default_factory=dict)  # name-suffix -> type, e.g. {"attention.wv.weight": "q6_k"}
     seed: int = 2
+    vocab: list | None = None  # explicit [(piece bytes, score)] of length n_vocab (e.g. converted from a sentencepiece model); default: make_vocab
     # weight-scale knobs (multipliers on the 1/sqrt(fan_in) default) — see DESIGN.md "synthetic weights / conditioning"
     qk_gain: float = 1.0      # wq, wk
     v_gain: float = 1.0       # wv
@@ -234,7 +235,8 @@ FTYPE_OF = {"f32": 0, "f16": 1, "q4_0": 2, "q4_1": 3, "q5_k": 17, "q6_k": 18}
 def write_llama_ggjt(path: str | Path, spec: LlamaSpec) -> dict:
     """Write a ggjt v3 file; returns {'bytes_per_token': algorithmic weight bytes streamed per decoded token}."""
     rng = np.random.default_rng(spec.seed)
-    vocab = make_vocab(spec.n_vocab)
+    vocab = spec.vocab if spec.vocab is not None else make_vocab(spec.n_vocab)
+    assert len(vocab) == spec.n_vocab
     E, FF = spec.n_embd, spec.n_ff
     sig = 1.0 / np.sqrt(E)
     stats = {"bytes_per_token": 0}
