@@ -1,6 +1,7 @@
 // llama.cu — host side of the device-resident LLaMA step (see llama.h, llama_kernels.cuh).
 #include "llama_kernels.cuh"
 #include "llama_mega.cuh"
+#include "llama_mega_ll.cuh"
 #include "tp.h"
 #include <stdlib.h>
 #include <math.h>
@@ -139,6 +140,8 @@ LlamaDevice::~LlamaDevice() {
     if (mega_barrier_) cudaFree(mega_barrier_);
     if (mega_trace_) cudaFree(mega_trace_);
     delete (mk::MegaParams *)mega_params_;
+    delete (mk::MegaParamsLL *)mega_params_ll_;
+    if (mega_ll_buf_) cudaFree(mega_ll_buf_);
     if (h_state_) cudaFreeHost(h_state_);
     if (h_argmax_) cudaFreeHost(h_argmax_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -447,6 +450,19 @@ bool LlamaDevice::build_mega() {
     if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, ops.size() * 16 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, ops.size() * 16 * sizeof(long long))); P->trace = mega_trace_; }
     mega_n_ops_ = (int)ops.size();
     mega_params_ = P;
+    // experimental flag-in-data variant (llama_mega_ll.cuh): the exchanged activation vectors as {value, tag} pairs, one zeroed allocation
+    if (getenv("MINIGPT4_B200_MEGA_LL") && atoi(getenv("MINIGPT4_B200_MEGA_LL")) && !mega_trace_ && ops.size() < 1023 && d_.n_head <= sm_count_) {
+        const size_t nE = (size_t)E, nF = (size_t)FF;
+        const size_t bytes = (3 * nE + nF + nE) * sizeof(LLf) + 256;  // x, q, att | act | kcur + vcur (E/2 each) | seq
+        CUDA_CHECK(cudaMalloc(&mega_ll_buf_, bytes)); CUDA_CHECK(cudaMemset(mega_ll_buf_, 0, bytes));
+        MegaParamsLL *PL = new MegaParamsLL();
+        PL->p = *P;
+        LLf *b = (LLf *)mega_ll_buf_;
+        PL->ll.x = b; PL->ll.q = b + nE; PL->ll.att = b + 2 * nE; PL->ll.act = b + 3 * nE; PL->ll.kcur = b + 3 * nE + nF; PL->ll.vcur = PL->ll.kcur + nE / 2;
+        PL->ll.seq = (unsigned *)(PL->ll.vcur + nE / 2);
+        mega_params_ll_ = PL; mega_ll_ = true;
+        MG4_INFO("decode megakernel: EXPERIMENTAL flag-in-data variant enabled (MINIGPT4_B200_MEGA_LL)");
+    }
     mega_smem_ = (size_t)n_slots * slot + xs_b + act_b + (size_t)n_slots * 16 + ops.size() * sizeof(MegaOp) + 64;
     mega_type_ = wt;
     mega_stk_ = (std::max(E, FF) + 2047) / 2048;
@@ -460,6 +476,7 @@ bool LlamaDevice::build_mega() {
 }
 const void *LlamaDevice::mega_fn() const {
     using namespace mk;
+    if (mega_ll_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel_ll<GG_Q4_1> : (const void *)decode_megakernel_ll<GG_Q4_0>;
     if (mega_trace_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1, true> : (const void *)decode_megakernel<GG_Q4_0, true>;
     return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1, false> : (const void *)decode_megakernel<GG_Q4_0, false>;
 }
@@ -471,7 +488,7 @@ void LlamaDevice::launch_mega() {
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    void *args[1] = {mega_params_};
+    void *args[1] = {mega_ll_ ? mega_params_ll_ : mega_params_};
     CUDA_CHECK(cudaLaunchKernelExC(&cfg, mega_fn(), args));
     ++launches_;
     CUDA_CHECK(cudaMemcpyAsync(h_argmax_, &state_->argmax_id, 4, cudaMemcpyDeviceToHost, stream_));

@@ -102,6 +102,7 @@ private:
     int graph_kernels_ = 0;
     long long *mega_trace_ = nullptr; int mega_n_ops_ = 0;
     int mega_stk_ = 7;
+    bool mega_ll_ = false; void *mega_params_ll_ = nullptr; void *mega_ll_buf_ = nullptr;  // experimental flag-in-data variant (llama_mega_ll.cuh)
     bool mega_ = false; void *mega_ops_ = nullptr; unsigned *mega_barrier_ = nullptr; void *mega_params_ = nullptr; size_t mega_smem_ = 0; int mega_type_ = -1;
     int sm_count_ = 148;
 };
