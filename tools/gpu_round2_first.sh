@@ -1,0 +1,15 @@
+#!/bin/bash
+# First GPU-box call of round 2 (≈ 6 min): re-validate HEAD, try the prepared-but-never-run pieces, re-measure.
+#   gpurun --timeout 700 -- 'bash tools/gpu_round2_first.sh'
+mkdir -p gpurun_out
+run() { name=$1; shift; t=$1; shift; echo "=== $name"; timeout -k 5 $t "$@" > gpurun_out/$name.log 2>&1; rc=$?; echo "exit $rc"; tail -n ${TAILN:-12} gpurun_out/$name.log; return $rc; }
+TAILN=4 run canary 240 python tools/canary.py || { echo "CANARY FAILED - aborting"; exit 1; }
+TAILN=4 run pytest_gpu 300 python -m pytest tests -m gpu -x -q -p no:cacheprovider
+# experimental flag-in-data megakernel: a protocol bug is a hang, so everything runs under a short timeout
+MINIGPT4_B200_MEGA_LL=1 TAILN=6 run canary_ll 150 python tools/canary.py
+NOTRACE=1 TAILN=1 run ab_default 120 python tools/mega_trace.py
+[ -s gpurun_out/canary_ll.log ] && grep -q MISMATCH gpurun_out/canary_ll.log || NOTRACE=1 MINIGPT4_B200_MEGA_LL=1 TAILN=1 run ab_ll 120 python tools/mega_trace.py
+TAILN=22 run trace 200 python tools/mega_trace.py
+TAILN=3 run bench 600 python bench.py --steps 3 --warmup 3 --no-cpu
+TAILN=8 run crosscheck_vllm 400 python tools/crosscheck_vllm_gguf.py
+echo done
