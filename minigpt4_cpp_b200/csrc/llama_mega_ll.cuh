@@ -42,10 +42,13 @@ __device__ __forceinline__ unsigned long long ll_load(const LLf *p) {
     asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return w;
 }
+// Every spin is bounded: a protocol bug must end in a trapped launch (an error the host reports), never in a hung GPU.
+constexpr unsigned kLLSpinLimit = 1u << 22;  // ~ seconds of polling; a healthy wait is microseconds
+__device__ __forceinline__ void ll_spin_guard(unsigned &spins) { if (++spins > kLLSpinLimit) asm volatile("trap;"); }
 // spin until the element carries `tag`; returns the payload bits
 __device__ __forceinline__ unsigned ll_wait(const LLf *p, unsigned tag) {
-    unsigned long long w;
-    do { w = ll_load(p); } while ((unsigned)(w >> 32) != tag);
+    unsigned long long w; unsigned spins = 0;
+    do { w = ll_load(p); ll_spin_guard(spins); } while ((unsigned)(w >> 32) != tag);
     return (unsigned)w;
 }
 // four consecutive elements (one float4 of payload); all four loads are in flight before the first tag is looked at
@@ -63,7 +66,9 @@ __device__ __forceinline__ void stage_plain_ll(const LLf *__restrict__ x, unsign
     unsigned need = 0;
 #pragma unroll
     for (int it = 0; it < kPlainItems; ++it) { xv[it] = make_float4(0.f, 0.f, 0.f, 0.f); if (4 * (tid + kConsumerThreads * it) < cols) need |= 1u << it; }
+    unsigned spins = 0;
     while (need) {
+        ll_spin_guard(spins);
 #pragma unroll
         for (int it = 0; it < kPlainItems; ++it)
             if (need & (1u << it)) { if (ll_try4(x + 4 * (tid + kConsumerThreads * it), tag, xv[it])) need &= ~(1u << it); }
@@ -82,7 +87,9 @@ __device__ __forceinline__ void stage_norm_ll(const LLf *__restrict__ x, unsigne
     unsigned need = 0;
 #pragma unroll
     for (int it = 0; it < kNormItems; ++it) { xv[it] = make_float4(0.f, 0.f, 0.f, 0.f); if (1024 * it + 4 * tid < cols) need |= 1u << it; }
+    unsigned spins = 0;
     while (need) {
+        ll_spin_guard(spins);
 #pragma unroll
         for (int it = 0; it < kNormItems; ++it)
             if (need & (1u << it)) { if (ll_try4(x + 1024 * it + 4 * tid, tag, xv[it])) need &= ~(1u << it); }
