@@ -8,7 +8,7 @@
 namespace mg4 {
 using namespace vk;
 
-struct GemmPlan { CUtensorMap tmW, tmX; GemmArgs a; size_t smem; int grid; };
+struct GemmPlan { CUtensorMap tmW, tmX; GemmArgs a; size_t smem; int grid; int grid_y; };  // grid_y > 0: token-split variant
 
 // ---- TMA descriptor encoding through the driver entry point (no libcuda link dependency) ----------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -49,14 +49,31 @@ static GemmPlan *make_plan(const __half *W, int M, int K, const __half *X, int T
     a.tmem_cols = next_pow2_cols(a.t_pad);
     p->smem = (size_t)a.stages * a.stage_bytes + 1024 + 256;
     p->grid = M / 128;
+    // EXPERIMENTAL (MINIGPT4_B200_VISION_TSPLIT=1): split the tokens of the 257-token GEMMs over grid.y CTAs so that ~132-144 SMs work
+    static const bool tsplit = getenv("MINIGPT4_B200_VISION_TSPLIT") && atoi(getenv("MINIGPT4_B200_VISION_TSPLIT"));
+    if (tsplit && T > 128 && epi != GE_PATCH) {
+        const int splits = std::max(2, std::min(4, 148 / p->grid));            // 33 tiles -> 4, 48 -> 3, 11 / 12 -> 4
+        const int tt = (((T + splits - 1) / splits) + 15) & ~15;               // tokens per CTA, multiple of 16 (UMMA N)
+        a.t_tile = tt; a.t_pad = tt; a.n1 = tt; a.n2 = 0; a.box_rows = tt; a.n_box = 1;
+        a.stage_bytes = 16384 + tt * 128;                                      // stays a multiple of 1024 (128-byte-swizzle atoms)
+        a.stages = std::min(8, (200 * 1024) / a.stage_bytes);
+        a.tmem_cols = next_pow2_cols(tt);
+        p->smem = (size_t)a.stages * a.stage_bytes + 1024 + 256;
+        p->grid_y = (T + tt - 1) / tt;
+    }
     make_map_f16(&p->tmW, W, M, K, 128);
     make_map_f16(&p->tmX, X, T, K, a.box_rows);
     return p;
 }
 static void launch_plan(const GemmPlan *p, cudaStream_t s) {
     static bool configured = false;
-    if (!configured) { CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024)); configured = true; }
-    gemm_f16_tcgen05<<<p->grid, 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        configured = true;
+    }
+    if (p->grid_y > 0) gemm_f16_tcgen05<true><<<dim3((unsigned)p->grid, (unsigned)p->grid_y), 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
+    else gemm_f16_tcgen05<false><<<p->grid, 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
     CUDA_CHECK(cudaGetLastError());
 }
 

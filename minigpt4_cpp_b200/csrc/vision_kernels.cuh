@@ -29,6 +29,7 @@ struct GemmArgs {
     const float *resid;       // GE_RESID: out = resid + (acc + bias)   (may alias out_f32)
     const float *pos;         // GE_PATCH: out[t+1] = acc + bias + pos[t+1]
     const __half *tab_gelu;
+    int t_tile;               // token-split variant only (gemm_f16_tcgen05<true>): tokens per CTA, grid.y = ceil(T / t_tile); t_pad == n1 == t_tile, n2 == 0
 };
 
 // ---- raw PTX wrappers ---------------------------------------------------------------------------------
@@ -78,6 +79,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // out[t][m] = epi( sum_k W[m][k] * X[t][k] )      W: F16 [M_out][K] (TMA map tmW), X: F16 [T][K] (TMA map tmX)
 // grid = M_out/128 CTAs of 192 threads: warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue
 // ---------------------------------------------------------------------------------------------
+// TS = true: EXPERIMENTAL token-split variant (MINIGPT4_B200_VISION_TSPLIT=1, not the default, not yet run - DESIGN.md §7): grid.y CTAs share
+// one 128-feature weight slab and take t_tile tokens each, so the T = 257 GEMMs run on 44-144 SMs instead of 11-48 (r1_v3 ncu: an 11-CTA
+// GEMM is bound by what ONE SM can pull through TMA, 70 GB/s).  Rows past T come back from TMA as zeros and are masked in the epilogue.
+template <bool TS>
 __global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -87,6 +92,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05(const __grid_constant
     uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x;
+    const int t0 = TS ? (int)blockIdx.y * g.t_tile : 0;  // first token of this CTA
     const int num_k = g.K / 64;
 
     if (warp == 0 && lane == 0) {
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05(const __grid_constant
                 unsigned char *sa = smem + (size_t)s * g.stage_bytes, *sb = sa + 16384;
                 mbar_expect_tx(&full[s], tx);
                 tma_load_2d(sa, &tmW, kb * 64, m_tile * 128, &full[s]);
-                for (int b = 0; b < g.n_box; ++b) tma_load_2d(sb + (size_t)b * g.box_rows * 128, &tmX, kb * 64, b * g.box_rows, &full[s]);
+                for (int b = 0; b < g.n_box; ++b) tma_load_2d(sb + (size_t)b * g.box_rows * 128, &tmX, kb * 64, t0 + b * g.box_rows, &full[s]);
             }
         }
     } else if (warp == 1) {
@@ -153,19 +159,19 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05(const __grid_constant
                 const float *src = g.epi == GE_RESID ? g.resid : g.pos;
                 const int off = g.epi == GE_PATCH ? 1 : 0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { const int t = c0 + j; aux[j] = t < g.T ? src[(size_t)(t + off) * g.ld_out + m] : 0.f; }
+                for (int j = 0; j < 16; ++j) { const int t = t0 + c0 + j; aux[j] = t < g.T ? src[(size_t)(t + off) * g.ld_out + m] : 0.f; }
             }
             if (g.epi == GE_GELU_F16) {
                 __half hv[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) hv[j] = g.tab_gelu[__half_as_ushort(__float2half_rn(bias + v[j]))];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { const int t = c0 + j; if (t < g.T) g.out_f16[(size_t)t * g.ld_out + m] = hv[j]; }
+                for (int j = 0; j < 16; ++j) { const int t = t0 + c0 + j; if (t < g.T) g.out_f16[(size_t)t * g.ld_out + m] = hv[j]; }
                 continue;
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int t = c0 + j;
+                const int t = t0 + c0 + j;
                 if (t < g.T) {
                     float r = bias + v[j];
                     switch (g.epi) {
