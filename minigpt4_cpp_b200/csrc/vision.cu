@@ -50,7 +50,7 @@ static GemmPlan *make_plan(const __half *W, int M, int K, const __half *X, int T
     p->smem = (size_t)a.stages * a.stage_bytes + 1024 + 256;
     p->grid = M / 128;
     // EXPERIMENTAL (MINIGPT4_B200_VISION_TSPLIT=1): split the tokens of the 257-token GEMMs over grid.y CTAs so that ~132-144 SMs work
-    static const bool tsplit = getenv("MINIGPT4_B200_VISION_TSPLIT") && atoi(getenv("MINIGPT4_B200_VISION_TSPLIT"));
+    const bool tsplit = getenv("MINIGPT4_B200_VISION_TSPLIT") && atoi(getenv("MINIGPT4_B200_VISION_TSPLIT"));  // (read per plan: a test loads both variants)
     if (tsplit && T > 128 && epi != GE_PATCH) {
         const int splits = std::max(2, std::min(4, 148 / p->grid));            // 33 tiles -> 4, 48 -> 3, 11 / 12 -> 4
         const int tt = (((T + splits - 1) / splits) + 15) & ~15;               // tokens per CTA, multiple of 16 (UMMA N)

@@ -1,0 +1,53 @@
+"""Prepared-but-unmeasured variants (round-2 work).  Skipped unless MG4_EXPERIMENTAL=1:
+
+    MG4_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -m gpu -x -q
+
+* MINIGPT4_B200_MEGA_LL=1       flag-in-data decode megakernel (csrc/llama_mega_ll.cuh): must stay bit-identical to the per-op path / oracle
+* MINIGPT4_B200_VISION_TSPLIT=1 token-split tensor-core GEMMs: each output element keeps its K order, so the embedding must not change at all
+Both are selected by environment variables that the engine reads when a model is loaded."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("MG4_EXPERIMENTAL"), reason="experimental variants: set MG4_EXPERIMENTAL=1")]
+
+
+def test_flag_in_data_megakernel_is_bit_identical(ext, orc, tiny, monkeypatch):
+    for wt in ("q4_1", "q4_0"):
+        ids = list(range(7, 19))
+        monkeypatch.setenv("MINIGPT4_B200_NO_MEGAKERNEL", "1")
+        c1 = ext.llm_load(tiny[wt], n_ctx=512)
+        monkeypatch.delenv("MINIGPT4_B200_NO_MEGAKERNEL")
+        monkeypatch.setenv("MINIGPT4_B200_MEGA_LL", "1")
+        c2 = ext.llm_load(tiny[wt], n_ctx=512)
+        monkeypatch.delenv("MINIGPT4_B200_MEGA_LL")
+        assert ext.stats(c2).decode_megakernel == 1
+        e = orc.OracleEngine(None, tiny[wt], n_ctx=512)
+        ext.eval_tokens(c1, ids); ext.eval_tokens(c2, ids); e.eval_tokens(ids)
+        for _ in range(40):
+            t1, t2 = ext.greedy_id(c1), ext.greedy_id(c2)
+            assert t1 == t2 == int(np.argmax(e.logits))
+            ext.eval_tokens(c1, [t1]); ext.eval_tokens(c2, [t2]); e.eval_tokens([t1])
+            assert np.array_equal(ext.logits(c1), ext.logits(c2)) and np.array_equal(ext.logits(c2), e.logits)
+        # a per-op prefill in between (new prompt rows), then the chained loop: launch sequence numbers keep counting
+        ext.eval_tokens(c1, ids); ext.eval_tokens(c2, ids)
+        ch, _ = ext.decode_chain(c2, 16)
+        host = []
+        for _ in range(16):
+            t = ext.greedy_id(c1); host.append(t); ext.eval_tokens(c1, [t])
+        assert ch.tolist() == host
+        ext.base.minigpt4_free(c1); ext.base.minigpt4_free(c2)
+
+
+def test_token_split_gemms_do_not_change_the_embedding(lib, ext, mg, tiny, tmp_path, monkeypatch):
+    llm = str(tmp_path / "llama-4096.bin")
+    mg.write_llama_ggjt(llm, mg.LlamaSpec(n_vocab=512, n_embd=4096, n_head=32, n_layer=1, wtype="q4_1"))
+    img = mg.synth_image(5)
+    c1 = lib.minigpt4_model_load(tiny["vision"], llm, 1, 1, 64, 8, 0)
+    monkeypatch.setenv("MINIGPT4_B200_VISION_TSPLIT", "1")
+    c2 = lib.minigpt4_model_load(tiny["vision"], llm, 1, 1, 64, 8, 0)
+    monkeypatch.delenv("MINIGPT4_B200_VISION_TSPLIT")
+    a, b = ext.encode_array(c1, img), ext.encode_array(c2, img)
+    assert np.array_equal(a, b), float(np.abs(a - b).max())
+    lib.minigpt4_free(c1); lib.minigpt4_free(c2)

@@ -7,6 +7,7 @@ TAILN=4 run canary 240 python tools/canary.py || { echo "CANARY FAILED - abortin
 TAILN=4 run pytest_gpu 300 python -m pytest tests -m gpu -x -q -p no:cacheprovider
 # experimental flag-in-data megakernel: a protocol bug is a hang, so everything runs under a short timeout
 MINIGPT4_B200_MEGA_LL=1 TAILN=6 run canary_ll 150 python tools/canary.py
+MG4_EXPERIMENTAL=1 TAILN=6 run pytest_experimental 300 python -m pytest tests/test_experimental_gpu.py -m gpu -q -p no:cacheprovider
 NOTRACE=1 TAILN=1 run ab_default 120 python tools/mega_trace.py
 [ -s gpurun_out/canary_ll.log ] && grep -q MISMATCH gpurun_out/canary_ll.log || NOTRACE=1 MINIGPT4_B200_MEGA_LL=1 TAILN=1 run ab_ll 120 python tools/mega_trace.py
 TAILN=22 run trace 200 python tools/mega_trace.py
