@@ -24,8 +24,11 @@ DT_F16, DT_F32, DT_I32, DT_L64 = 0, 1, 2, 3
 DT_Q4_0, DT_Q4_1, DT_Q5_K, DT_Q6_K = 4, 5, 13, 14
 # ggml_type ids used inside ggjt files
 GG_F32, GG_F16, GG_Q4_0, GG_Q4_1, GG_Q5_K, GG_Q6_K = 0, 1, 2, 3, 13, 14
-GG_NAMES = {"f32": GG_F32, "f16": GG_F16, "q4_0": GG_Q4_0, "q4_1": GG_Q4_1, "q5_k": GG_Q5_K, "q6_k": GG_Q6_K}
-GG_BLOCK = {GG_F32: (1, 4), GG_F16: (1, 2), GG_Q4_0: (32, 18), GG_Q4_1: (32, 20), GG_Q5_K: (256, 176), GG_Q6_K: (256, 210)}
+GG_Q5_0, GG_Q5_1, GG_Q8_0, GG_Q4_K = 6, 7, 8, 12  # oracle / file-format support only so far: no CUDA matvec for these on the LLaMA path yet
+GG_NAMES = {"f32": GG_F32, "f16": GG_F16, "q4_0": GG_Q4_0, "q4_1": GG_Q4_1, "q5_k": GG_Q5_K, "q6_k": GG_Q6_K,
+            "q5_0": GG_Q5_0, "q5_1": GG_Q5_1, "q8_0": GG_Q8_0, "q4_k": GG_Q4_K}
+GG_BLOCK = {GG_F32: (1, 4), GG_F16: (1, 2), GG_Q4_0: (32, 18), GG_Q4_1: (32, 20), GG_Q5_K: (256, 176), GG_Q6_K: (256, 210),
+            GG_Q5_0: (32, 22), GG_Q5_1: (32, 24), GG_Q8_0: (32, 34), GG_Q4_K: (256, 144)}
 
 
 def gg_row_bytes(gtype: int, cols: int) -> int:
@@ -69,6 +72,30 @@ def synth_quant(rng: np.random.Generator, gtype: int, rows: int, cols: int, sigm
         out[:, 2:4] = dmin.view(np.uint8).reshape(nblk, 2)
         out[:, 4:16] = pack_scales_k4(sc, mn)
         out[:, 16:] = rng.integers(0, 256, size=(nblk, 160), dtype=np.uint8)
+    elif gtype == GG_Q5_0:
+        # w = d*(q5-16), q5 uniform 0..31 (std 9.23)
+        out[:, 0:2] = (sigma / 9.23 * jitter).astype(np.float16).view(np.uint8).reshape(nblk, 2)
+        out[:, 2:] = rng.integers(0, 256, size=(nblk, 20), dtype=np.uint8)
+    elif gtype == GG_Q5_1:
+        d = (sigma / 9.23 * jitter).astype(np.float16)
+        m = (-15.5 * d.astype(np.float32) * (0.9 + 0.2 * rng.random(nblk, dtype=np.float32))).astype(np.float16)
+        out[:, 0:2] = d.view(np.uint8).reshape(nblk, 2)
+        out[:, 2:4] = m.view(np.uint8).reshape(nblk, 2)
+        out[:, 4:] = rng.integers(0, 256, size=(nblk, 20), dtype=np.uint8)
+    elif gtype == GG_Q8_0:
+        # w = d*q8, q8 uniform -127..127 (std 73.3)
+        out[:, 0:2] = (sigma / 73.3 * jitter).astype(np.float16).view(np.uint8).reshape(nblk, 2)
+        out[:, 2:] = rng.integers(-127, 128, size=(nblk, 32), dtype=np.int8).view(np.uint8)
+    elif gtype == GG_Q4_K:
+        # w = d*sc*q4 - dmin*mn ; q4 uniform 0..15 (std 4.61, mean 7.5)
+        d = (sigma / (4.61 * 44.0) * jitter).astype(np.float16)
+        out[:, 0:2] = d.view(np.uint8).reshape(nblk, 2)
+        sc = rng.integers(24, 64, size=(nblk, 8), dtype=np.uint8)
+        mn = rng.integers(20, 44, size=(nblk, 8), dtype=np.uint8)
+        dmin = (d.astype(np.float32) * 7.5 * 44.0 / 32.0).astype(np.float16)
+        out[:, 2:4] = dmin.view(np.uint8).reshape(nblk, 2)
+        out[:, 4:16] = pack_scales_k4(sc, mn)
+        out[:, 16:] = rng.integers(0, 256, size=(nblk, 128), dtype=np.uint8)
     elif gtype == GG_Q6_K:
         # w = d*sc*(q6-32); q6 uniform 0..63 (std 18.47), sc int8 in +-[32,127]
         out[:, 0:192] = rng.integers(0, 256, size=(nblk, 192), dtype=np.uint8)
@@ -229,7 +256,7 @@ class LlamaSpec:
 
 LLAMA_7B = dict(n_embd=4096, n_head=32, n_layer=32)
 LLAMA_13B = dict(n_embd=5120, n_head=40, n_layer=40)
-FTYPE_OF = {"f32": 0, "f16": 1, "q4_0": 2, "q4_1": 3, "q5_k": 17, "q6_k": 18}
+FTYPE_OF = {"f32": 0, "f16": 1, "q4_0": 2, "q4_1": 3, "q8_0": 7, "q5_0": 8, "q5_1": 9, "q4_k": 15, "q5_k": 17, "q6_k": 18}
 
 
 def write_llama_ggjt(path: str | Path, spec: LlamaSpec) -> dict:

@@ -47,7 +47,7 @@ static inline float h2f(f16_t h) { return _cvtsh_ss(h); }
 static inline f16_t f2h(float f) { return _cvtss_sh(f, 0); }  // round-to-nearest-even
 
 // ggml type ids (ggml.h enum ggml_type at master-31cfbb1)
-enum { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q5_K = 13, T_Q6_K = 14 };
+enum { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
 
 #define QK 32
 #define QK_K 256
@@ -59,6 +59,7 @@ struct block_q5_0 { f16_t d; uint8_t qh[4]; uint8_t qs[16]; };           // 22 B
 struct block_q5_1 { f16_t d; f16_t m; uint8_t qh[4]; uint8_t qs[16]; };  // 24 B
 struct block_q8_0 { f16_t d; int8_t qs[32]; };                           // 34 B
 struct block_q8_1 { float d; float s; int8_t qs[32]; };                  // 40 B (d,s are F32 at this revision)
+struct block_q4_K { f16_t d; f16_t dmin; uint8_t scales[12]; uint8_t qs[128]; };                  // 144 B
 struct block_q5_K { f16_t d; f16_t dmin; uint8_t scales[12]; uint8_t qh[32]; uint8_t qs[128]; }; // 176 B
 struct block_q6_K { uint8_t ql[128]; uint8_t qh[64]; int8_t scales[16]; f16_t d; };             // 210 B
 struct block_q8_K { float d; int8_t qs[256]; int16_t bsums[16]; };        // 292 B
@@ -210,6 +211,42 @@ static float vec_dot_q5_K_q8_K(int n, const block_q5_K *x, const block_q8_K *y) 
             a += 32; m <<= 1;
             for (int l = 0; l < 32; ++l) a[l] = (int8_t)((q4[l] >> 4) + ((hm[l] & m) ? 16 : 0));
             a += 32; m <<= 1; q4 += 32;
+        }
+        uint8_t sc[8], mn[8];
+        for (int j = 0; j < 8; ++j) get_scale_min_k4(j, x[i].scales, &sc[j], &mn[j]);
+        int sumi = 0;
+        for (int j = 0; j < QK_K / 16; ++j) sumi += y[i].bsums[j] * mn[j / 2];
+        a = aux8; int is = 0;
+        for (int j = 0; j < QK_K / 32; ++j) {
+            int32_t scale = sc[is++];
+            for (int r = 0; r < 4; ++r) {
+                for (int l = 0; l < 8; ++l) aux16[l] = (int16_t)(q8[l] * a[l]);
+                for (int l = 0; l < 8; ++l) aux32[l] += scale * aux16[l];
+                q8 += 8; a += 8;
+            }
+        }
+        const float d = h2f(x[i].d) * y[i].d;
+        for (int l = 0; l < 8; ++l) sums[l] += d * aux32[l];
+        const float dmin = h2f(x[i].dmin) * y[i].d;
+        sumf -= dmin * sumi;
+    }
+    for (int l = 0; l < 8; ++l) sumf += sums[l];
+    return sumf;
+}
+// k_quants.c ggml_vec_dot_q4_K_q8_K (scalar shape): Q5_K without the fifth bits
+static float vec_dot_q4_K_q8_K(int n, const block_q4_K *x, const block_q8_K *y) {
+    const int nb = n / QK_K;
+    float sums[8] = {0}; float sumf = 0;
+    int8_t aux8[QK_K]; int16_t aux16[8]; int32_t aux32[8];
+    for (int i = 0; i < nb; ++i) {
+        const uint8_t *q4 = x[i].qs; const int8_t *q8 = y[i].qs;
+        memset(aux32, 0, sizeof(aux32));
+        int8_t *a = aux8;
+        for (int j = 0; j < QK_K / 64; ++j) {
+            for (int l = 0; l < 32; ++l) a[l] = (int8_t)(q4[l] & 0xF);
+            a += 32;
+            for (int l = 0; l < 32; ++l) a[l] = (int8_t)(q4[l] >> 4);
+            a += 32; q4 += 32;
         }
         uint8_t sc[8], mn[8];
         for (int j = 0; j < 8; ++j) get_scale_min_k4(j, x[i].scales, &sc[j], &mn[j]);
@@ -418,6 +455,52 @@ static float dot_canon_q5_K(int n, const block_q5_K *x, const block_q8_K *y) {
     const float sd = butterfly(accd, 32), sm = butterfly(accm, 32);
     return sd - sm;
 }
+// Q4_K: the Q5_K canonical order without the fifth bits (8 lanes per super-block, 4 super-blocks per warp pass)
+static float dot_canon_q4_K(int n, const block_q4_K *x, const block_q8_K *y) {
+    const int nsb = n / QK_K;
+    float accd[32], accm[32];
+    for (int l = 0; l < 32; ++l) { accd[l] = 0.f; accm[l] = 0.f; }
+    for (int sb = 0; sb < nsb; ++sb) {
+        const float d = h2f(x[sb].d), dmin = h2f(x[sb].dmin), d8 = y[sb].d;
+        for (int part = 0; part < 8; ++part) {
+            const int l = 8 * (sb & 3) + part, j = part >> 1, hf = part & 1;
+            uint8_t sca, mna, scb, mnb;
+            get_scale_min_k4(2 * j, x[sb].scales, &sca, &mna); get_scale_min_k4(2 * j + 1, x[sb].scales, &scb, &mnb);
+            int s0 = 0, s1 = 0;
+            for (int i = 0; i < 16; ++i) {
+                const uint8_t qb = x[sb].qs[32 * j + 16 * hf + i];
+                s0 += (qb & 0xF) * y[sb].qs[64 * j + 16 * hf + i]; s1 += (qb >> 4) * y[sb].qs[64 * j + 32 + 16 * hf + i];
+            }
+            accd[l] += (d * d8) * (float)(sca * s0 + scb * s1);
+            accm[l] += (dmin * d8) * (float)(mna * y[sb].bsums[4 * j + hf] + mnb * y[sb].bsums[4 * j + 2 + hf]);
+        }
+    }
+    const float sd = butterfly(accd, 32), sm = butterfly(accm, 32);
+    return sd - sm;
+}
+// Q5_0 / Q5_1 / Q8_0 in the canonical 32-lane strided order (the shapes of dot_canon_q4_0 / q4_1): the specification the CUDA kernels
+// for these types will have to meet bit for bit
+static float dot_canon_q5_0(int n, const block_q5_0 *x, const block_q8_0 *y) {
+    float acc[32];
+    for (int l = 0; l < 32; ++l) acc[l] = 0.f;
+    for (int b = 0; b < n / QK; ++b) { const int l = b & 31; acc[l] += ((float)dot_q5_block(x[b].qs, x[b].qh, y[b].qs, 16) * h2f(x[b].d)) * h2f(y[b].d); }
+    return butterfly(acc, 32);
+}
+static float dot_canon_q5_1(int n, const block_q5_1 *x, const block_q8_1 *y) {
+    float accd[32], accm[32];
+    for (int l = 0; l < 32; ++l) { accd[l] = 0.f; accm[l] = 0.f; }
+    for (int b = 0; b < n / QK; ++b) { const int l = b & 31;
+        accd[l] = fmaf(h2f(x[b].d) * y[b].d, (float)dot_q5_block(x[b].qs, x[b].qh, y[b].qs, 0), accd[l]); accm[l] = fmaf(h2f(x[b].m), y[b].s, accm[l]); }
+    const float sd = butterfly(accd, 32), sm = butterfly(accm, 32);
+    return sd + sm;
+}
+static float dot_canon_q8_0(int n, const block_q8_0 *x, const block_q8_0 *y) {
+    float acc[32];
+    for (int l = 0; l < 32; ++l) acc[l] = 0.f;
+    for (int b = 0; b < n / QK; ++b) { const int l = b & 31; int sumi = 0; for (int j = 0; j < 32; ++j) sumi += x[b].qs[j] * y[b].qs[j];
+        acc[l] += ((float)sumi * h2f(x[b].d)) * h2f(y[b].d); }
+    return butterfly(acc, 32);
+}
 static float dot_canon_q6_K(int n, const block_q6_K *x, const block_q8_K *y) {
     const int nsb = n / QK_K;
     float acc[32];
@@ -463,7 +546,7 @@ static size_t row_bytes(int type, int64_t cols) {
         case T_F32: return cols * 4; case T_F16: return cols * 2;
         case T_Q4_0: return cols / 32 * 18; case T_Q4_1: return cols / 32 * 20;
         case T_Q5_0: return cols / 32 * 22; case T_Q5_1: return cols / 32 * 24; case T_Q8_0: return cols / 32 * 34;
-        case T_Q5_K: return cols / 256 * 176; case T_Q6_K: return cols / 256 * 210;
+        case T_Q4_K: return cols / 256 * 144; case T_Q5_K: return cols / 256 * 176; case T_Q6_K: return cols / 256 * 210;
     }
     fprintf(stderr, "oracle: unsupported type %d\n", type); abort();
 }
@@ -502,9 +585,10 @@ static void mul_mat(const Tensor &W, const float *X, int n, float *Y, bool canon
         const uint8_t *w = wd + r * rb;
         for (int i = 0; i < n; ++i) {
             const uint8_t *q = wdata.data() + qrb * i; float v;
-            if (W.type == T_Q5_0) v = vec_dot_q5_0_q8_0((int)cols, (const block_q5_0 *)w, (const block_q8_0 *)q);
-            else if (W.type == T_Q5_1) v = vec_dot_q5_1_q8_1((int)cols, (const block_q5_1 *)w, (const block_q8_1 *)q);
-            else if (W.type == T_Q8_0) v = vec_dot_q8_0_q8_0((int)cols, (const block_q8_0 *)w, (const block_q8_0 *)q);
+            if (W.type == T_Q5_0) v = canon ? dot_canon_q5_0((int)cols, (const block_q5_0 *)w, (const block_q8_0 *)q) : vec_dot_q5_0_q8_0((int)cols, (const block_q5_0 *)w, (const block_q8_0 *)q);
+            else if (W.type == T_Q5_1) v = canon ? dot_canon_q5_1((int)cols, (const block_q5_1 *)w, (const block_q8_1 *)q) : vec_dot_q5_1_q8_1((int)cols, (const block_q5_1 *)w, (const block_q8_1 *)q);
+            else if (W.type == T_Q8_0) v = canon ? dot_canon_q8_0((int)cols, (const block_q8_0 *)w, (const block_q8_0 *)q) : vec_dot_q8_0_q8_0((int)cols, (const block_q8_0 *)w, (const block_q8_0 *)q);
+            else if (W.type == T_Q4_K) v = canon ? dot_canon_q4_K((int)cols, (const block_q4_K *)w, (const block_q8_K *)q) : vec_dot_q4_K_q8_K((int)cols, (const block_q4_K *)w, (const block_q8_K *)q);
             else if (canon) switch (W.type) {
                 case T_F16: v = dot_canon_f16((int)cols, (const f16_t *)w, (const f16_t *)q); break;
                 case T_Q4_0: v = dot_canon_q4_0((int)cols, (const block_q4_0 *)w, (const block_q8_0 *)q); break;
@@ -548,6 +632,17 @@ static void dequant_row(const Tensor &W, int64_t r, float *y) {
                     y[i * 32 + j + 16] = ((b[i].qs[j] >> 4) | (int)(((qh >> (j + 16)) & 1u) << 4)) * d + m; } } } break;
         case T_Q8_0: { const block_q8_0 *b = (const block_q8_0 *)w;
             for (int i = 0; i < cols / 32; ++i) { const float d = h2f(b[i].d); for (int j = 0; j < 32; ++j) y[i * 32 + j] = b[i].qs[j] * d; } } break;
+        case T_Q4_K: { const block_q4_K *b = (const block_q4_K *)w;
+            for (int i = 0; i < cols / 256; ++i) {
+                const uint8_t *ql = b[i].qs; const float d = h2f(b[i].d), min = h2f(b[i].dmin);
+                int is = 0; uint8_t sc, m; float *yy = y + i * 256;
+                for (int j = 0; j < 256; j += 64) {
+                    get_scale_min_k4(is + 0, b[i].scales, &sc, &m); const float d1 = d * sc, m1 = min * m;
+                    get_scale_min_k4(is + 1, b[i].scales, &sc, &m); const float d2 = d * sc, m2 = min * m;
+                    for (int l = 0; l < 32; ++l) *yy++ = d1 * (ql[l] & 0xF) - m1;
+                    for (int l = 0; l < 32; ++l) *yy++ = d2 * (ql[l] >> 4) - m2;
+                    ql += 32; is += 2;
+                } } } break;
         case T_Q5_K: { const block_q5_K *b = (const block_q5_K *)w;
             for (int i = 0; i < cols / 256; ++i) {
                 const uint8_t *ql = b[i].qs, *qh = b[i].qh; const float d = h2f(b[i].d), min = h2f(b[i].dmin);

@@ -28,9 +28,9 @@ _LIB = None
 SYSTEM_PROMPT = ("Give the following image: <Img>ImageContent</Img>. You will be able to see the image once I provide it to you. "
                  "Please answer my questions.###")  # reference minigpt4.cpp:139
 
-GG_BLOCK = {0: (1, 4), 1: (1, 2), 2: (32, 18), 3: (32, 20), 6: (32, 22), 7: (32, 24), 8: (32, 34), 13: (256, 176), 14: (256, 210)}
+GG_BLOCK = {0: (1, 4), 1: (1, 2), 2: (32, 18), 3: (32, 20), 6: (32, 22), 7: (32, 24), 8: (32, 34), 12: (256, 144), 13: (256, 176), 14: (256, 210)}
 # MiniGPT4DataType -> ggml type (reference minigpt4.cpp:555-739)
-MG4_TO_GG = {0: 1, 1: 0, 4: 2, 5: 3, 6: 6, 7: 7, 8: 8, 13: 13, 14: 14}
+MG4_TO_GG = {0: 1, 1: 0, 4: 2, 5: 3, 6: 6, 7: 7, 8: 8, 12: 12, 13: 13, 14: 14}
 
 
 def usable_cpus() -> int:
