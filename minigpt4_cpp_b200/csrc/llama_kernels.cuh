@@ -26,7 +26,7 @@ enum Epi : int { EPI_PLAIN = 0, EPI_QKV = 1, EPI_RESID = 2, EPI_SWIGLU = 3, EPI_
 enum Act : int { ACT_Q8_0 = 0, ACT_Q8_1 = 1, ACT_Q8_K = 2, ACT_F16 = 3 };
 
 __host__ __device__ constexpr int act_of(int wt) {
-    return wt == GG_Q4_0 ? ACT_Q8_0 : wt == GG_Q4_1 ? ACT_Q8_1 : (wt == GG_Q5_K || wt == GG_Q6_K) ? ACT_Q8_K : ACT_F16;
+    return wt == GG_Q4_0 ? ACT_Q8_0 : wt == GG_Q4_1 ? ACT_Q8_1 : (wt == GG_Q4_K || wt == GG_Q5_K || wt == GG_Q6_K) ? ACT_Q8_K : ACT_F16;
 }
 // bytes of one staged activation vector in shared memory (16-byte aligned)
 __host__ __device__ inline size_t act_bytes(int act, int cols) {
@@ -329,6 +329,65 @@ __device__ __forceinline__ void dot2_q5k(const QMat &w, int r0, const unsigned c
         for (int t = 0; t < NT; ++t) res[r][t] = warp_sum(accd[r][t]) - warp_sum(accm[r][t]);
 }
 
+// Q4_K (EXPERIMENTAL, never run on a GPU yet - reached only by loading a ggjt file that holds Q4_K tensors): Q5_K without the fifth bits;
+// device layout p0 = qs (128 B / super-block), p2 = {scales[12], d, dmin}; canonical order = oracle.cpp dot_canon_q4_K
+template <int NT>
+__device__ __forceinline__ void dot2_q4k(const QMat &w, int r0, const unsigned char *act, size_t astride, int lane, float (&res)[2][NT]) {
+    const int nsb = w.cols / 256;
+    const int sub = lane >> 3, j = (lane & 7) >> 1, hf = lane & 1;  // 8 lanes per super-block: (j, half)
+    float accd[2][NT], accm[2][NT];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { accd[r][t] = 0.f; accm[r][t] = 0.f; }
+    for (int sb0 = 0; sb0 < nsb; sb0 += 4) {
+        const int sb = sb0 + sub;
+        if (sb < nsb) {
+            uint4 qs[2], sc[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const size_t o = (size_t)(r0 + r) * nsb + sb;
+                qs[r] = ldg_stream((const uint4 *)w.p0 + o * 8 + j * 2 + hf);
+                sc[r] = ldg_stream((const uint4 *)w.p2 + o);
+            }
+            int lo[2][4], hi[2][4]; float dd[2], dmin[2]; int sca[2], scb[2], mna[2], mnb[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const unsigned qv[4] = {qs[r].x, qs[r].y, qs[r].z, qs[r].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    lo[r][i] = (int)(qv[i] & 0x0F0F0F0Fu);
+                    hi[r][i] = (int)((qv[i] >> 4) & 0x0F0F0F0Fu);
+                }
+                const unsigned char *sp = (const unsigned char *)&sc[r];
+                scale_min_k4(sp, 2 * j, sca[r], mna[r]); scale_min_k4(sp, 2 * j + 1, scb[r], mnb[r]);
+                const float2 f = __half22float2(*(const __half2 *)&sc[r].w);
+                dd[r] = f.x; dmin[r] = f.y;
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const unsigned char *at = act + t * astride;
+                const int4 a0 = *(const int4 *)(at + sb * 256 + 64 * j + 16 * hf);
+                const int4 a1 = *(const int4 *)(at + sb * 256 + 64 * j + 32 + 16 * hf);
+                const float d8 = ((const float *)(at + w.cols))[sb];
+                const int16_t *bs = (const int16_t *)(at + w.cols + nsb * 4) + sb * 16;
+                const int b0 = bs[4 * j + hf], b1 = bs[4 * j + 2 + hf];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    int s0 = __dp4a(lo[r][0], a0.x, 0); s0 = __dp4a(lo[r][1], a0.y, s0); s0 = __dp4a(lo[r][2], a0.z, s0); s0 = __dp4a(lo[r][3], a0.w, s0);
+                    int s1 = __dp4a(hi[r][0], a1.x, 0); s1 = __dp4a(hi[r][1], a1.y, s1); s1 = __dp4a(hi[r][2], a1.z, s1); s1 = __dp4a(hi[r][3], a1.w, s1);
+                    accd[r][t] += (dd[r] * d8) * (float)(sca[r] * s0 + scb[r] * s1);
+                    accm[r][t] += (dmin[r] * d8) * (float)(mna[r] * b0 + mnb[r] * b1);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) res[r][t] = warp_sum(accd[r][t]) - warp_sum(accm[r][t]);
+}
+
 template <int NT>
 __device__ __forceinline__ void dot2_q6k(const QMat &w, int r0, const unsigned char *act, size_t astride, int lane, float (&res)[2][NT]) {
     const int nsb = w.cols / 256;
@@ -465,6 +524,7 @@ __global__ void __launch_bounds__(kThreads, 2) matvec_kernel(const MatvecArgs a)
             dot2_q4<NT, false>(row0, row0 + a.w.row_bytes, a.w.cols / 32, a.w.cols, WT == GG_Q4_1, smem, astride, lane, res);
         }
         else if (WT == GG_Q5_K) dot2_q5k<NT>(a.w, r0, smem, astride, lane, res);
+        else if (WT == GG_Q4_K) dot2_q4k<NT>(a.w, r0, smem, astride, lane, res);
         else if (WT == GG_Q6_K) dot2_q6k<NT>(a.w, r0, smem, astride, lane, res);
         else dot2_f16<NT>(a.w, r0, smem, astride, lane, res);
 
@@ -680,6 +740,19 @@ __global__ void embed_kernel(int type, const unsigned char *tok, size_t row_byte
     const unsigned char *row = tok + (size_t)st->tokens[t] * row_bytes;
     for (int i = threadIdx.x; i < E; i += blockDim.x) x[(size_t)t * E + i] = dequant_elem(type, row, i);
 }
+// Q4_K token-embedding rows (EXPERIMENTAL, with the Q4_K matvec): kept out of dequant_elem so that the kernels which inline it
+// (embed_kernel, the decode megakernel) stay byte-identical to the measured build
+__global__ void embed_q4k_kernel(const unsigned char *tok, size_t row_bytes, int E, const DeviceState *st, float *x) {
+    const int t = blockIdx.x;
+    const unsigned char *row = tok + (size_t)st->tokens[t] * row_bytes;
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+        const unsigned char *b = row + (i / 256) * 144; const int e = i % 256, sub = e / 32, l = e % 32;
+        const float d = __half2float(*(const __half *)b), dmin = __half2float(*(const __half *)(b + 2));
+        int sc, mn; scale_min_k4(b + 4, sub, sc, mn);
+        const unsigned char qb = b[16 + (sub / 2) * 32 + l]; const int nib = (sub & 1) ? (qb >> 4) : (qb & 0xF);
+        x[(size_t)t * E + i] = (d * (float)sc) * (float)nib - dmin * (float)mn;
+    }
+}
 __global__ void finalize_kernel(DeviceState *st, int want_logits, int *argmax_out) {
     if (threadIdx.x == 0) {
         if (want_logits) {
@@ -722,6 +795,16 @@ __global__ void repack_q5k(const unsigned char *src, int src_nb, int blk0, int n
     const size_t o = (size_t)(r * row_mul + row_off) * dst_nb + dst_blk0 + b;
     for (int j = 0; j < 128; ++j) qs[o * 128 + j] = p[48 + j];
     for (int j = 0; j < 32; ++j) qh[o * 32 + j] = p[16 + j];
+    for (int j = 0; j < 12; ++j) sc[o * 16 + j] = p[4 + j];
+    for (int j = 0; j < 4; ++j) sc[o * 16 + 12 + j] = p[j];
+}
+__global__ void repack_q4k(const unsigned char *src, int src_nb, int blk0, int nblk, int rows, unsigned char *qs, unsigned char *sc, int dst_nb, int row_mul, int row_off, int dst_blk0) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * nblk) return;
+    const int r = (int)(i / nblk), b = (int)(i % nblk);
+    const unsigned char *p = src + ((size_t)r * src_nb + blk0 + b) * 144;  // block_q4_K: d, dmin, scales[12], qs[128]
+    const size_t o = (size_t)(r * row_mul + row_off) * dst_nb + dst_blk0 + b;
+    for (int j = 0; j < 128; ++j) qs[o * 128 + j] = p[16 + j];
     for (int j = 0; j < 12; ++j) sc[o * 16 + j] = p[4 + j];
     for (int j = 0; j < 4; ++j) sc[o * 16 + 12 + j] = p[j];
 }

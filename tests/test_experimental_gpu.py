@@ -51,3 +51,30 @@ def test_token_split_gemms_do_not_change_the_embedding(lib, ext, mg, tiny, tmp_p
     a, b = ext.encode_array(c1, img), ext.encode_array(c2, img)
     assert np.array_equal(a, b), float(np.abs(a - b).max())
     lib.minigpt4_free(c1); lib.minigpt4_free(c2)
+
+
+@pytest.mark.parametrize("shape", [(64, 512), (130, 4096), (48, 11008 - 11008 % 256), (33, 256)])
+@pytest.mark.parametrize("n", [1, 3, 8, 11])
+def test_q4_k_matvec_is_bit_identical(ext, orc, mg, shape, n):
+    """Q4_K device path (dot2_q4k, repack_q4k): prepared from the Q5_K kernel minus the fifth bits, never run when it was committed."""
+    rows, cols = shape
+    rng = np.random.default_rng(rows * 7 + cols + n)
+    raw = mg.synth_quant(rng, 12, rows, cols, 0.02)
+    x = rng.standard_normal((n, cols)).astype(np.float32)
+    x[0, :256] = 0.0
+    assert np.array_equal(ext.op_matvec(12, raw, rows, cols, x), orc.mul_mat(12, raw, rows, cols, x))
+
+
+def test_q4_k_llama_file_matches_oracle(ext, orc, mg, tmp_path):
+    llm = str(tmp_path / "llama-q4_k.bin")
+    mg.write_llama_ggjt(llm, mg.LlamaSpec(n_vocab=1024, n_embd=512, n_head=4, n_layer=2, wtype="q4_k", output_type="q6_k"))
+    c = ext.llm_load(llm, n_ctx=256)
+    e = orc.OracleEngine(None, llm, n_ctx=256)
+    ids = np.random.default_rng(11).integers(3, 1024, size=21).tolist()
+    ext.eval_tokens(c, ids)
+    assert np.array_equal(ext.logits(c), e.eval_tokens(ids))
+    a, b = [], []
+    for _ in range(32):
+        t = ext.greedy_id(c); a.append(t); ext.eval_tokens(c, [t]); b.append(e.end_chat_greedy()[0])
+    assert a == b
+    ext.base.minigpt4_free(c)
