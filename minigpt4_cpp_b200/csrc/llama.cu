@@ -61,6 +61,9 @@ static void launch_matvec(MatvecArgs a, int nt, int sm_count, cudaStream_t s, un
         case GG_Q4_1: launch_mv_nt<GG_Q4_1>(nt, a, grid, smem, s); break;
         case GG_Q5_K: launch_mv_nt<GG_Q5_K>(nt, a, grid, smem, s); break;
         case GG_Q4_K: launch_mv_nt<GG_Q4_K>(nt, a, grid, smem, s); break;
+        case GG_Q5_0: launch_mv_nt<GG_Q5_0>(nt, a, grid, smem, s); break;
+        case GG_Q5_1: launch_mv_nt<GG_Q5_1>(nt, a, grid, smem, s); break;
+        case GG_Q8_0: launch_mv_nt<GG_Q8_0>(nt, a, grid, smem, s); break;
         case GG_Q6_K: launch_mv_nt<GG_Q6_K>(nt, a, grid, smem, s); break;
         case GG_F16: launch_mv_nt<GG_F16>(nt, a, grid, smem, s); break;
         default: MG4_PANIC("no matvec kernel for ggml type %d", a.w.type);
@@ -72,7 +75,9 @@ static void launch_matvec(MatvecArgs a, int nt, int sm_count, cudaStream_t s, un
 // ------------------------------------------------------------------------------------------------
 // weight upload + repack
 // ------------------------------------------------------------------------------------------------
-static bool type_supported(int t) { return t == GG_Q4_0 || t == GG_Q4_1 || t == GG_Q4_K || t == GG_Q5_K || t == GG_Q6_K || t == GG_F16; }  // (Q4_K: experimental, unmeasured)
+static bool type_supported(int t) {  // (Q4_K, Q5_0, Q5_1, Q8_0: experimental device paths, not yet run - tests/test_experimental_gpu.py)
+    return t == GG_Q4_0 || t == GG_Q4_1 || t == GG_Q4_K || t == GG_Q5_K || t == GG_Q6_K || t == GG_F16 || t == GG_Q5_0 || t == GG_Q5_1 || t == GG_Q8_0;
+}
 
 static void qmat_alloc(QMat &m, int type, int rows, int cols) {
     m.type = type; m.rows = (rows + 1) & ~1; m.cols = cols;
@@ -83,6 +88,9 @@ static void qmat_alloc(QMat &m, int type, int rows, int cols) {
         case GG_Q4_1: m.row_bytes = (cols / 32 * 20 + 15) & ~15; zalloc(&m.p0, R * m.row_bytes + 256); break;
         case GG_Q5_K: zalloc(&m.p0, R * cols / 256 * 128); zalloc(&m.p1, R * cols / 256 * 32); zalloc(&m.p2, R * cols / 256 * 16); break;
         case GG_Q4_K: zalloc(&m.p0, R * cols / 256 * 128); zalloc(&m.p2, R * cols / 256 * 16); break;
+        case GG_Q8_0: zalloc(&m.p0, R * cols / 32 * 32); zalloc(&m.p2, R * cols / 32 * 2); break;
+        case GG_Q5_0: zalloc(&m.p0, R * cols / 32 * 16); zalloc(&m.p1, R * cols / 32 * 4); zalloc(&m.p2, R * cols / 32 * 2); break;
+        case GG_Q5_1: zalloc(&m.p0, R * cols / 32 * 16); zalloc(&m.p1, R * cols / 32 * 4); zalloc(&m.p2, R * cols / 32 * 4); break;
         case GG_Q6_K: zalloc(&m.p0, R * cols / 256 * 128); zalloc(&m.p1, R * cols / 256 * 64); zalloc(&m.p2, R * cols / 256 * 16); zalloc(&m.p3, R * cols / 256 * 2); break;
         case GG_F16: zalloc(&m.p0, R * cols * 2); break;
         default: MG4_PANIC("unsupported weight type %d", type);
@@ -117,6 +125,8 @@ static void repack_into(QMat &dst, const HostTensor &src, Stager &st, int row0, 
         case GG_Q4_1: repack_q4<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, true, (unsigned char *)dst.p0, dst_nb, dst.row_bytes, row_mul, row_off, dblk0); break;
         case GG_Q5_K: repack_q5k<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, (unsigned char *)dst.p0, (unsigned char *)dst.p1, (unsigned char *)dst.p2, dst_nb, row_mul, row_off, dblk0); break;
         case GG_Q4_K: repack_q4k<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, (unsigned char *)dst.p0, (unsigned char *)dst.p2, dst_nb, row_mul, row_off, dblk0); break;
+        case GG_Q5_0: case GG_Q5_1: case GG_Q8_0:
+            repack_b32<<<gr, th>>>(src.gg, raw, src_nb, blk0, nblk, nrows, (unsigned char *)dst.p0, (unsigned char *)dst.p1, (unsigned char *)dst.p2, dst_nb, row_mul, row_off, dblk0); break;
         case GG_Q6_K: repack_q6k<<<gr, th>>>(raw, src_nb, blk0, nblk, nrows, (unsigned char *)dst.p0, (unsigned char *)dst.p1, (unsigned char *)dst.p2, (unsigned short *)dst.p3, dst_nb, row_mul, row_off, dblk0); break;
         case GG_F16: repack_f16<<<gr, th>>>((const unsigned short *)raw, src_cols, col0, ncols, nrows, (unsigned short *)dst.p0, dst.cols, row_mul, row_off, dst_col0); break;
         default: MG4_PANIC("unsupported weight type %d", src.gg);
@@ -323,6 +333,7 @@ void LlamaDevice::run_chunk(int n, bool want_logits, bool from_tokens) {
     CUDA_CHECK(cudaMemcpyAsync(state_, h_state_, offsetof(DeviceState, argmax_key), cudaMemcpyHostToDevice, stream_));
     if (from_tokens) {
         if (tok_type_ == GG_Q4_K) embed_q4k_kernel<<<n, 256, 0, stream_>>>((const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, state_, x_);
+        else if (tok_type_ == GG_Q5_0 || tok_type_ == GG_Q5_1 || tok_type_ == GG_Q8_0) embed_b32_kernel<<<n, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, state_, x_);
         else embed_kernel<<<n, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, state_, x_);
         ++launches_;
     }
@@ -506,6 +517,7 @@ void LlamaDevice::build_graph() {
     if (mega_) launch_mega();
     else {
         if (tok_type_ == GG_Q4_K) embed_q4k_kernel<<<1, 256, 0, stream_>>>((const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, state_, x_);
+        else if (tok_type_ == GG_Q5_0 || tok_type_ == GG_Q5_1 || tok_type_ == GG_Q8_0) embed_b32_kernel<<<1, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, state_, x_);
         else embed_kernel<<<1, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, state_, x_);
         launch_layers(1, 1, true);
     }

@@ -26,7 +26,8 @@ enum Epi : int { EPI_PLAIN = 0, EPI_QKV = 1, EPI_RESID = 2, EPI_SWIGLU = 3, EPI_
 enum Act : int { ACT_Q8_0 = 0, ACT_Q8_1 = 1, ACT_Q8_K = 2, ACT_F16 = 3 };
 
 __host__ __device__ constexpr int act_of(int wt) {
-    return wt == GG_Q4_0 ? ACT_Q8_0 : wt == GG_Q4_1 ? ACT_Q8_1 : (wt == GG_Q4_K || wt == GG_Q5_K || wt == GG_Q6_K) ? ACT_Q8_K : ACT_F16;
+    return (wt == GG_Q4_0 || wt == GG_Q5_0 || wt == GG_Q8_0) ? ACT_Q8_0 : (wt == GG_Q4_1 || wt == GG_Q5_1) ? ACT_Q8_1
+         : (wt == GG_Q4_K || wt == GG_Q5_K || wt == GG_Q6_K) ? ACT_Q8_K : ACT_F16;
 }
 // bytes of one staged activation vector in shared memory (16-byte aligned)
 __host__ __device__ inline size_t act_bytes(int act, int cols) {
@@ -329,6 +330,64 @@ __device__ __forceinline__ void dot2_q5k(const QMat &w, int r0, const unsigned c
         for (int t = 0; t < NT; ++t) res[r][t] = warp_sum(accd[r][t]) - warp_sum(accm[r][t]);
 }
 
+// Q5_0 / Q5_1 / Q8_0 (EXPERIMENTAL, never run on a GPU yet - reached only by loading a ggjt file that holds such tensors).  Device layout
+// (planes, [row][block]): p0 = payload (Q8_0: 32 int8; Q5_x: 16 B of nibbles), p1 = Q5_x fifth bits (32-bit qh), p2 = half d (Q5_0, Q8_0) or
+// half2 {d, m} (Q5_1).  Canonical order = oracle.cpp dot_canon_q5_0 / q5_1 / q8_0: lane l owns blocks l, l+32, ...; xor butterflies.
+__device__ __forceinline__ unsigned spread4_to_bit4(unsigned n) { return ((n * 0x00204081u) & 0x01010101u) << 4; }  // bit i of n (< 16) -> bit 4 of byte i
+template <int WT, int NT>
+__device__ __forceinline__ void dot2_b32(const QMat &w, int r0, const unsigned char *act, size_t astride, int lane, float (&res)[2][NT]) {
+    constexpr bool Q8 = WT == GG_Q8_0, Q51 = WT == GG_Q5_1;
+    const int nb = w.cols / 32, cols = w.cols;
+    float accd[2][NT], accm[2][NT];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { accd[r][t] = 0.f; accm[r][t] = 0.f; }
+    for (int b = lane; b < nb; b += 32) {
+        int lo[2][4], hi[2][4]; float dv[2], mv[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const size_t o = (size_t)(r0 + r) * nb + b;
+            if (Q8) {
+                const uint4 q0 = ldg_stream((const uint4 *)w.p0 + o * 2), q1 = ldg_stream((const uint4 *)w.p0 + o * 2 + 1);
+                lo[r][0] = (int)q0.x; lo[r][1] = (int)q0.y; lo[r][2] = (int)q0.z; lo[r][3] = (int)q0.w;
+                hi[r][0] = (int)q1.x; hi[r][1] = (int)q1.y; hi[r][2] = (int)q1.z; hi[r][3] = (int)q1.w;
+            } else {
+                const uint4 q = ldg_stream((const uint4 *)w.p0 + o);
+                const unsigned qh = ldg_stream((const unsigned *)w.p1 + o);
+                const unsigned wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    unsigned l5 = (wv[k] & 0x0F0F0F0Fu) | spread4_to_bit4((qh >> (4 * k)) & 0xFu);
+                    unsigned h5 = ((wv[k] >> 4) & 0x0F0F0F0Fu) | spread4_to_bit4((qh >> (16 + 4 * k)) & 0xFu);
+                    if (!Q51) { l5 = __vsub4(l5, 0x10101010u); h5 = __vsub4(h5, 0x10101010u); }
+                    lo[r][k] = (int)l5; hi[r][k] = (int)h5;
+                }
+            }
+            if (Q51) { const unsigned a = ldg_stream((const unsigned *)w.p2 + o); const float2 f = __half22float2(*(const __half2 *)&a); dv[r] = f.x; mv[r] = f.y; }
+            else { dv[r] = __half2float(((const __half *)w.p2)[o]); mv[r] = 0.f; }
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const unsigned char *at = act + t * astride;
+            const int4 a0 = *(const int4 *)(at + b * 16), a1 = *(const int4 *)(at + cols / 2 + b * 16);
+            const float ad = ((const float *)(at + cols))[b];
+            const float as = ((const float *)(at + cols))[nb + b];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                int sdot = __dp4a(lo[r][0], a0.x, 0); sdot = __dp4a(lo[r][1], a0.y, sdot); sdot = __dp4a(lo[r][2], a0.z, sdot); sdot = __dp4a(lo[r][3], a0.w, sdot);
+                sdot = __dp4a(hi[r][0], a1.x, sdot); sdot = __dp4a(hi[r][1], a1.y, sdot); sdot = __dp4a(hi[r][2], a1.z, sdot); sdot = __dp4a(hi[r][3], a1.w, sdot);
+                if (Q51) { accd[r][t] = fmaf(dv[r] * ad, (float)sdot, accd[r][t]); accm[r][t] = fmaf(mv[r], as, accm[r][t]); }
+                else { accd[r][t] += ((float)sdot * dv[r]) * ad; }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) res[r][t] = warp_sum(accd[r][t]) + warp_sum(accm[r][t]);
+}
+
 // Q4_K (EXPERIMENTAL, never run on a GPU yet - reached only by loading a ggjt file that holds Q4_K tensors): Q5_K without the fifth bits;
 // device layout p0 = qs (128 B / super-block), p2 = {scales[12], d, dmin}; canonical order = oracle.cpp dot_canon_q4_K
 template <int NT>
@@ -525,6 +584,7 @@ __global__ void __launch_bounds__(kThreads, 2) matvec_kernel(const MatvecArgs a)
         }
         else if (WT == GG_Q5_K) dot2_q5k<NT>(a.w, r0, smem, astride, lane, res);
         else if (WT == GG_Q4_K) dot2_q4k<NT>(a.w, r0, smem, astride, lane, res);
+        else if (WT == GG_Q5_0 || WT == GG_Q5_1 || WT == GG_Q8_0) dot2_b32<WT, NT>(a.w, r0, smem, astride, lane, res);
         else if (WT == GG_Q6_K) dot2_q6k<NT>(a.w, r0, smem, astride, lane, res);
         else dot2_f16<NT>(a.w, r0, smem, astride, lane, res);
 
@@ -753,6 +813,25 @@ __global__ void embed_q4k_kernel(const unsigned char *tok, size_t row_bytes, int
         x[(size_t)t * E + i] = (d * (float)sc) * (float)nib - dmin * (float)mn;
     }
 }
+// token-embedding rows of Q5_0 / Q5_1 / Q8_0 files (ggml dequantize_row_q5_0 / q5_1 / q8_0), raw ggml blocks; kept out of dequant_elem (see above)
+__global__ void embed_b32_kernel(int type, const unsigned char *tok, size_t row_bytes, int E, const DeviceState *st, float *x) {
+    const int t = blockIdx.x;
+    const unsigned char *row = tok + (size_t)st->tokens[t] * row_bytes;
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+        const int j = i % 32, jj = j & 15;
+        float v;
+        if (type == GG_Q8_0) { const unsigned char *b = row + (i / 32) * 34; v = (float)(int)(signed char)b[2 + j] * __half2float(*(const __half *)b); }
+        else {
+            const int hdr = type == GG_Q5_1 ? 4 : 2;
+            const unsigned char *b = row + (i / 32) * (hdr + 20);
+            const unsigned qh = b[hdr] | (b[hdr + 1] << 8) | (b[hdr + 2] << 16) | ((unsigned)b[hdr + 3] << 24);
+            const int q = (j < 16 ? (b[hdr + 4 + jj] & 0xF) : (b[hdr + 4 + jj] >> 4)) | (int)(((qh >> j) & 1u) << 4);
+            const float d = __half2float(*(const __half *)b);
+            v = type == GG_Q5_1 ? (float)q * d + __half2float(*(const __half *)(b + 2)) : (float)(q - 16) * d;
+        }
+        x[(size_t)t * E + i] = v;
+    }
+}
 __global__ void finalize_kernel(DeviceState *st, int want_logits, int *argmax_out) {
     if (threadIdx.x == 0) {
         if (want_logits) {
@@ -797,6 +876,23 @@ __global__ void repack_q5k(const unsigned char *src, int src_nb, int blk0, int n
     for (int j = 0; j < 32; ++j) qh[o * 32 + j] = p[16 + j];
     for (int j = 0; j < 12; ++j) sc[o * 16 + j] = p[4 + j];
     for (int j = 0; j < 4; ++j) sc[o * 16 + 12 + j] = p[j];
+}
+__global__ void repack_b32(int type, const unsigned char *src, int src_nb, int blk0, int nblk, int rows, unsigned char *p0, unsigned char *p1, unsigned char *p2, int dst_nb, int row_mul, int row_off, int dst_blk0) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * nblk) return;
+    const int r = (int)(i / nblk), b = (int)(i % nblk);
+    const size_t o = (size_t)(r * row_mul + row_off) * dst_nb + dst_blk0 + b;
+    if (type == GG_Q8_0) {
+        const unsigned char *p = src + ((size_t)r * src_nb + blk0 + b) * 34;  // block_q8_0: d, qs[32]
+        for (int j = 0; j < 32; ++j) p0[o * 32 + j] = p[2 + j];
+        p2[o * 2] = p[0]; p2[o * 2 + 1] = p[1];
+    } else {
+        const int hdr = type == GG_Q5_1 ? 4 : 2;                              // block_q5_0: d, qh[4], qs[16]; block_q5_1: d, m, qh[4], qs[16]
+        const unsigned char *p = src + ((size_t)r * src_nb + blk0 + b) * (hdr + 20);
+        for (int j = 0; j < 16; ++j) p0[o * 16 + j] = p[hdr + 4 + j];
+        for (int j = 0; j < 4; ++j) p1[o * 4 + j] = p[hdr + j];
+        for (int j = 0; j < hdr; ++j) p2[o * hdr + j] = p[j];
+    }
 }
 __global__ void repack_q4k(const unsigned char *src, int src_nb, int blk0, int nblk, int rows, unsigned char *qs, unsigned char *sc, int dst_nb, int row_mul, int row_off, int dst_blk0) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
