@@ -466,7 +466,7 @@ bool LlamaDevice::build_mega() {
     mega_n_ops_ = (int)ops.size();
     mega_params_ = P;
     // experimental flag-in-data variant (llama_mega_ll.cuh): the exchanged activation vectors as {value, tag} pairs, one zeroed allocation
-    if (getenv("MINIGPT4_B200_MEGA_LL") && atoi(getenv("MINIGPT4_B200_MEGA_LL")) && !mega_trace_ && ops.size() < 1023 && d_.n_head <= sm_count_) {
+    if (getenv("MINIGPT4_B200_MEGA_LL") && atoi(getenv("MINIGPT4_B200_MEGA_LL")) && ops.size() < 1023 && d_.n_head <= sm_count_) {
         const size_t nE = (size_t)E, nF = (size_t)FF;
         const size_t bytes = (3 * nE + nF + nE) * sizeof(LLf) + 256;  // x, q, att | act | kcur + vcur (E/2 each) | seq
         CUDA_CHECK(cudaMalloc(&mega_ll_buf_, bytes)); CUDA_CHECK(cudaMemset(mega_ll_buf_, 0, bytes));
@@ -491,7 +491,8 @@ bool LlamaDevice::build_mega() {
 }
 const void *LlamaDevice::mega_fn() const {
     using namespace mk;
-    if (mega_ll_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel_ll<GG_Q4_1> : (const void *)decode_megakernel_ll<GG_Q4_0>;
+    if (mega_ll_ && mega_trace_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel_ll<GG_Q4_1, true> : (const void *)decode_megakernel_ll<GG_Q4_0, true>;
+    if (mega_ll_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel_ll<GG_Q4_1, false> : (const void *)decode_megakernel_ll<GG_Q4_0, false>;
     if (mega_trace_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1, true> : (const void *)decode_megakernel<GG_Q4_0, true>;
     return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1, false> : (const void *)decode_megakernel<GG_Q4_0, false>;
 }

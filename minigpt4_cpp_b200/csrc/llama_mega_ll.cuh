@@ -66,7 +66,7 @@ __device__ __forceinline__ bool ll_try4(const LLf *p, unsigned tag, float4 &out)
 
 // un-normed inputs (wo <- att, down <- act), all 480 consumer threads; same element ownership as stage_plain_mega
 template <int ACT>
-__device__ __forceinline__ void stage_plain_ll(const LLf *__restrict__ x, unsigned tag, int cols, unsigned char *sm) {
+__device__ __forceinline__ void stage_plain_ll(const LLf *__restrict__ x, unsigned tag, int cols, unsigned char *sm, long long *tr) {
     const int tid = threadIdx.x;
     float4 xv[kPlainItems];
     unsigned need = 0;
@@ -79,6 +79,7 @@ __device__ __forceinline__ void stage_plain_ll(const LLf *__restrict__ x, unsign
         for (int it = 0; it < kPlainItems; ++it)
             if (need & (1u << it)) { if (ll_try4(x + 4 * (tid + kConsumerThreads * it), tag, xv[it])) need &= ~(1u << it); }
     }
+    if (tr) tr[1] = clock64();  // this thread's share of the input has arrived
 #pragma unroll
     for (int it = 0; it < kPlainItems; ++it) {
         const int i = 4 * (tid + kConsumerThreads * it);
@@ -87,7 +88,7 @@ __device__ __forceinline__ void stage_plain_ll(const LLf *__restrict__ x, unsign
 }
 // RMS-normed inputs (qkv, gate/up, output <- x), warps 0-7; same element ownership and reduction order as stage_norm_mega
 template <int ACT>
-__device__ __forceinline__ void stage_norm_ll(const LLf *__restrict__ x, unsigned tag, const float *__restrict__ nw, int cols, unsigned char *sm, double *red) {
+__device__ __forceinline__ void stage_norm_ll(const LLf *__restrict__ x, unsigned tag, const float *__restrict__ nw, int cols, unsigned char *sm, double *red, long long *tr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // tid < 256
     float4 xv[kNormItems];
     unsigned need = 0;
@@ -100,6 +101,7 @@ __device__ __forceinline__ void stage_norm_ll(const LLf *__restrict__ x, unsigne
         for (int it = 0; it < kNormItems; ++it)
             if (need & (1u << it)) { if (ll_try4(x + 1024 * it + 4 * tid, tag, xv[it])) need &= ~(1u << it); }
     }
+    if (tr) tr[1] = clock64();  // this thread's share of the input has arrived
     float4 w[kNormItems];
     load_norm_weights(nw, cols, w);
     double ssa = 0.0, ssb = 0.0;
@@ -131,7 +133,7 @@ __device__ __forceinline__ void stage_norm_ll(const LLf *__restrict__ x, unsigne
 
 // front half of a matvec op: wait (on the data itself) for the input vector, stage it as Q8 blocks in shared memory
 template <int ACT>
-__device__ __forceinline__ void stage_op_ll(const MegaParamsLL &PL, int oi, unsigned tag_in) {
+__device__ __forceinline__ void stage_op_ll(const MegaParamsLL &PL, int oi, unsigned tag_in, long long *tr) {
     __shared__ double red[34];
     const MegaParams &P = PL.p;
     const MegaSmem m = carve_smem(P);
@@ -141,9 +143,10 @@ __device__ __forceinline__ void stage_op_ll(const MegaParamsLL &PL, int oi, unsi
     if (nw && tid * 32 < cols) prefetch_l2(nw + tid * 32);
     consumer_sync();  // every consumer warp of this CTA has finished the previous op: the staging area may be overwritten
     const LLf *src = kind == OP_WO ? PL.ll.att : kind == OP_DOWN ? PL.ll.act : PL.ll.x;
-    if (nw) { if (tid < 256) stage_norm_ll<ACT>(src, tag_in, nw, cols, m.actb, red); }
-    else stage_plain_ll<ACT>(src, tag_in, cols, m.actb);
+    if (nw) { if (tid < 256) stage_norm_ll<ACT>(src, tag_in, nw, cols, m.actb, red, tr); }
+    else stage_plain_ll<ACT>(src, tag_in, cols, m.actb, tr);
     consumer_sync();
+    if (tr) tr[2] = clock64();
 }
 
 // matvec phase of one op: as consume_units, with tagged outputs
@@ -219,7 +222,9 @@ __device__ __forceinline__ unsigned consume_units_ll(const MegaParamsLL &PL, int
     return n_next;
 }
 
-template <int WT>
+// TRACE: per-op clock stamps of thread 0 of CTA 0 and CTA G-1 in the layout tools/mega_trace.py reads ({op start, input arrived, staged, done};
+// the "barrier" column then means "waiting for the input data"); the per-unit fields stay zero
+template <int WT, bool TRACE>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel_ll(const __grid_constant__ MegaParamsLL PL) {
     __shared__ double red[34];
     __shared__ float redf[34];
@@ -251,6 +256,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel_ll(const __
     for (int oi = 0; oi < P.n_ops; ++oi) {
         const int kind = ops[oi].kind;
         const unsigned tag = tag0 + (unsigned)oi;
+        long long *tr = nullptr;
+        if (TRACE) { if (P.trace && tid == 0 && (cta == 0 || cta == G - 1)) tr = P.trace + ((size_t)(cta == 0 ? 0 : 1) * P.n_ops + oi) * 8; }
+        if (TRACE && tr) { tr[0] = clock64(); tr[1] = tr[0]; tr[2] = 0; tr[3] = 0; tr[4] = 0; tr[5] = 0; tr[6] = 0; tr[7] = 0; }
         if (kind == OP_EMBED) {
             const int token = __ldcg(&P.state->tokens[0]);
             const unsigned char *row = P.tok + (size_t)token * P.tok_row_bytes;
@@ -270,6 +278,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel_ll(const __
                     else { const int j = tid - 192; *(unsigned *)(P.vcache + lo + (size_t)pos * E + h * 128 + 2 * j) = ll_wait(PL.ll.vcur + h * 64 + j, tag_qkv); }
                     __threadfence_block();
                     cta_sync<true>();
+                    if (TRACE && tr) tr[1] = clock64();
                     attention_mega(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, h, E, P.n_ctx, P.kq_scale, P.tab_exp, m.actb, red, redf, qh, part);
                     if (tid < 128) ll_store(PL.ll.att + h * 128 + tid, __ldcg(&P.att[h * 128 + tid]), tag);  // (each thread re-reads its own store)
                 }
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel_ll(const __
         }
         // ---- matvec ops ----
         const unsigned tag_in = kind == OP_WO ? tag_att : kind == OP_DOWN ? tag_act : tag_x;
-        stage_op_ll<ACT>(PL, oi, tag_in);
+        stage_op_ll<ACT>(PL, oi, tag_in, TRACE ? tr : nullptr);
         if (kind == OP_QKV && (P.flags & 1) && cta < P.n_head && tid < 256) {
             const size_t lo = (size_t)ops[oi].layer * P.n_ctx * P.E;
             prefetch_kv_head(P.kcache + lo, P.vcache + lo, pos, cta, P.E);
@@ -303,6 +312,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel_ll(const __
             case OP_DOWN:   n_base = consume_units_ll<Q41, OP_DOWN>(PL, oi, n_base, pos, tag); tag_x = tag; break;
             default:        n_base = consume_units_ll<Q41, OP_OUTPUT>(PL, oi, n_base, pos, tag); break;
         }
+        if (TRACE && tr) tr[3] = clock64();
     }
 }
 

@@ -11,6 +11,7 @@ MG4_EXPERIMENTAL=1 TAILN=6 run pytest_experimental 300 python -m pytest tests/te
 NOTRACE=1 TAILN=1 run ab_default 120 python tools/mega_trace.py
 [ -s gpurun_out/canary_ll.log ] && grep -q MISMATCH gpurun_out/canary_ll.log || NOTRACE=1 MINIGPT4_B200_MEGA_LL=1 TAILN=1 run ab_ll 120 python tools/mega_trace.py
 TAILN=22 run trace 200 python tools/mega_trace.py
+MINIGPT4_B200_MEGA_LL=1 TAILN=22 run trace_ll 200 python tools/mega_trace.py   # "barrier" column = waiting for the input data
 # experimental token-split vision GEMMs: correctness first (encode + kernel seams), then encode time
 MINIGPT4_B200_VISION_TSPLIT=1 TAILN=4 run pytest_tsplit 300 python -m pytest tests/test_e2e_gpu.py tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "encode_image or chat_flow or gemm"
 TAILN=1 run encode_default 200 python tools/prof_vision.py
