@@ -8,7 +8,7 @@
 namespace mg4 {
 using namespace vk;
 
-struct GemmPlan { CUtensorMap tmW, tmX; GemmArgs a; size_t smem; int grid; int grid_y; };  // grid_y > 0: token-split variant
+struct GemmPlan { CUtensorMap tmW, tmX; GemmArgs a; size_t smem; int grid; int grid_y; int grid_z; SplitKArgs sk; };  // grid_y > 0: token-split variant; grid_z > 1: + split-K
 
 // ---- TMA descriptor encoding through the driver entry point (no libcuda link dependency) ----------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -35,7 +35,7 @@ static void make_map_f16(CUtensorMap *m, const void *ptr, int rows, int cols, in
 
 static int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
 
-static GemmPlan *make_plan(const __half *W, int M, int K, const __half *X, int T, int epi) {
+static GemmPlan *make_plan(const __half *W, int M, int K, const __half *X, int T, int epi, int ksplit = 1) {
     if (M % 128 || K % 64 || T < 1 || T > 272) MG4_PANIC("gemm plan: unsupported shape M=%d K=%d T=%d", M, K, T);
     GemmPlan *p = new GemmPlan();
     memset(p, 0, sizeof(*p));
@@ -60,6 +60,11 @@ static GemmPlan *make_plan(const __half *W, int M, int K, const __half *X, int T
         a.tmem_cols = next_pow2_cols(tt);
         p->smem = (size_t)a.stages * a.stage_bytes + 1024 + 256;
         p->grid_y = (T + tt - 1) / tt;
+        if (ksplit > 1 && ksplit <= K / 64) {                                  // split-K: grid.z slices of whole k-blocks, raw partials out (GE_PARTIAL)
+            p->sk.k_split_blocks = (K / 64 + ksplit - 1) / ksplit;
+            p->grid_z = (K / 64 + p->sk.k_split_blocks - 1) / p->sk.k_split_blocks;
+            if (p->grid_z > 1) a.epi = GE_PARTIAL; else { p->sk.k_split_blocks = 0; p->grid_z = 0; }
+        }
     }
     make_map_f16(&p->tmW, W, M, K, 128);
     make_map_f16(&p->tmX, X, T, K, a.box_rows);
@@ -72,7 +77,11 @@ static void launch_plan(const GemmPlan *p, cudaStream_t s) {
         CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         configured = true;
     }
-    if (p->grid_y > 0) gemm_f16_tcgen05<true><<<dim3((unsigned)p->grid, (unsigned)p->grid_y), 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
+    if (p->grid_z > 1) {
+        static bool sk = false;
+        if (!sk) { CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05_splitk, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024)); sk = true; }
+        gemm_f16_tcgen05_splitk<<<dim3((unsigned)p->grid, (unsigned)p->grid_y, (unsigned)p->grid_z), 192, p->smem, s>>>(p->tmW, p->tmX, p->a, p->sk);
+    } else if (p->grid_y > 0) gemm_f16_tcgen05<true><<<dim3((unsigned)p->grid, (unsigned)p->grid_y), 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
     else gemm_f16_tcgen05<false><<<p->grid, 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -168,6 +177,10 @@ Error VisionDevice::load(const VisionFile &f) {
     img_ = (float *)dalloc((size_t)3 * 224 * 224 * 4);
     patches_ = (__half *)dalloc((size_t)256 * 640 * 2);
     x_ = (float *)dalloc((size_t)T * D * 4);
+    // EXPERIMENTAL (MINIGPT4_B200_VISION_SPLITK=n, needs MINIGPT4_B200_VISION_TSPLIT=1; never run): proj / fc2 as n split-K slices whose partial
+    // sums the following LayerNorm folds into x in slice order
+    splitk_ = (getenv("MINIGPT4_B200_VISION_TSPLIT") && atoi(getenv("MINIGPT4_B200_VISION_TSPLIT")) && getenv("MINIGPT4_B200_VISION_SPLITK")) ? std::max(1, std::min(4, atoi(getenv("MINIGPT4_B200_VISION_SPLITK")))) : 1;
+    parts_ = splitk_ > 1 ? (float *)dalloc((size_t)splitk_ * T * D * 4) : nullptr;
     ln16_ = (__half *)dalloc((size_t)T * D * 2);
     qkv_ = (float *)dalloc((size_t)T * 3 * D * 4);
     ctx16_ = (__half *)dalloc((size_t)T * D * 2);
@@ -216,12 +229,14 @@ Error VisionDevice::load(const VisionFile &f) {
         }
         b.qkv = add_plan(make_plan(w16(f, VE, p + "attn.qkv.weight", 3 * D, D), 3 * D, D, ln16_, T, GE_QSCALE));
         b.qkv->a.bias = b.qkv_bias; b.qkv->a.qscale = 1.0f / sqrtf((float)d_.dh); b.qkv->a.qscale_rows = D; b.qkv->a.out_f32 = qkv_; b.qkv->a.ld_out = 3 * D;
-        b.proj = add_plan(make_plan(w16(f, VE, p + "attn.proj.weight", D, D), D, D, ctx16_, T, GE_RESID));
+        b.proj = add_plan(make_plan(w16(f, VE, p + "attn.proj.weight", D, D), D, D, ctx16_, T, GE_RESID, splitk_));
         b.proj->a.bias = w32(f, VE, p + "attn.proj.bias", D); b.proj->a.out_f32 = x_; b.proj->a.resid = x_; b.proj->a.ld_out = D;
+        b.proj->sk.partial = parts_; b.proj->sk.partial_stride = (long long)T * D;
         b.fc1 = add_plan(make_plan(w16(f, VE, p + "mlp.fc1.weight", FF, D), FF, D, ln16_, T, GE_GELU_F16));
         b.fc1->a.bias = w32(f, VE, p + "mlp.fc1.bias", FF); b.fc1->a.out_f16 = h16_; b.fc1->a.ld_out = FF; b.fc1->a.tab_gelu = tab_gelu_;
-        b.fc2 = add_plan(make_plan(w16(f, VE, p + "mlp.fc2.weight", D, FF), D, FF, h16_, T, GE_RESID));
+        b.fc2 = add_plan(make_plan(w16(f, VE, p + "mlp.fc2.weight", D, FF), D, FF, h16_, T, GE_RESID, splitk_));
         b.fc2->a.bias = w32(f, VE, p + "mlp.fc2.bias", D); b.fc2->a.out_f32 = x_; b.fc2->a.resid = x_; b.fc2->a.ld_out = D;
+        b.fc2->sk.partial = parts_; b.fc2->sk.partial_stride = (long long)T * D;
         flops_ += 4.0 * d_.H * (double)T * T * d_.dh;
     }
     lnv_w_ = w32(f, "ln_vision", "weight", D); lnv_b_ = w32(f, "ln_vision", "bias", D);
@@ -312,10 +327,14 @@ static void launch_attention(int dh, dim3 grid, cudaStream_t s, const float *q, 
 void VisionDevice::record() {
     const int D = d_.D, T = d_.T, QH = 768, NQ = 32;
     cudaStream_t s = stream_;
+    int pending_parts = 0;  // split-K slices of the last residual GEMM that the next LayerNorm over x_ must fold in
     auto ln = [&](const float *x, int rows, int n, const float *w, const float *b, __half *o16, float *o32) {
-        layernorm_kernel<<<rows, 128, 0, s>>>(x, rows, n, w, b, o16, o32, nullptr); ++launches_;
+        if (pending_parts > 0 && x == x_ && !o32) {
+            layernorm_fold_kernel<<<rows, 128, 0, s>>>(x_, rows, n, w, b, o16, parts_, pending_parts, (long long)rows * n); pending_parts = 0;
+        } else layernorm_kernel<<<rows, 128, 0, s>>>(x, rows, n, w, b, o16, o32, nullptr);
+        ++launches_;
     };
-    auto gemm = [&](GemmPlan *p) { launch_plan(p, s); ++launches_; };
+    auto gemm = [&](GemmPlan *p) { launch_plan(p, s); ++launches_; if (p->a.epi == GE_PARTIAL) pending_parts = std::max(1, p->grid_z); };
 
     im2col_patch_kernel<<<256, 128, 0, s>>>(img_, patches_, 640); ++launches_;
     gemm(patch_);

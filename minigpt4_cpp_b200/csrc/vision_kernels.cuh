@@ -15,7 +15,7 @@
 namespace mg4 {
 namespace vk {
 
-enum GemmEpi : int { GE_BIAS = 0, GE_QSCALE = 1, GE_GELU_F16 = 2, GE_RESID = 3, GE_PATCH = 4 };
+enum GemmEpi : int { GE_BIAS = 0, GE_QSCALE = 1, GE_GELU_F16 = 2, GE_RESID = 3, GE_PATCH = 4, GE_PARTIAL = 5 /* split-K kernel only */ };
 
 struct GemmArgs {
     int M_out, T, K;          // output features (multiple of 128), valid tokens, contraction (multiple of 64)
@@ -30,6 +30,10 @@ struct GemmArgs {
     const float *pos;         // GE_PATCH: out[t+1] = acc + bias + pos[t+1]
     const __half *tab_gelu;
     int t_tile;               // token-split variant only (gemm_f16_tcgen05<true>): tokens per CTA, grid.y = ceil(T / t_tile); t_pad == n1 == t_tile, n2 == 0
+};
+struct SplitKArgs {           // extra launch parameters of gemm_f16_tcgen05_splitk (kept out of GemmArgs: the measured kernels' parameter block must not change)
+    int k_split_blocks;       // 64-wide k-blocks per grid.z slice
+    float *partial; long long partial_stride;  // slice z writes acc (+ bias if z == 0) to partial[z * partial_stride + t * ld_out + m]
 };
 
 // ---- raw PTX wrappers ---------------------------------------------------------------------------------
@@ -189,6 +193,124 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05(const __grid_constant
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
 }
 
+// EXPERIMENTAL split-K companion of gemm_f16_tcgen05<true> (MINIGPT4_B200_VISION_SPLITK, never run): the same pipeline, but a CTA covers only the
+// k-blocks [z * k_split_blocks, ...) of its (128-feature, t_tile-token) tile and writes raw partial sums (GE_PARTIAL); layernorm_fold_kernel folds
+// the slices into the residual stream in slice order.  A separate kernel so that the measured gemm_f16_tcgen05<false> stays byte-identical.
+__global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05_splitk(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmArgs g, const SplitKArgs sk) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + (size_t)g.stages * g.stage_bytes);
+    uint64_t *empty = full + 8;
+    uint64_t *tmem_full = empty + 8;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x;
+    const int t0 = (int)blockIdx.y * g.t_tile;  // first token of this CTA
+    const int num_k_all = g.K / 64;
+    const int kb0 = (sk.k_split_blocks != 0) ? (int)blockIdx.z * sk.k_split_blocks : 0;          // first k-block of this CTA (split-K)
+    const int num_k = (sk.k_split_blocks != 0) ? min(sk.k_split_blocks, num_k_all - kb0) : num_k_all;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        for (int i = 0; i < g.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx = 16384u + (uint32_t)g.t_pad * 128u;
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % g.stages; const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                unsigned char *sa = smem + (size_t)s * g.stage_bytes, *sb = sa + 16384;
+                mbar_expect_tx(&full[s], tx);
+                tma_load_2d(sa, &tmW, (kb0 + kb) * 64, m_tile * 128, &full[s]);
+                for (int b = 0; b < g.n_box; ++b) tma_load_2d(sb + (size_t)b * g.box_rows * 128, &tmX, (kb0 + kb) * 64, t0 + b * g.box_rows, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t id1 = umma_idesc_f16(g.n1), id2 = umma_idesc_f16(g.n2 ? g.n2 : 16);
+        for (int kb = 0; kb < num_k; ++kb) {
+            const int s = kb % g.stages; const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * g.stage_bytes), sb = sa + 16384u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = umma_desc_sw128(sa + k * 32), bd = umma_desc_sw128(sb + k * 32);
+                    tc_mma_f16(tmem_base, ad, bd, id1, (uint32_t)((kb | k) != 0));
+                    if (g.n2) tc_mma_f16(tmem_base + 256u, ad, umma_desc_sw128(sb + 256u * 128u + k * 32), id2, (uint32_t)((kb | k) != 0));
+                }
+                tc_commit(&empty[s]);
+                if (kb == num_k - 1) tc_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;
+        const int m = m_tile * 128 + quarter * 32 + lane;
+        const float bias = g.bias ? g.bias[m] : 0.f;
+        const float qs = (g.epi == GE_QSCALE && m < g.qscale_rows) ? g.qscale : 1.0f;
+        for (int c0 = 0; c0 < g.t_pad; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            if (g.epi == GE_PARTIAL) {  // split-K slice: raw partial sums (bias rides on slice 0); the following LayerNorm folds the slices into x
+                float *dst = sk.partial + (size_t)blockIdx.z * (size_t)sk.partial_stride;
+                const float b0 = blockIdx.z == 0 ? bias : 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const int t = t0 + c0 + j; if (t < g.T) dst[(size_t)t * g.ld_out + m] = b0 + v[j]; }
+                continue;
+            }
+            // No early exit inside the 16-token batch: every load of the batch (residual / positional embedding) is issued
+            // before its first use, so the epilogue pays one L2 round trip per batch instead of one per token.
+            float aux[16];
+            if (g.epi == GE_RESID || g.epi == GE_PATCH) {
+                const float *src = g.epi == GE_RESID ? g.resid : g.pos;
+                const int off = g.epi == GE_PATCH ? 1 : 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const int t = t0 + c0 + j; aux[j] = t < g.T ? src[(size_t)(t + off) * g.ld_out + m] : 0.f; }
+            }
+            if (g.epi == GE_GELU_F16) {
+                __half hv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hv[j] = g.tab_gelu[__half_as_ushort(__float2half_rn(bias + v[j]))];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const int t = t0 + c0 + j; if (t < g.T) g.out_f16[(size_t)t * g.ld_out + m] = hv[j]; }
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int t = t0 + c0 + j;
+                if (t < g.T) {
+                    float r = bias + v[j];
+                    switch (g.epi) {
+                        case GE_QSCALE: r *= qs; g.out_f32[(size_t)t * g.ld_out + m] = r; break;
+                        case GE_RESID: g.out_f32[(size_t)t * g.ld_out + m] = aux[j] + r; break;
+                        case GE_PATCH: g.out_f32[(size_t)(t + 1) * g.ld_out + m] = (0.0f + r) + aux[j]; break;
+                        default: g.out_f32[(size_t)t * g.ld_out + m] = r; if (g.out_f16) g.out_f16[(size_t)t * g.ld_out + m] = __float2half_rn(r); break;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm (ggml_norm eps 1e-5 with double accumulation, then w*x+b): F32 rows -> F16 (GEMM operand) and/or F32
 // one warp per row
@@ -247,6 +369,48 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float *__restrict_
             if (out16) out16[(size_t)row * n + i] = __float2half_rn(y);
             if (out32) out32[(size_t)row * n + i] = y;
         }
+    }
+}
+
+// LayerNorm that first folds split-K partial sums into the residual stream (EXPERIMENTAL, with GE_PARTIAL): t = ((x + p0) + p1) + ... in
+// slice order (deterministic), written back to x, then normalised exactly like layernorm_kernel.  One CTA of 128 threads per row.
+__global__ void __launch_bounds__(128) layernorm_fold_kernel(float *__restrict__ x, int rows, int n, const float *__restrict__ w, const float *__restrict__ b,
+                                                             __half *__restrict__ out16, const float *__restrict__ parts, int n_parts, long long part_stride) {
+    __shared__ double red[8];
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (row >= rows) return;
+    float *xr = x + (size_t)row * n;
+    constexpr int MAXE = 12;
+    float v[MAXE];
+#pragma unroll
+    for (int k = 0; k < MAXE; ++k) {
+        const int i = tid + 128 * k, ic = min(i, n - 1);
+        float t = xr[ic];
+        for (int p = 0; p < n_parts; ++p) t = t + parts[(size_t)p * (size_t)part_stride + (size_t)row * n + ic];
+        if (i < n) xr[i] = t;
+        v[k] = i < n ? t : 0.f;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < MAXE; ++k) s += (double)v[k];
+    s = warp_sum_d(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = (red[0] + red[1]) + (red[2] + red[3]);
+    const float mean = (float)(s / (double)n);
+    double s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < MAXE; ++k) { v[k] = v[k] - mean; if (tid + 128 * k < n) s2 += (double)(v[k] * v[k]); }
+    s2 = warp_sum_d(s2);
+    if (lane == 0) red[4 + warp] = s2;
+    __syncthreads();
+    s2 = (red[4] + red[5]) + (red[6] + red[7]);
+    const float variance = (float)(s2 / (double)n);
+    const float scale = 1.0f / sqrtf(variance + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < MAXE; ++k) {
+        const int i = tid + 128 * k;
+        if (i < n) { float y = w[i] * (v[k] * scale); if (b) y = y + b[i]; out16[(size_t)row * n + i] = __float2half_rn(y); }
     }
 }
 

@@ -16,6 +16,7 @@ MINIGPT4_B200_MEGA_LL=1 TAILN=22 run trace_ll 200 python tools/mega_trace.py   #
 MINIGPT4_B200_VISION_TSPLIT=1 TAILN=4 run pytest_tsplit 300 python -m pytest tests/test_e2e_gpu.py tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "encode_image or chat_flow or gemm"
 TAILN=1 run encode_default 200 python tools/prof_vision.py
 MINIGPT4_B200_VISION_TSPLIT=1 TAILN=1 run encode_tsplit 200 python tools/prof_vision.py
+MINIGPT4_B200_VISION_TSPLIT=1 MINIGPT4_B200_VISION_SPLITK=3 TAILN=1 run encode_splitk 200 python tools/prof_vision.py
 TAILN=3 run bench 600 python bench.py --steps 3 --warmup 3 --no-cpu
 TAILN=8 run crosscheck_vllm 400 python tools/crosscheck_vllm_gguf.py
 echo done
