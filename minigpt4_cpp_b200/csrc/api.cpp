@@ -86,19 +86,21 @@ int minigpt4_end_chat(struct MiniGPT4Context *ctx, const char **token, size_t n_
 
 int minigpt4_reset_chat(struct MiniGPT4Context *ctx) { E(ctx)->reset(); return ErrNone; }
 
-int minigpt4_contains_eos_token(const char *s) { return strcmp(s, kEosTokenSuffix) == 0 ? ErrEosToken : ErrNone; }
+// (the reference dereferences a null argument in the next five entry points; here a null is simply "nothing to do")
+int minigpt4_contains_eos_token(const char *s) { return (s && strcmp(s, kEosTokenSuffix) == 0) ? ErrEosToken : ErrNone; }
 int minigpt4_is_eos(const char *s) {
+    if (!s) return ErrNone;
     const size_t n = strlen(s), m = strlen(kEosSuffix);
     return (n >= m && memcmp(s + n - m, kEosSuffix, m) == 0) ? ErrEos : ErrNone;
 }
 
 int minigpt4_free(struct MiniGPT4Context *ctx) { delete E(ctx); return ErrNone; }
 int minigpt4_free_image(struct MiniGPT4Image *image) {
-    if (image->data) { delete[] (float *)image->data; image->data = nullptr; }
+    if (image && image->data) { delete[] (float *)image->data; image->data = nullptr; }
     return ErrNone;
 }
 int minigpt4_free_embedding(struct MiniGPT4Embedding *embedding) {
-    if (embedding->data) { delete[] embedding->data; embedding->data = nullptr; }
+    if (embedding && embedding->data) { delete[] embedding->data; embedding->data = nullptr; }
     return ErrNone;
 }
 const char *minigpt4_error_code_to_string(int error_code) { return error_name(error_code); }
@@ -107,7 +109,7 @@ void minigpt4_set_verbosity(int verbosity) { g_verbosity = verbosity; }
 // quantize.cpp
 int mg4_quantize_container(const char *in_path, const char *out_path, int data_type);
 int minigpt4_quantize_model(const char *in_path, const char *out_path, int data_type) {
-    if (!path_exists(in_path)) return ErrPathDoesNotExist;
+    if (!in_path || !out_path || !path_exists(in_path)) return ErrPathDoesNotExist;
     return mg4_quantize_container(in_path, out_path, data_type);
 }
 

@@ -85,3 +85,17 @@ def test_reference_binding_binds_unmodified(lib):
     spec.loader.exec_module(mod)
     rlib = mod.MiniGPT4SharedLibrary(str(OUT))
     assert rlib.minigpt4_is_eos("x###") and rlib.minigpt4_contains_eos_token("##")
+
+
+def test_null_arguments_are_harmless(lib):
+    """The reference dereferences NULL in these entry points (minigpt4.cpp:2764-2809); here a null is 'nothing to do' / 'no such path'."""
+    import ctypes
+    L = lib.library
+    for name in ("minigpt4_free", "minigpt4_free_image", "minigpt4_free_embedding"):
+        fn = getattr(L, name); fn.argtypes = [ctypes.c_void_p]; fn.restype = ctypes.c_int
+        assert fn(None) == 0
+    for name in ("minigpt4_contains_eos_token", "minigpt4_is_eos"):
+        fn = getattr(L, name); fn.argtypes = [ctypes.c_char_p]; fn.restype = ctypes.c_int
+        assert fn(None) == 0
+    L.minigpt4_quantize_model.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    assert L.minigpt4_quantize_model(None, None, 5) == 17  # PathDoesNotExist
