@@ -90,7 +90,7 @@ def test_reference_binding_binds_unmodified(lib):
 def test_null_arguments_are_harmless(lib):
     """The reference dereferences NULL in these entry points (minigpt4.cpp:2764-2809); here a null is 'nothing to do' / 'no such path'."""
     import ctypes
-    L = lib.library
+    L = ctypes.CDLL(lib.library._name)  # a private handle: the prototypes set below must not leak into the session-wide binding
     for name in ("minigpt4_free", "minigpt4_free_image", "minigpt4_free_embedding"):
         fn = getattr(L, name); fn.argtypes = [ctypes.c_void_p]; fn.restype = ctypes.c_int
         assert fn(None) == 0
