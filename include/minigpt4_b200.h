@@ -53,8 +53,8 @@ struct MiniGPT4B200Stats {
     double last_encode_ms;              /* CUDA-event time of the last encode graph */
     unsigned long long kernel_launches; /* kernels of this library launched so far (both graphs) */
     int n_layer, n_embd, n_ff, n_vocab, n_ctx, tp_rank, tp_world, sm_count;
-    int decode_megakernel;              /* 1: decode step = one persistent kernel per token; 0: one launch per op (graph) */
-    int reserved;
+    int decode_megakernel;              /* > 0: decode step = one persistent kernel per token (value = kernel generation: 1 or 5); 0: one launch per op (graph) */
+    int prefill_gemm;                   /* 1: prompt / prefix rows (N >= 2) run through the tcgen05 kind::i8 prefill GEMM; 0: per-op matvec path */
 };
 MINIGPT4_API int minigpt4_b200_stats(struct MiniGPT4Context *ctx, struct MiniGPT4B200Stats *out);
 

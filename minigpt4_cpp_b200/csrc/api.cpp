@@ -174,7 +174,8 @@ int minigpt4_b200_stats(struct MiniGPT4Context *ctx, struct MiniGPT4B200Stats *o
     out->last_encode_ms = e->last_encode_ms;
     out->n_layer = d.n_layer; out->n_embd = d.n_embd; out->n_ff = d.n_ff; out->n_vocab = d.n_vocab; out->n_ctx = d.n_ctx;
     out->tp_rank = e->tp.rank; out->tp_world = e->tp.world; out->sm_count = e->llm().sm_count();
-    out->decode_megakernel = e->llm().uses_megakernel() ? 1 : 0;
+    out->decode_megakernel = e->llm().mega_generation();
+    out->prefill_gemm = e->llm().uses_prefill_gemm() ? 1 : 0;
     return 0;
 }
 int minigpt4_b200_time_matvec(struct MiniGPT4Context *ctx, int kind, int reps, float *avg_ms, double *bytes_per_launch) {

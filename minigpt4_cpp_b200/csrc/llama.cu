@@ -2,6 +2,8 @@
 #include "llama_kernels.cuh"
 #include "llama_mega.cuh"
 #include "llama_mega_ll.cuh"
+#include "llama_mega5.cuh"
+#include "llama_prefill.cuh"
 #include "tp.h"
 #include <stdlib.h>
 #include <math.h>
@@ -149,11 +151,15 @@ LlamaDevice::~LlamaDevice() {
     qmat_free(output_);
     for (void *p : {(void *)final_norm_, tok_raw_, (void *)kcache_, (void *)vcache_, (void *)rope_, (void *)tab_exp_, (void *)tab_silu_, (void *)x_, (void *)q_, (void *)att_,
                     (void *)act_, (void *)logits_, (void *)partial_, (void *)qact_, (void *)embd_in_, (void *)state_}) if (p) cudaFree(p);
+    for (auto &L : layers_) for (PQMat *m : {&L.pqkv, &L.pwo, &L.pw13, &L.pw2}) { if (m->q) cudaFree(m->q); if (m->sc) cudaFree(m->sc); }
+    for (void *p : {(void *)pf_q8_, pf_sc_, (void *)tok_ids_}) if (p) cudaFree(p);
     if (mega_ops_) cudaFree(mega_ops_);
     if (mega_barrier_) cudaFree(mega_barrier_);
     if (mega_trace_) cudaFree(mega_trace_);
     delete (mk::MegaParams *)mega_params_;
     delete (mk::MegaParamsLL *)mega_params_ll_;
+    delete (mk5::Params *)mega5_params_;
+    if (mega5_ops_) cudaFree(mega5_ops_);
     if (mega_ll_buf_) cudaFree(mega_ll_buf_);
     if (h_state_) cudaFreeHost(h_state_);
     if (h_argmax_) cudaFreeHost(h_argmax_);
@@ -252,11 +258,13 @@ bool LlamaDevice::load(const LlamaFile &f, int n_ctx, TPLink *tp) {
     const size_t kv = (size_t)d_.n_layer * n_ctx * El;
     CUDA_CHECK(cudaMalloc((void **)&kcache_, kv * 2)); CUDA_CHECK(cudaMemset(kcache_, 0, kv * 2));
     CUDA_CHECK(cudaMalloc((void **)&vcache_, kv * 2)); CUDA_CHECK(cudaMemset(vcache_, 0, kv * 2));
-    CUDA_CHECK(cudaMalloc((void **)&x_, (size_t)8 * E * 4));
-    CUDA_CHECK(cudaMalloc((void **)&q_, (size_t)8 * El * 4));
-    CUDA_CHECK(cudaMalloc((void **)&att_, (size_t)8 * El * 4));
-    CUDA_CHECK(cudaMalloc((void **)&act_, (size_t)8 * FFl * 4));
+    const size_t R = (size_t)kPrefillMax;  // rows of one prefill pass (the per-op path uses the first 8)
+    CUDA_CHECK(cudaMalloc((void **)&x_, R * E * 4));
+    CUDA_CHECK(cudaMalloc((void **)&q_, R * El * 4));
+    CUDA_CHECK(cudaMalloc((void **)&att_, R * El * 4));
+    CUDA_CHECK(cudaMalloc((void **)&act_, R * FFl * 4));
     CUDA_CHECK(cudaMalloc((void **)&partial_, (size_t)8 * E * 4));
+    CUDA_CHECK(cudaMalloc((void **)&tok_ids_, R * 4));
     CUDA_CHECK(cudaMalloc((void **)&qact_, (size_t)8 * ((size_t)std::max(E, FF) * 2 + 4096)));
     CUDA_CHECK(cudaMalloc((void **)&logits_, (size_t)(d_.n_vocab + 1) * 4));
     CUDA_CHECK(cudaMalloc((void **)&embd_in_, (size_t)512 * E * 4));
@@ -264,6 +272,7 @@ bool LlamaDevice::load(const LlamaFile &f, int n_ctx, TPLink *tp) {
     CUDA_CHECK(cudaHostAlloc((void **)&h_state_, sizeof(DeviceState), cudaHostAllocDefault)); memset(h_state_, 0, sizeof(DeviceState));
     CUDA_CHECK(cudaHostAlloc((void **)&h_argmax_, 64, cudaHostAllocDefault)); *h_argmax_ = 0;
     CUDA_CHECK(cudaDeviceSynchronize());
+    pf_ready_ = build_prefill();
     build_graph();
     MG4_INFO("LLaMA on device: %d layers, n_embd %d, n_ff %d, vocab %d, %.1f MB streamed per token, tp %d/%d", d_.n_layer, E, FF, d_.n_vocab,
              bytes_per_token_ / 1048576.0, rank, world);
@@ -345,6 +354,20 @@ bool LlamaDevice::eval_tokens(const int32_t *ids, int n, int n_past) {
     if (n <= 0) return true;
     if (n_past + n > d_.n_ctx) { MG4_ERR("context overflow: %d + %d > n_ctx %d", n_past, n, d_.n_ctx); return false; }
     for (int i = 0; i < n; ++i) if (ids[i] < 0 || ids[i] >= d_.n_vocab) { MG4_ERR("token id %d out of range", ids[i]); return false; }
+    if (pf_ready_ && n >= 2) {   // tensor-core prefill: up to kPrefillMax rows per pass over the weights (reference: n_batch chunks, minigpt4.cpp:2369-2379)
+        for (int i = 0; i < n; i += kPrefillMax) {
+            const int c = std::min(kPrefillMax, n - i);
+            h_state_->n_past = n_past + i; h_state_->n_tok = c;
+            CUDA_CHECK(cudaStreamSynchronize(stream_));  // (h_state_ / the pinned id staging of the previous pass have been consumed)
+            CUDA_CHECK(cudaMemcpyAsync(state_, h_state_, offsetof(DeviceState, argmax_key), cudaMemcpyHostToDevice, stream_));
+            CUDA_CHECK(cudaMemcpyAsync(tok_ids_, ids + i, (size_t)c * 4, cudaMemcpyHostToDevice, stream_));
+            embed_ids_kernel<<<c, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, tok_ids_, x_);
+            ++launches_;
+            prefill_chunk(c, i + c == n);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        return true;
+    }
     for (int i = 0; i < n; i += 8) {
         const int c = std::min(8, n - i);
         h_state_->n_past = n_past + i; h_state_->n_tok = c;
@@ -356,6 +379,18 @@ bool LlamaDevice::eval_tokens(const int32_t *ids, int n, int n_past) {
 bool LlamaDevice::eval_embd_device(const float *rows_dev, int n, int n_past) {
     if (n <= 0) return true;
     if (n_past + n > d_.n_ctx) { MG4_ERR("context overflow: %d + %d > n_ctx %d", n_past, n, d_.n_ctx); return false; }
+    if (pf_ready_ && n >= 2) {   // e.g. the 32 image-embedding rows in ONE batch (reference add_embedding, minigpt4.cpp:2405-2412)
+        for (int i = 0; i < n; i += kPrefillMax) {
+            const int c = std::min(kPrefillMax, n - i);
+            h_state_->n_past = n_past + i; h_state_->n_tok = c;
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            CUDA_CHECK(cudaMemcpyAsync(state_, h_state_, offsetof(DeviceState, argmax_key), cudaMemcpyHostToDevice, stream_));
+            CUDA_CHECK(cudaMemcpyAsync(x_, rows_dev + (size_t)i * d_.n_embd, (size_t)c * d_.n_embd * 4, cudaMemcpyDeviceToDevice, stream_));
+            prefill_chunk(c, i + c == n);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        return true;
+    }
     for (int i = 0; i < n; i += 8) {
         const int c = std::min(8, n - i);
         h_state_->n_past = n_past + i; h_state_->n_tok = c;
@@ -382,6 +417,121 @@ void LlamaDevice::sync() { CUDA_CHECK(cudaStreamSynchronize(stream_)); }
 void LlamaDevice::hidden_to_host(float *dst, int n) {
     CUDA_CHECK(cudaMemcpyAsync(dst, x_, (size_t)n * d_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core prefill (llama_prefill.cuh)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tm_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr; cudaDriverEntryPointQueryResult qr;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+        if (!p || qr != cudaDriverEntryPointSuccess) MG4_PANIC("cuTensorMapEncodeTiled is not available from this driver");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// bytes [rows][pitch] -> boxes of box_bytes x box_rows
+static void make_map_u8(void *tm, const void *ptr, size_t rows, size_t pitch, int box_bytes, int box_rows, bool swizzle128) {
+    cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {(cuuint32_t)box_bytes, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = tm_encode_fn()((CUtensorMap *)tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) MG4_PANIC("cuTensorMapEncodeTiled failed (%d) for [%zu x %zu] box %d x %d", (int)r, rows, pitch, box_bytes, box_rows);
+}
+static int pf_slots(int cols) { const int nbl = (cols / 32 + 31) / 32; return 4 * ((nbl + 3) / 4); }
+
+static void pq_build(PQMat &p, const QMat &m) {
+    p.rows = m.rows; p.rows_pad = (m.rows + 127) & ~127; p.cols = m.cols; p.nb = m.cols / 32; p.S = pf_slots(m.cols); p.q41 = m.type == GG_Q4_1;
+    const size_t pitch = (size_t)32 * p.S * 32;
+    CUDA_CHECK(cudaMalloc((void **)&p.q, (size_t)p.rows_pad * pitch)); CUDA_CHECK(cudaMemset(p.q, 0, (size_t)p.rows_pad * pitch));
+    CUDA_CHECK(cudaMalloc(&p.sc, (size_t)p.rows_pad * 32 * p.S * 4)); CUDA_CHECK(cudaMemset(p.sc, 0, (size_t)p.rows_pad * 32 * p.S * 4));
+    const size_t n = (size_t)m.rows * p.nb;
+    pf::expand_q4_classmajor<<<(unsigned)((n + 255) / 256), 256>>>((const unsigned char *)m.p0, m.row_bytes, m.rows, p.nb, p.q41 ? 1 : 0, p.S, p.q, (__half2 *)p.sc);
+    CUDA_CHECK(cudaGetLastError());
+    make_map_u8(p.tm, p.q, (size_t)p.rows_pad, pitch, 128, pf::kRows, true);
+}
+
+bool LlamaDevice::build_prefill() {
+    if (getenv("MINIGPT4_B200_NO_PREFILL_GEMM")) return false;
+    if (tp_ && tp_->world > 1) return false;  // (tensor-parallel ranks keep the per-op prefill path for now)
+    if (!(tok_type_ == GG_F32 || tok_type_ == GG_F16 || tok_type_ == GG_Q4_0 || tok_type_ == GG_Q4_1 || tok_type_ == GG_Q5_K || tok_type_ == GG_Q6_K)) return false;
+    for (auto &L : layers_) {
+        if (!L.fused_qkv) return false;
+        for (const QMat *m : {&L.qkv, &L.wo, &L.w13, &L.w2}) if (m->type != GG_Q4_0 && m->type != GG_Q4_1) return false;
+        if (act_of(L.qkv.type) != act_of(L.w13.type)) {}  // (each matrix stages its own input: mixed Q4_0 / Q4_1 layers are fine)
+    }
+    const int E = d_.n_embd, FF = d_.n_ff;
+    size_t free_b = 0, total_b = 0; CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = (size_t)d_.n_layer * ((size_t)4 * E * E + (size_t)3 * E * (size_t)32 * pf_slots(FF) * 32 / 1) + ((size_t)1 << 30);
+    if (need > free_b) { MG4_INFO("prefill operand cache (%.1f GB) does not fit: per-op prefill path", need / 1073741824.0); return false; }
+    for (auto &L : layers_) { pq_build(L.pqkv, L.qkv); pq_build(L.pwo, L.wo); pq_build(L.pw13, L.w13); pq_build(L.pw2, L.w2); }
+    pf_S_e_ = pf_slots(E); pf_S_ff_ = pf_slots(FF);
+    const size_t pitch_e = (size_t)32 * pf_S_e_ * 32, pitch_ff = (size_t)32 * pf_S_ff_ * 32, R = (size_t)kPrefillMax;
+    CUDA_CHECK(cudaMalloc((void **)&pf_q8_, R * std::max(pitch_e, pitch_ff))); CUDA_CHECK(cudaMemset(pf_q8_, 0, R * std::max(pitch_e, pitch_ff)));
+    CUDA_CHECK(cudaMalloc(&pf_sc_, R * std::max(pitch_e, pitch_ff) / 4)); CUDA_CHECK(cudaMemset(pf_sc_, 0, R * std::max(pitch_e, pitch_ff) / 4));
+    make_map_u8(pf_tmB_e_, pf_q8_, R, pitch_e, 128, pf::kTok, true);
+    make_map_u8(pf_tmS_e_, pf_sc_, R, pitch_e / 4, 32, pf::kTok, false);
+    make_map_u8(pf_tmB_ff_, pf_q8_, R, pitch_ff, 128, pf::kTok, true);
+    make_map_u8(pf_tmS_ff_, pf_sc_, R, pitch_ff / 4, 32, pf::kTok, false);
+    const size_t smem = 1024 + (size_t)pf::kStages * pf::kStageBytes + pf::kStackBytes + 256;
+    CUDA_CHECK(cudaFuncSetAttribute(pf::prefill_gemm_q4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(pf::prefill_gemm_q4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(49152, d_.n_ctx * 6)));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    MG4_INFO("tensor-core prefill: int8 class-major operand cache built (%d / %d slots per class)", pf_S_e_, pf_S_ff_);
+    return true;
+}
+
+// one pass of all layers over n (<= kPrefillMax) rows in x_; positions from *state_ (n_past), KV rows appended, logits of the last row
+void LlamaDevice::prefill_chunk(int n, bool want_logits) {
+    const int E = d_.n_embd, El = n_embd_local_, FFl = n_ff_local_, C = d_.n_ctx;
+    const float kq_scale = 1.0f / sqrtf((float)d_.n_embd / (float)d_.n_head);
+    const size_t smem = 1024 + (size_t)pf::kStages * pf::kStageBytes + pf::kStackBytes + 256;
+    const unsigned ty = (unsigned)((n + pf::kTok - 1) / pf::kTok);
+    auto stage = [&](const QMat &w, const float *x, int x_stride, const float *nw, int S) {
+        const int act = act_of(w.type);
+        const size_t sm = act_bytes(act, w.cols);
+        if (act == ACT_Q8_1) pf::stage_rows_classmajor<ACT_Q8_1><<<n, 256, sm, stream_>>>(x, x_stride, nw, w.cols, S, pf_q8_, (float2 *)pf_sc_);
+        else pf::stage_rows_classmajor<ACT_Q8_0><<<n, 256, sm, stream_>>>(x, x_stride, nw, w.cols, S, pf_q8_, (float2 *)pf_sc_);
+        ++launches_;
+    };
+    auto gemm = [&](const PQMat &p, bool ff_wide, pf::PrefillArgs a) {
+        a.rows = p.rows; a.n_tok = n; a.nb = p.nb; a.S = p.S; a.wsc = (const __half2 *)p.sc; a.state = state_; a.tab_silu = tab_silu_;
+        const CUtensorMap *tb = (const CUtensorMap *)(ff_wide ? pf_tmB_ff_ : pf_tmB_e_), *ts = (const CUtensorMap *)(ff_wide ? pf_tmS_ff_ : pf_tmS_e_);
+        const dim3 grid((unsigned)(p.rows_pad / pf::kRows), ty);
+        if (p.q41) pf::prefill_gemm_q4<true><<<grid, pf::kThreads, smem, stream_>>>(*(const CUtensorMap *)p.tm, *tb, *ts, a);
+        else pf::prefill_gemm_q4<false><<<grid, pf::kThreads, smem, stream_>>>(*(const CUtensorMap *)p.tm, *tb, *ts, a);
+        ++launches_;
+    };
+    for (int il = 0; il < d_.n_layer; ++il) {
+        Layer &L = layers_[(size_t)il];
+        __half *kc = kcache_ + (size_t)il * C * El, *vc = vcache_ + (size_t)il * C * El;
+        stage(L.qkv, x_, E, L.attn_norm, pf_S_e_);
+        { pf::PrefillArgs a{}; a.epi = EPI_QKV; a.q_out = q_; a.kcache = kc; a.vcache = vc; a.rope = rope_; a.e_local = El; a.half_dim = 64; gemm(L.pqkv, false, a); }
+        attn_kernel<<<dim3((unsigned)n_head_local_, (unsigned)n), 256, (size_t)C * 6, stream_>>>(q_, kc, vc, att_, state_, El, C, kq_scale, tab_exp_); ++launches_;
+        stage(L.wo, att_, El, nullptr, pf_S_e_);
+        { pf::PrefillArgs a{}; a.epi = EPI_RESID; a.out = x_; a.out_stride = E; a.resid = x_; gemm(L.pwo, false, a); }
+        stage(L.w13, x_, E, L.ffn_norm, pf_S_e_);
+        { pf::PrefillArgs a{}; a.epi = EPI_SWIGLU; a.out = act_; a.out_stride = FFl; gemm(L.pw13, false, a); }
+        stage(L.w2, act_, FFl, nullptr, pf_S_ff_);
+        { pf::PrefillArgs a{}; a.epi = EPI_RESID; a.out = x_; a.out_stride = E; a.resid = x_; gemm(L.pw2, true, a); }
+    }
+    CUDA_CHECK(cudaGetLastError());
+    if (want_logits) {
+        MatvecArgs o{};
+        o.w = output_; o.x = x_ + (size_t)(n - 1) * E; o.x_stride = E; o.norm_w = final_norm_; o.ntok = 1; o.epi = EPI_LOGITS; o.out = logits_; o.n_valid = d_.n_vocab;
+        o.state = state_; o.tab_silu = tab_silu_; o.staged = qact_;
+        launch_matvec(o, 1, sm_count_, stream_, &launches_);
+    }
+    finalize_kernel<<<1, 32, 0, stream_>>>(state_, want_logits ? 1 : 0, nullptr); ++launches_;
+    CUDA_CHECK(cudaGetLastError());
+    if (want_logits) CUDA_CHECK(cudaMemcpyAsync(h_argmax_, &state_->argmax_id, 4, cudaMemcpyDeviceToHost, stream_));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -462,7 +612,7 @@ bool LlamaDevice::build_mega() {
     // delays the fills; with the lane off: 1459 us.  The 28-slot ring alone keeps ~28 MB in flight chip-wide.
     P->l2_ahead = getenv("MINIGPT4_B200_L2_AHEAD") ? atoi(getenv("MINIGPT4_B200_L2_AHEAD")) : 0;
     P->flags = getenv("MINIGPT4_B200_MEGA_FLAGS") ? atoi(getenv("MINIGPT4_B200_MEGA_FLAGS")) : 1;
-    if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, ops.size() * 16 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, ops.size() * 16 * sizeof(long long))); P->trace = mega_trace_; }
+    if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, (ops.size() + 1) * 16 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, (ops.size() + 1) * 16 * sizeof(long long))); P->trace = mega_trace_; }
     mega_n_ops_ = (int)ops.size();
     mega_params_ = P;
     // experimental flag-in-data variant (llama_mega_ll.cuh): the exchanged activation vectors as {value, tag} pairs, one zeroed allocation
@@ -480,6 +630,52 @@ bool LlamaDevice::build_mega() {
     }
     mega_smem_ = (size_t)n_slots * slot + xs_b + act_b + (size_t)n_slots * 16 + ops.size() * sizeof(MegaOp) + 64;
     mega_type_ = wt;
+    // generation 5 (llama_mega5.cuh): register-resident activations, flag-in-data exchange, quantised attention output, L2 look-ahead
+    if (getenv("MINIGPT4_B200_MEGA5") && atoi(getenv("MINIGPT4_B200_MEGA5")) && ops.size() < 1023 && d_.n_head <= sm_count_ && E <= 256 * 4 * mk::kNormItems) {
+        using mk5::LLf; using mk5::Op5;
+        const size_t e_b = (mk5::act5_bytes(E) + 127) & ~(size_t)127;
+        size_t ff_b = std::max(mk5::act5_bytes(FF), std::max(mk5::act5_bytes(E), (size_t)d_.n_ctx * 6));
+        ff_b = (ff_b + 127) & ~(size_t)127;
+        const size_t ops_b5 = ops.size() * sizeof(Op5);
+        const size_t fixed = ff_b + e_b + ops_b5 + 64;
+        const size_t stat5 = 10752;  // static shared memory of decode_megakernel5 (red, redf, qs, kcur, vcur, part)
+        const long long room = (long long)budget - (long long)stat5 - (long long)fixed - 1024;
+        const int n_slots5 = (int)std::min<long long>(48, room / (long long)(slot + 16));
+        if (n_slots5 >= 12) {
+            std::vector<Op5> ops5;
+            for (auto &o : ops) {
+                Op5 q{}; q.kind = (unsigned char)o.kind; q.layer = (unsigned short)o.layer; q.cols = o.cols; q.n_su = o.n_su; q.row_bytes = (unsigned short)o.row_bytes;
+                q.sps = (unsigned char)o.sps; q.w = o.w; q.norm_w = o.norm_w;
+                if (o.w) {
+                    if (o.row_bytes > 65535) return false;
+                    q.n_warps = (unsigned char)std::max(1, std::min(kConsumerWarps, (n_slots5 - (q.sps == 2 ? inflight2 : inflight)) / q.sps));
+                }
+                ops5.push_back(q);
+            }
+            CUDA_CHECK(cudaMalloc(&mega5_ops_, ops5.size() * sizeof(Op5)));
+            CUDA_CHECK(cudaMemcpy(mega5_ops_, ops5.data(), ops5.size() * sizeof(Op5), cudaMemcpyHostToDevice));
+            const size_t nE = (size_t)E, nF = (size_t)FF, nbE = nE / 32;
+            const size_t n_ll = 2 * nE + nF + nE + nbE * 10;  // x, q | act | kcur + vcur (E/2 each) | att words
+            const size_t bytes = n_ll * sizeof(LLf) + 256;
+            CUDA_CHECK(cudaMalloc(&mega_ll_buf_, bytes)); CUDA_CHECK(cudaMemset(mega_ll_buf_, 0, bytes));
+            mk5::Params *Q = new mk5::Params();
+            LLf *b = (LLf *)mega_ll_buf_;
+            Q->ops = (const Op5 *)mega5_ops_; Q->n_ops = (int)ops.size();
+            Q->n_slots = n_slots5; Q->slot_bytes = slot; Q->ff_bytes = (int)ff_b; Q->e_bytes = (int)e_b;
+            Q->E = E; Q->FF = FF; Q->n_head = d_.n_head; Q->n_ctx = d_.n_ctx; Q->n_vocab = d_.n_vocab; Q->kq_scale = P->kq_scale;
+            Q->x = b; Q->q = b + nE; Q->act = b + 2 * nE; Q->kcur = b + 2 * nE + nF; Q->vcur = Q->kcur + nE / 2; Q->att = Q->vcur + nE / 2;
+            Q->seq = (unsigned *)(Q->att + nbE * 10);
+            Q->logits = logits_; Q->kcache = kcache_; Q->vcache = vcache_; Q->rope = rope_; Q->tab_exp = tab_exp_; Q->tab_silu = tab_silu_;
+            Q->tok = P->tok; Q->tok_type = P->tok_type; Q->tok_row_bytes = P->tok_row_bytes; Q->state = state_; Q->barrier = mega_barrier_;
+            Q->l2_ahead = getenv("MINIGPT4_B200_L2_AHEAD") ? atoi(getenv("MINIGPT4_B200_L2_AHEAD")) : 0;
+            Q->flags = P->flags; Q->trace = P->trace;
+            mega5_params_ = Q; mega_gen_ = 5; mega_ll_ = false;
+            mega5_nbl_ = (E == 4096 && !getenv("MINIGPT4_B200_MEGA5_NOREG")) ? 4 : (E == 5120 && !getenv("MINIGPT4_B200_MEGA5_NOREG")) ? 5 : 0;
+            mega_smem_ = (size_t)n_slots5 * slot + fixed + (size_t)n_slots5 * 16;
+            MG4_INFO("decode megakernel generation 5: ring %d x %d B, act buffers %zu + %zu B, register-resident blocks per lane %d, L2 look-ahead %d chunks, flags %d",
+                     n_slots5, slot, ff_b, e_b, mega5_nbl_, Q->l2_ahead, Q->flags);
+        }
+    }
     mega_stk_ = (std::max(E, FF) + 2047) / 2048;
     const void *fn = mega_fn();
     CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_));
@@ -491,6 +687,14 @@ bool LlamaDevice::build_mega() {
 }
 const void *LlamaDevice::mega_fn() const {
     using namespace mk;
+    if (mega_gen_ == 5) {
+        using namespace mk5;
+        const bool t = mega_trace_ != nullptr, q41 = mega_type_ == GG_Q4_1;
+#define MG4_M5(NBL) (q41 ? (t ? (const void *)decode_megakernel5<GG_Q4_1, NBL, true> : (const void *)decode_megakernel5<GG_Q4_1, NBL, false>) \
+                         : (t ? (const void *)decode_megakernel5<GG_Q4_0, NBL, true> : (const void *)decode_megakernel5<GG_Q4_0, NBL, false>))
+        return mega5_nbl_ == 4 ? MG4_M5(4) : mega5_nbl_ == 5 ? MG4_M5(5) : MG4_M5(0);
+#undef MG4_M5
+    }
     if (mega_ll_ && mega_trace_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel_ll<GG_Q4_1, true> : (const void *)decode_megakernel_ll<GG_Q4_0, true>;
     if (mega_ll_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel_ll<GG_Q4_1, false> : (const void *)decode_megakernel_ll<GG_Q4_0, false>;
     if (mega_trace_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1, true> : (const void *)decode_megakernel<GG_Q4_0, true>;
@@ -504,7 +708,7 @@ void LlamaDevice::launch_mega() {
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    void *args[1] = {mega_ll_ ? mega_params_ll_ : mega_params_};
+    void *args[1] = {mega_gen_ == 5 ? mega5_params_ : mega_ll_ ? mega_params_ll_ : mega_params_};
     CUDA_CHECK(cudaLaunchKernelExC(&cfg, mega_fn(), args));
     ++launches_;
     CUDA_CHECK(cudaMemcpyAsync(h_argmax_, &state_->argmax_id, 4, cudaMemcpyDeviceToHost, stream_));
@@ -559,7 +763,7 @@ float LlamaDevice::decode_chain(int steps, int n_past, int32_t *ids_out) {
 
 int LlamaDevice::mega_trace(long long *out, int max_values) {
     if (!mega_trace_) return 0;
-    const int n = std::min(max_values, mega_n_ops_ * 16);
+    const int n = std::min(max_values, (mega_n_ops_ + (mega_gen_ == 5 ? 1 : 0)) * 16);  // generation 5 appends [2 CTAs][8] producer counters
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaMemcpy(out, mega_trace_, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
     return n;

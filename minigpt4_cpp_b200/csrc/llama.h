@@ -24,6 +24,12 @@ struct QMat {          // one repacked weight matrix (or a fused group of matric
     int row_bytes = 0; // Q4_0/Q4_1 row-packed layout: p0 holds rows of [nb x 16 B nibbles][nb x scales], row_bytes each
 };
 
+struct PQMat {         // prefill operand cache of one Q4_0 / Q4_1 matrix (llama_prefill.cuh): int8, class-major, + {d, m} in the same order
+    int rows = 0, rows_pad = 0, cols = 0, nb = 0, S = 0; bool q41 = false;
+    signed char *q = nullptr; void *sc = nullptr;
+    alignas(64) unsigned char tm[128];  // CUtensorMap over q
+};
+
 struct LlamaDims { int n_vocab, n_embd, n_head, n_layer, n_ff, n_ctx, head_dim; };
 
 struct DeviceState {   // lives in device memory; kernels read positions/tokens from here so graphs are position independent
@@ -51,6 +57,9 @@ public:
     void sync();
     int sm_count() const { return sm_count_; }
     bool uses_megakernel() const { return mega_; }
+    bool uses_prefill_gemm() const { return pf_ready_; }
+    static constexpr int kPrefillMax = 512;   // rows per prefill pass (the reference's default n_batch)
+    int mega_generation() const { return mega_ ? (mega_gen_ == 5 ? 5 : 1) : 0; }
     int mega_trace(long long *out, int max_values);  // debug: per-op clock64 stamps of the last megakernel launch (env MINIGPT4_B200_MEGA_TRACE)
     // one decode step through the captured CUDA graph: feeds `id` (or, if id < 0, the on-device arg-max of the
     // previous step), leaves new logits/arg-max on device.
@@ -71,7 +80,12 @@ public:
     static void test_matvec(int gg, int rows, int cols, const void *w_host, const float *x_host, int n, float *y_host);
 
 private:
-    struct Layer { QMat qkv, wq, wk, wv, wo, w13, w2; bool fused_qkv; float *attn_norm, *ffn_norm; };
+    struct Layer { QMat qkv, wq, wk, wv, wo, w13, w2; bool fused_qkv; float *attn_norm, *ffn_norm; PQMat pqkv, pwo, pw13, pw2; };
+    bool build_prefill();            // tensor-core prefill (llama_prefill.cuh): homogeneous Q4_0 / Q4_1 layers, single GPU
+    void prefill_chunk(int n, bool want_logits);   // n <= kPrefillMax rows that sit in x_
+    bool pf_ready_ = false; int pf_S_e_ = 0, pf_S_ff_ = 0;
+    signed char *pf_q8_ = nullptr; void *pf_sc_ = nullptr; int32_t *tok_ids_ = nullptr;
+    alignas(64) unsigned char pf_tmB_e_[128], pf_tmS_e_[128], pf_tmB_ff_[128], pf_tmS_ff_[128];
     void run_chunk(int n, bool want_logits, bool from_tokens);
     void launch_layers(int nt, int ntok, bool want_logits);
     void build_graph();
@@ -102,6 +116,7 @@ private:
     int graph_kernels_ = 0;
     long long *mega_trace_ = nullptr; int mega_n_ops_ = 0;
     int mega_stk_ = 7;
+    int mega_gen_ = 4; void *mega5_params_ = nullptr; void *mega5_ops_ = nullptr; int mega5_nbl_ = 0;  // generation 5 (llama_mega5.cuh)
     bool mega_ll_ = false; void *mega_params_ll_ = nullptr; void *mega_ll_buf_ = nullptr;  // experimental flag-in-data variant (llama_mega_ll.cuh)
     bool mega_ = false; void *mega_ops_ = nullptr; unsigned *mega_barrier_ = nullptr; void *mega_params_ = nullptr; size_t mega_smem_ = 0; int mega_type_ = -1;
     int sm_count_ = 148;

@@ -800,6 +800,12 @@ __global__ void embed_kernel(int type, const unsigned char *tok, size_t row_byte
     const unsigned char *row = tok + (size_t)st->tokens[t] * row_bytes;
     for (int i = threadIdx.x; i < E; i += blockDim.x) x[(size_t)t * E + i] = dequant_elem(type, row, i);
 }
+// the same gather for a long id list (prefill passes of up to 512 tokens; DeviceState::tokens holds 8)
+__global__ void embed_ids_kernel(int type, const unsigned char *tok, size_t row_bytes, int E, const int *ids, float *x) {
+    const int t = blockIdx.x;
+    const unsigned char *row = tok + (size_t)ids[t] * row_bytes;
+    for (int i = threadIdx.x; i < E; i += blockDim.x) x[(size_t)t * E + i] = dequant_elem(type, row, i);
+}
 // Q4_K token-embedding rows (EXPERIMENTAL, with the Q4_K matvec): kept out of dequant_elem so that the kernels which inline it
 // (embed_kernel, the decode megakernel) stay byte-identical to the measured build
 __global__ void embed_q4k_kernel(const unsigned char *tok, size_t row_bytes, int E, const DeviceState *st, float *x) {

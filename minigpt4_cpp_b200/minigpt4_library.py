@@ -191,7 +191,7 @@ class Stats(C.Structure):
     _fields_ = [("llm_weight_bytes_per_token", C.c_double), ("vision_flops_per_image", C.c_double), ("vision_weight_bytes", C.c_double),
                 ("last_encode_ms", C.c_double), ("kernel_launches", C.c_ulonglong), ("n_layer", C.c_int), ("n_embd", C.c_int), ("n_ff", C.c_int),
                 ("n_vocab", C.c_int), ("n_ctx", C.c_int), ("tp_rank", C.c_int), ("tp_world", C.c_int), ("sm_count", C.c_int), ("decode_megakernel", C.c_int),
-                ("reserved", C.c_int)]
+                ("prefill_gemm", C.c_int)]
 
 
 _VP = C.c_void_p
@@ -295,9 +295,16 @@ class B200:
         return ms.value, nb.value
 
     def mega_trace(self, ctx) -> np.ndarray:
-        buf = np.zeros(2 * 400 * 8, np.int64)
+        """per-op clock stamps [2 CTAs][n_ops][8]; generation 5 appends [2 CTAs][8] producer counters (see mega_trace_producer)"""
+        buf = np.zeros(2 * 401 * 8, np.int64)
         n = self.L.minigpt4_b200_mega_trace(ctx.ptr, _ptr(buf), buf.size)
+        self._trace_tail = buf[n - 16:n].reshape(2, 8).copy() if n and self.stats(ctx).decode_megakernel == 5 else None
+        if self._trace_tail is not None: n -= 16
         return buf[:n].reshape(2, -1, 8) if n else buf[:0]
+
+    def mega_trace_producer(self):
+        """generation 5: per traced CTA {cycles the producer waited for a free ring slot, cycles total, chunks} of the last mega_trace() call"""
+        return getattr(self, "_trace_tail", None)
 
     def stats(self, ctx) -> Stats:
         s = Stats()

@@ -19,7 +19,7 @@ with tempfile.TemporaryDirectory() as d:
         p = f"{d}/llama-{wt}-{dims['n_embd']}.bin"
         mg.write_llama_ggjt(p, mg.LlamaSpec(wtype=wt, **dims))
         c = ext.llm_load(p, n_ctx=512)
-        assert ext.stats(c).decode_megakernel == 1, "megakernel not active"
+        assert ext.stats(c).decode_megakernel >= 1, "megakernel not active"
         e = orc.OracleEngine(None, p, n_ctx=512)
         ids = [int(x) for x in np.random.default_rng(3).integers(3, dims["n_vocab"], n_prompt)]
         ext.eval_tokens(c, ids); e.eval_tokens(ids)

@@ -9,16 +9,22 @@ import bench
 lib = m.load_library(); ext = m.B200(lib)
 from minigpt4_cpp_b200 import modelgen as mg
 NL = int(os.environ.get("TRACE_LAYERS", "4"))  # per-layer numbers do not depend on depth; 4 layers keep generation fast
-llm = str(bench.model_dir() / f"llama-7bwide-{NL}l-q4_1.bin")
+NV = int(os.environ.get("TRACE_VOCAB", "32000"))  # a huge vocabulary turns the token into one long barrier-free weight stream (the output matvec)
+llm = str(bench.model_dir() / f"llama-7bwide-{NL}l-v{NV}-q4_1.bin")
 if not os.path.exists(llm):
-    mg.write_llama_ggjt(llm, mg.LlamaSpec(wtype="q4_1", n_embd=4096, n_head=32, n_layer=NL))
+    mg.write_llama_ggjt(llm, mg.LlamaSpec(wtype="q4_1", n_vocab=NV, n_embd=4096, n_head=32, n_layer=NL))
 ctx = ext.llm_load(llm, n_ctx=2048)
 rows = np.random.default_rng(0).standard_normal((32, 4096)).astype(np.float32)
 ext.eval_embd(ctx, rows)
 ids, ms = ext.decode_chain(ctx, 128)
-print("chain ms/token", ms / 128, "(trace off)" if NOTRACE else "(trace on)")
+print("chain ms/token", ms / 128, "(trace off)" if NOTRACE else "(trace on)", f"| {ext.stats(ctx).llm_weight_bytes_per_token / (ms / 128) * 1e-6:.0f} GB/s of weights")
 if NOTRACE: sys.exit(0)
 tr = ext.mega_trace(ctx).astype(np.float64)  # last launch
+prod = ext.mega_trace_producer()
+if prod is not None:
+    for c in range(2):
+        b, t, n = prod[c][:3]
+        print(f"producer CTA {'0' if c == 0 else 'G-1'}: {n} chunks, {t / 1965.0:.1f} us total, {b / 1965.0:.1f} us waiting for a free ring slot (= HBM idle for this SM's stream)")
 names = {0: "embed", 1: "qkv", 2: "attn", 3: "wo", 4: "gate_up", 5: "down", 6: "output", 7: "final"}
 kinds = [0] + [1, 2, 3, 4, 5] * NL + [6, 7]
 mhz = 1965.0
