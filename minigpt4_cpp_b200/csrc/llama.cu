@@ -409,8 +409,13 @@ void LlamaDevice::logits_to_host(float *dst) {
     CUDA_CHECK(cudaMemcpyAsync(dst, logits_, (size_t)d_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
+void LlamaDevice::sync_decode() {
+    const cudaError_t e = cudaStreamSynchronize(stream_);
+    if (e != cudaSuccess && mega_gen_ == 5) fprintf(stderr, "[minigpt4-b200][fatal] decode megakernel stopped; spin-guard reason code 0x%x (0 = not a guard trap)\n", (unsigned)h_argmax_[4]);
+    CUDA_CHECK(e);
+}
 int32_t LlamaDevice::argmax() {
-    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    sync_decode();
     return *h_argmax_;
 }
 void LlamaDevice::sync() { CUDA_CHECK(cudaStreamSynchronize(stream_)); }
@@ -640,15 +645,23 @@ bool LlamaDevice::build_mega() {
         const size_t fixed = ff_b + e_b + ops_b5 + 64;
         const size_t stat5 = 10752;  // static shared memory of decode_megakernel5 (red, redf, qs, kcur, vcur, part)
         const long long room = (long long)budget - (long long)stat5 - (long long)fixed - 1024;
-        const int n_slots5 = (int)std::min<long long>(48, room / (long long)(slot + 16));
-        if (n_slots5 >= 12) {
-            std::vector<Op5> ops5;
+        // group slots: one bulk copy brings 4 row pairs of an n_embd-wide matrix or 3 rows of the n_ff-wide one (7B: 20 480 / 20 640 B)
+        const int ub_e = 2 * rb_e, ub_f = rb_ff;
+        const int slot5 = (std::max(4 * ub_e, 3 * ub_f) + 127) & ~127;
+        const int n_slots5 = (int)std::min<long long>(48, room / (long long)(slot5 + 24));
+        const int free_slots = getenv("MINIGPT4_B200_INFLIGHT") ? atoi(getenv("MINIGPT4_B200_INFLIGHT")) : 4;  // slots kept free of consumers: the fills in flight
+        if (n_slots5 >= 5) {
+            std::vector<Op5> ops5; int upg_max = 1;
             for (auto &o : ops) {
-                Op5 q{}; q.kind = (unsigned char)o.kind; q.layer = (unsigned short)o.layer; q.cols = o.cols; q.n_su = o.n_su; q.row_bytes = (unsigned short)o.row_bytes;
-                q.sps = (unsigned char)o.sps; q.w = o.w; q.norm_w = o.norm_w;
+                Op5 q{}; q.kind = (unsigned char)o.kind; q.layer = (unsigned short)o.layer; q.cols = o.cols; q.row_bytes = (unsigned short)o.row_bytes;
+                q.w = o.w; q.norm_w = o.norm_w;
                 if (o.w) {
                     if (o.row_bytes > 65535) return false;
-                    q.n_warps = (unsigned char)std::max(1, std::min(kConsumerWarps, (n_slots5 - (q.sps == 2 ? inflight2 : inflight)) / q.sps));
+                    q.rpu = o.kind == OP_DOWN ? 1 : 2;
+                    q.n_su = o.rows / q.rpu;
+                    q.upg = (unsigned char)std::max(1, std::min(15, slot5 / (o.row_bytes * q.rpu)));
+                    q.n_warps = (unsigned char)std::max(1, std::min(kConsumerWarps, std::max(1, n_slots5 - free_slots) * q.upg));
+                    upg_max = std::max(upg_max, (int)q.upg);
                 }
                 ops5.push_back(q);
             }
@@ -656,24 +669,25 @@ bool LlamaDevice::build_mega() {
             CUDA_CHECK(cudaMemcpy(mega5_ops_, ops5.data(), ops5.size() * sizeof(Op5), cudaMemcpyHostToDevice));
             const size_t nE = (size_t)E, nF = (size_t)FF, nbE = nE / 32;
             const size_t n_ll = 2 * nE + nF + nE + nbE * 10;  // x, q | act | kcur + vcur (E/2 each) | att words
-            const size_t bytes = n_ll * sizeof(LLf) + 256;
+            const size_t bytes = n_ll * sizeof(LLf) + 256 + ops.size() * 4;
             CUDA_CHECK(cudaMalloc(&mega_ll_buf_, bytes)); CUDA_CHECK(cudaMemset(mega_ll_buf_, 0, bytes));
             mk5::Params *Q = new mk5::Params();
             LLf *b = (LLf *)mega_ll_buf_;
             Q->ops = (const Op5 *)mega5_ops_; Q->n_ops = (int)ops.size();
-            Q->n_slots = n_slots5; Q->slot_bytes = slot; Q->ff_bytes = (int)ff_b; Q->e_bytes = (int)e_b;
+            Q->n_slots = n_slots5; Q->slot_bytes = slot5; Q->ff_bytes = (int)ff_b; Q->e_bytes = (int)e_b; Q->upg_max = upg_max;
             Q->E = E; Q->FF = FF; Q->n_head = d_.n_head; Q->n_ctx = d_.n_ctx; Q->n_vocab = d_.n_vocab; Q->kq_scale = P->kq_scale;
             Q->x = b; Q->q = b + nE; Q->act = b + 2 * nE; Q->kcur = b + 2 * nE + nF; Q->vcur = Q->kcur + nE / 2; Q->att = Q->vcur + nE / 2;
             Q->seq = (unsigned *)(Q->att + nbE * 10);
+            Q->done = Q->seq + 64;                                  // [n_ops] completion-hint counters (zeroed with the buffer)
+            h_argmax_[4] = 0; Q->dbg = (volatile unsigned *)(h_argmax_ + 4);   // pinned host word (unified addressing): trap reason
             Q->logits = logits_; Q->kcache = kcache_; Q->vcache = vcache_; Q->rope = rope_; Q->tab_exp = tab_exp_; Q->tab_silu = tab_silu_;
             Q->tok = P->tok; Q->tok_type = P->tok_type; Q->tok_row_bytes = P->tok_row_bytes; Q->state = state_; Q->barrier = mega_barrier_;
-            Q->l2_ahead = getenv("MINIGPT4_B200_L2_AHEAD") ? atoi(getenv("MINIGPT4_B200_L2_AHEAD")) : 0;
             Q->flags = P->flags; Q->trace = P->trace;
             mega5_params_ = Q; mega_gen_ = 5; mega_ll_ = false;
             mega5_nbl_ = (E == 4096 && !getenv("MINIGPT4_B200_MEGA5_NOREG")) ? 4 : (E == 5120 && !getenv("MINIGPT4_B200_MEGA5_NOREG")) ? 5 : 0;
-            mega_smem_ = (size_t)n_slots5 * slot + fixed + (size_t)n_slots5 * 16;
-            MG4_INFO("decode megakernel generation 5: ring %d x %d B, act buffers %zu + %zu B, register-resident blocks per lane %d, L2 look-ahead %d chunks, flags %d",
-                     n_slots5, slot, ff_b, e_b, mega5_nbl_, Q->l2_ahead, Q->flags);
+            mega_smem_ = (size_t)n_slots5 * slot5 + fixed + (size_t)n_slots5 * 24;
+            MG4_INFO("decode megakernel generation 5: ring %d x %d B (up to %d units per copy), act buffers %zu + %zu B, register-resident blocks per lane %d, flags %d",
+                     n_slots5, slot5, upg_max, ff_b, e_b, mega5_nbl_, Q->flags);
         }
     }
     mega_stk_ = (std::max(E, FF) + 2047) / 2048;
@@ -753,7 +767,7 @@ float LlamaDevice::decode_chain(int steps, int n_past, int32_t *ids_out) {
         CUDA_CHECK(cudaGraphLaunch(graph_, stream_));
     }
     CUDA_CHECK(cudaEventRecord(ev1_, stream_));
-    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    sync_decode();
     launches_ += (unsigned long long)graph_kernels_ * steps;
     float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
     if (ids_out) CUDA_CHECK(cudaMemcpy(ids_out, ids_dev, (size_t)steps * 4, cudaMemcpyDeviceToHost));

@@ -55,6 +55,7 @@ public:
     void logits_to_host(float *dst);   // n_vocab floats, synchronous
     int32_t argmax();                  // greedy id of the current logits (already in pinned host memory after a sync)
     void sync();
+    void sync_decode();              // stream sync that reports the megakernel's spin-guard reason code if the launch failed
     int sm_count() const { return sm_count_; }
     bool uses_megakernel() const { return mega_; }
     bool uses_prefill_gemm() const { return pf_ready_; }

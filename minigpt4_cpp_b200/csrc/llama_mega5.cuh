@@ -14,8 +14,10 @@
 //   * ATTENTION OUTPUT IS EXCHANGED QUANTISED: the head's CTA quantises its 128 outputs to the Q8 blocks `wo` consumes (the blocks are
 //     local to a head) and publishes 40 tagged words per head; the `wo` staging of every CTA is then a 10 KB gather instead of a 32 KB
 //     gather + quantisation.
-//   * L2 LOOK-AHEAD WITHOUT A POLLING LANE: the producer thread, when the ring is full (= exactly when HBM would go idle), asks L2 for the
-//     chunks behind the ring (cp.async.bulk.prefetch.L2), up to `l2_ahead` chunks ahead of the fill cursor.
+//   * GROUP SLOTS: a ring slot holds SEVERAL consecutive units (7B: 4 row pairs of an n_embd-wide matrix = 20 480 B, or 3 rows of the n_ff-wide
+//     one = 20 640 B, in a 20 736 B slot) filled by ONE cp.async.bulk.  Measured on a barrier-free stream (1 layer + 200 000-row output matrix):
+//     with one 5 KB copy per row pair the single producer thread tops out near 4.4 TB/s (its per-copy cost: try_wait + expect_tx + issue) and a
+//     quarter of every 6.9 KB slot stayed empty; group slots cut the producer's work per byte by 4 and use 99 % of the ring.
 // Arithmetic and every float reduction order are those of llama_kernels.cuh / oracle.cpp: logits stay bit-identical.
 #pragma once
 #include "llama_mega.cuh"
@@ -32,9 +34,9 @@ using mk::kNormItems; using mk::kPlainItems;
 struct LLf { float v; unsigned tag; };  // 8 bytes, 8-byte aligned: one 64-bit access
 
 struct Op5 {                 // one op of the token program, 32 bytes (the program lives in shared memory: 5 n_layer + 3 entries)
-    int cols, n_su;          // input width; units (row pairs) of the op over the whole grid
+    int cols, n_su;          // input width; units of the op over the whole grid (a unit = a row pair; `down`: ONE n_ff-wide row)
     unsigned short row_bytes, layer;
-    unsigned char kind, sps, n_warps, pad;   // sps = ring slots per unit (1: the unit sits in one slot; 2: one row per slot)
+    unsigned char kind, rpu, n_warps, upg;   // rpu = rows per unit (2 | 1); upg = units per ring slot: ONE bulk copy brings upg consecutive units
     const unsigned char *w;  // row-packed Q4 weights (null for non-matvec ops)
     const float *norm_w;
 };
@@ -49,15 +51,17 @@ struct Params {
     LLf *kcur, *vcur;            // [E/2] each: the current position's K / V as tagged half2 (the F16 cache rows have no room for a tag)
     LLf *att;                    // quantised attention output: [E/32 * 8] words of 4 int8 | [E/32] d | [E/32] s, all tagged
     unsigned *seq;               // launches so far (advanced by OP_FINAL); part of every tag
+    unsigned *done;              // [n_ops] monotonic completion counters: CTAs that finished op i (all launches).  Only a HINT that tells pollers
+                                 // when to look (no fence orders it against the data); readiness itself is the tag in every element
+    volatile unsigned *dbg;      // pinned host word: reason code of a spin-guard trap (readable after the launch failed)
     float *logits;
     __half *kcache, *vcache;
     const float2 *rope; const __half *tab_exp, *tab_silu;
     const unsigned char *tok; int tok_type; size_t tok_row_bytes;
     DeviceState *state; unsigned *barrier;
-    int l2_ahead;                // producer: chunks requested into L2 beyond the fill cursor while the ring is full (0 = off)
+    int upg_max;                 // arrival count of the slots' "empty" barriers = the largest upg of the program
     int flags;                   // bit 0: request the head's K/V history into L2 while the qkv weights are consumed
                                  // bit 2: CTA barrier BEFORE staging too (polling starts when the whole CTA is done with the previous op)
-                                 // bit 3: units are dealt to CTAs round-robin (unit u -> CTA u mod G: the grid streams adjacent chunks) instead of in contiguous shares
     long long *trace;            // optional [2 CTAs][n_ops][8] clock64 stamps (layout of tools/mega_trace.py)
 };
 
@@ -80,14 +84,30 @@ __device__ __forceinline__ unsigned long long ll_load(const LLf *p) {
     asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return w;
 }
-// Every spin is bounded: a protocol bug must end in a trapped launch (an error the host reports), never in a hung GPU.
+// Every spin is bounded: a protocol bug must end in a trapped launch (an error the host reports), never in a hung GPU.  The reason code goes to
+// a pinned host word first (device memory is unreadable after a trap).
 constexpr unsigned kSpinLimit = 1u << 22;
-__device__ __forceinline__ void spin_guard(unsigned &spins) { if (++spins > kSpinLimit) asm volatile("trap;"); }
-__device__ __forceinline__ unsigned ll_wait(const LLf *p, unsigned tag) {
+__device__ unsigned *g_dbg_word = nullptr;
+__device__ __forceinline__ void spin_guard(unsigned &spins, unsigned code) {
+    if (++spins > kSpinLimit) { if (g_dbg_word) { *(volatile unsigned *)g_dbg_word = code; __threadfence_system(); } asm volatile("trap;"); }
+}
+__device__ __forceinline__ unsigned ll_wait(const LLf *p, unsigned tag, unsigned code) {
     unsigned long long w; unsigned spins = 0;
-    do { w = ll_load(p); spin_guard(spins); } while ((unsigned)(w >> 32) != tag);
+    for (;;) { w = ll_load(p); if ((unsigned)(w >> 32) == tag) break; spin_guard(spins, code); __nanosleep(40); }
     return (unsigned)w;
 }
+// hint: sleep-poll ONE word until `target` CTAs have finished the producing op, then look at the tagged data (normally ready at the first look).
+// Polling the data itself from 148 x 256 threads saturates the L2 request path and slows the weight stream (measured: 272 -> 221 us per token
+// just by not polling while the CTA's own warps still consume).
+__device__ __forceinline__ void hint_wait(const unsigned *counter, unsigned target, unsigned code) {
+    unsigned v, spins = 0;
+    for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if ((int)(v - target) >= 0) break;
+        spin_guard(spins, code); __nanosleep(60);
+    }
+}
+__device__ __forceinline__ void hint_post(unsigned *counter) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory"); }
 // two elements with one 16-byte access (each 8-byte half was written by one 64-bit store, so it is seen whole)
 __device__ __forceinline__ void ll_load2(const LLf *p, unsigned long long &a, unsigned long long &b) {
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
@@ -130,7 +150,7 @@ __device__ __forceinline__ void stage_plain5(const LLf *__restrict__ x, unsigned
     for (int it = 0; it < kPlainItems; ++it) { xv[it] = make_float4(0.f, 0.f, 0.f, 0.f); if (4 * (tid + kConsumerThreads * it) < cols) need |= 1u << it; }
     unsigned spins = 0;
     while (need) {
-        spin_guard(spins);
+        spin_guard(spins, 0x100u);
 #pragma unroll
         for (int it = 0; it < kPlainItems; ++it)
             if (need & (1u << it)) { if (ll_try4(x + 4 * (tid + kConsumerThreads * it), tag, xv[it])) need &= ~(1u << it); }
@@ -152,7 +172,7 @@ __device__ __forceinline__ void stage_norm5(const LLf *__restrict__ x, unsigned 
     for (int it = 0; it < kNormItems; ++it) { xv[it] = make_float4(0.f, 0.f, 0.f, 0.f); if (1024 * it + 4 * tid < cols) need |= 1u << it; }
     unsigned spins = 0;
     while (need) {
-        spin_guard(spins);
+        spin_guard(spins, 0x200u);
 #pragma unroll
         for (int it = 0; it < kNormItems; ++it)
             if (need & (1u << it)) { if (ll_try4(x + 1024 * it + 4 * tid, tag, xv[it])) need &= ~(1u << it); }
@@ -195,7 +215,7 @@ __device__ __forceinline__ void stage_att5(const LLf *__restrict__ att, unsigned
     for (int it = 0; it < kAttItems; ++it) { val[it] = 0u; if (tid + 256 * it < total) need |= 1u << it; }
     unsigned spins = 0;
     while (need) {
-        spin_guard(spins);
+        spin_guard(spins, 0x300u);
 #pragma unroll
         for (int it = 0; it < kAttItems; ++it)
             if (need & (1u << it)) { const unsigned long long w = ll_load(att + tid + 256 * it); if ((unsigned)(w >> 32) == tag) { val[it] = (unsigned)w; need &= ~(1u << it); } }
@@ -239,6 +259,31 @@ __device__ __forceinline__ void dot2_q4_smem(const unsigned char *row0, const un
     r0 = warp_sum(accd0) + warp_sum(accm0);
     r1 = warp_sum(accd1) + warp_sum(accm1);
 }
+// one row (the n_ff-wide `down` matrix: a unit is one row, three rows share a ring slot)
+template <bool Q41>
+__device__ __forceinline__ float dot1_q4_smem(const unsigned char *row0, int nb, int cols, const unsigned char *act, int lane) {
+    const uint4 *qs0 = (const uint4 *)row0;
+    const unsigned char *sc0 = row0 + (size_t)nb * 16;
+    const int4 *alo = (const int4 *)act, *ahi = (const int4 *)(act + act5_hi(cols));
+    const float *ad = (const float *)(act + act5_d(cols)), *as = ad + nb;
+    float accd0 = 0.f, accm0 = 0.f;
+#pragma unroll 4
+    for (int b = lane; b < nb; b += 32) {
+        const uint4 q0 = qs0[b];
+        const int4 la = alo[b], ha = ahi[b];
+        const float adv = ad[b], asv = as[b];
+        int s0 = q4_block_idot(q0, la, ha);
+        if (Q41) {
+            const float2 f0 = __half22float2(((const __half2 *)sc0)[b]);
+            accd0 = fmaf(f0.x * adv, (float)s0, accd0); accm0 = fmaf(f0.y, asv, accm0);
+        } else {
+            const float d0 = __half2float(((const __half *)sc0)[b]);
+            s0 -= 8 * (int)asv;
+            accd0 += ((float)s0 * d0) * adv;
+        }
+    }
+    return warp_sum(accd0) + warp_sum(accm0);
+}
 // register-resident activations: lane l holds blocks l + 32 i (i < NBL) of the staged vector; same per-lane order and arithmetic
 template <int NBL> struct ActRegs { int4 lo[NBL], hi[NBL]; float d[NBL], s[NBL]; };
 template <int NBL>
@@ -274,73 +319,74 @@ __device__ __forceinline__ void dot2_q4_reg(const unsigned char *row0, const uns
     r1 = warp_sum(accd1) + warp_sum(accm1);
 }
 
-// unit -> CTA mapping.  Contiguous shares (round 1): CTA c owns units [c n / G, (c + 1) n / G).  Interleaved (flags bit 3): CTA c owns units
-// c, c + G, c + 2 G, ...: at any moment the grid's 148 producers request ADJACENT chunks of the matrix (a DRAM-sequential burst, like a copy kernel).
-__device__ __forceinline__ int cta_units(bool il, int cta, int n_su, int G) {
-    return il ? (cta < n_su ? (n_su - cta + G - 1) / G : 0) : unit_begin(cta + 1, n_su, G) - unit_begin(cta, n_su, G);
-}
-__device__ __forceinline__ int cta_unit(bool il, int cta, int n_su, int G, int k) { return il ? cta + k * G : unit_begin(cta, n_su, G) + k; }
+// unit -> CTA mapping: CTA c owns the contiguous units [c n / G, (c + 1) n / G), so that a group of consecutive units is one contiguous copy
+__device__ __forceinline__ int cta_units(int cta, int n_su, int G) { return unit_begin(cta + 1, n_su, G) - unit_begin(cta, n_su, G); }
 
 // shared memory carve-up (dynamic)
-struct Smem5 { unsigned char *ring, *ff, *e0; uint64_t *full, *empty; Op5 *ops; };
+struct Smem5 { unsigned char *ring, *ff, *e0; uint64_t *full, *empty; Op5 *ops; };  // full: [2][n_slots] (even / odd ring laps), empty: [n_slots]
 __device__ __forceinline__ Smem5 carve5(const Params &P) {
     extern __shared__ __align__(128) unsigned char smem[];
     Smem5 m;
     m.ring = smem; m.ff = smem + (size_t)P.n_slots * P.slot_bytes;
     m.e0 = m.ff + P.ff_bytes;
-    m.full = (uint64_t *)(m.e0 + P.e_bytes); m.empty = m.full + P.n_slots;
+    m.full = (uint64_t *)(m.e0 + P.e_bytes); m.empty = m.full + 2 * P.n_slots;
     m.ops = (Op5 *)(m.empty + P.n_slots);
     return m;
 }
 
-// The matvec phase of one op for one consumer warp (see mk::consume_units for the ring / parity argument): outputs are tagged.
-// Units: a row PAIR (one slot of two n_embd-wide rows, or two slots of one n_ff-wide row each).
+// The matvec phase of one op for one consumer warp: outputs are tagged.  Unit k of the CTA's share sits in fill (n_base + k / upg) at offset
+// (k % upg) * unit bytes; warp w takes units w, w + W, ...
+// Every slot has TWO "full" barriers, used by even and odd ring laps.  With one, a warp that waits for fill n could see the completed phase of
+// fill n - 2 laps while fill n - 1 lap is still in flight (same parity: the async copies of different fills may complete out of order under
+// load), read a half-written slot and release it.  With two, the previous phase of fill n's barrier is fill n - 2 laps, which must have been
+// consumed before fill n - 1 lap could be issued, and that fill was issued before the fill of this warp's previous unit (fills are issued in
+// order; the previous unit is less than a lap back, or in the previous op, all of whose fills are consumed).
 template <bool Q41, int KIND, int NBL, bool TRACE>
 __device__ __forceinline__ unsigned consume5(const Params &P, int oi, unsigned n_base, int pos, unsigned tag, const unsigned char *actb, long long *tr) {
     const Smem5 m = carve5(P);
     const Op5 &op = m.ops[oi];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = (int)gridDim.x, cta = (int)blockIdx.x;
-    const int W = op.n_warps, sps = op.sps;
-    const bool il = (P.flags & 8) != 0;
-    const int cnt = cta_units(il, cta, op.n_su, G);
-    const unsigned n_next = n_base + (unsigned)cnt * (unsigned)sps;
+    const int W = op.n_warps, upg = op.upg;
+    const int lo = unit_begin(cta, op.n_su, G), cnt = unit_begin(cta + 1, op.n_su, G) - lo;
+    const unsigned n_next = n_base + (unsigned)((cnt + upg - 1) / upg);
     if (warp >= W) return n_next;
-    const int cols = op.cols, nb = cols >> 5, S = P.n_slots, stepn = W * sps;
+    const int cols = op.cols, nb = cols >> 5, S = P.n_slots;
     constexpr bool REG = NBL > 0 && KIND != OP_DOWN;  // n_embd-wide input held in registers
+    constexpr int RPU = KIND == OP_DOWN ? 1 : 2;       // rows per unit
     ActRegs<REG ? NBL : 1> ar;
     if (REG) load_act_regs<REG ? NBL : 1>(actb, cols, lane, ar);
     const unsigned rb = (unsigned)op.row_bytes, slot_bytes = (unsigned)P.slot_bytes;
-    const unsigned n0 = n_base + (unsigned)(warp * sps);
-    int s0 = (int)(n0 % (unsigned)S);
-    unsigned ph0 = (n0 / (unsigned)S) & 1u;
     unsigned long long best = 0ull;
     __half pend_h = __ushort_as_half((unsigned short)0); float pend_up = 0.f; int pend_i = -1;
     long long t_wait = 0, t_dot = 0, t_epi = 0; int n_units = 0;  // (TRACE: kept in registers, stored once per op)
     for (int k = warp; k < cnt; k += W) {
-        const int su = cta_unit(il, cta, op.n_su, G, k);
-        int s1 = s0 + 1; unsigned ph1 = ph0;
-        if (s1 == S) { s1 = 0; ph1 ^= 1u; }
-        const int r0 = su * 2;
+        const int g = k / upg, sub = k - g * upg;
+        const unsigned n = n_base + (unsigned)g;
+        const int sl = (int)(n % (unsigned)S);
+        const unsigned lap = n / (unsigned)S;
+        uint64_t *const fb = &m.full[(lap & 1u) * (unsigned)S + (unsigned)sl];
+        const unsigned ph = (lap >> 1) & 1u;
+        const int r0 = (lo + k) * RPU;
         float2 rs = make_float2(0.f, 0.f);
-        if (KIND == OP_WO || KIND == OP_DOWN) {  // residual rows: final since this CTA gathered the whole of x for the previous normed op
+        if (KIND == OP_WO) {  // residual rows: final since this CTA gathered the whole of x for the previous normed op
             const uint4 t = __ldcg((const uint4 *)(P.x + r0));
             rs = make_float2(__uint_as_float(t.x), __uint_as_float(t.z));
         }
+        if (KIND == OP_DOWN) rs.x = __uint_as_float(__ldcg((const unsigned *)(P.x + r0)));
         if (KIND == OP_QKV) { if (r0 < 2 * P.E) rs = __ldg(&P.rope[(size_t)pos * 64 + ((r0 % P.E) % 128) / 2]); }
         long long tw0 = 0, tw1 = 0, tw2 = 0;
         if (TRACE && tr) tw0 = clock64();
-        mb_wait(&m.full[s0], ph0);
-        if (sps == 2) mb_wait(&m.full[s1], ph1);
+        mb_wait(fb, ph);
         if (TRACE && tr) tw1 = clock64();
-        const unsigned char *row0 = m.ring + (size_t)s0 * slot_bytes;
-        const unsigned char *row1 = sps == 2 ? m.ring + (size_t)s1 * slot_bytes : row0 + rb;
-        float v0, v1;
-        if (REG) dot2_q4_reg<Q41, REG ? NBL : 1>(row0, row1, ar, lane, v0, v1);
+        const unsigned char *row0 = m.ring + (size_t)sl * slot_bytes + (size_t)sub * (RPU * rb);
+        const unsigned char *row1 = row0 + rb;
+        float v0, v1 = 0.f;
+        if (KIND == OP_DOWN) v0 = dot1_q4_smem<Q41>(row0, nb, cols, actb, lane);
+        else if (REG) dot2_q4_reg<Q41, REG ? NBL : 1>(row0, row1, ar, lane, v0, v1);
         else dot2_q4_smem<Q41>(row0, row1, nb, cols, actb, lane, v0, v1);
         if (TRACE && tr) { tw2 = clock64(); t_wait += tw1 - tw0; t_dot += tw2 - tw1; ++n_units; }
         if (lane == 0) {
-            mb_arrive(&m.empty[s0]);
-            if (sps == 2) mb_arrive(&m.empty[s1]);
+            mb_arrive(&m.empty[sl]);
             if (KIND == OP_QKV) {
                 const int E = P.E, partn = r0 / E, rr = r0 % E;
                 const size_t kvo = ((size_t)op.layer * P.n_ctx + pos) * E + rr;
@@ -358,8 +404,10 @@ __device__ __forceinline__ unsigned consume5(const Params &P, int oi, unsigned n
                         ll_store_bits(P.kcur + (rr >> 1), *(const unsigned *)&h2, tag);
                     }
                 }
-            } else if (KIND == OP_WO || KIND == OP_DOWN) {
+            } else if (KIND == OP_WO) {
                 ll_store(P.x + r0, v0 + rs.x, tag); ll_store(P.x + r0 + 1, v1 + rs.y, tag);
+            } else if (KIND == OP_DOWN) {
+                ll_store(P.x + r0, v0 + rs.x, tag);
             } else if (KIND == OP_GATEUP) {
                 if (pend_i >= 0) ll_store(P.act + pend_i, __half2float(pend_h) * pend_up, tag);
                 pend_h = P.tab_silu[__half_as_ushort(__float2half_rn(v0))]; pend_up = v1; pend_i = r0 >> 1;
@@ -370,7 +418,6 @@ __device__ __forceinline__ unsigned consume5(const Params &P, int oi, unsigned n
                 if (r0 + 1 < P.n_vocab) { P.logits[r0 + 1] = v1; const unsigned long long k1 = argmax_key(v1, r0 + 1); best = best > k1 ? best : k1; }
             }
         }
-        s0 += stepn; while (s0 >= S) { s0 -= S; ph0 ^= 1u; }
         if (TRACE && tr) t_epi += clock64() - tw2;
     }
     if (KIND == OP_GATEUP) { if (lane == 0 && pend_i >= 0) ll_store(P.act + pend_i, __half2float(pend_h) * pend_up, tag); }
@@ -393,9 +440,9 @@ __device__ __noinline__ void attention5(const Params &P, int layer, int pos, int
     const int nkv = pos + 1;
     const int sub = lane >> 4, l16 = lane & 15;
     uint4 kv[B];
-    if (tid < 128) qs[tid] = __uint_as_float(ll_wait(P.q + h * 128 + tid, tag_in));
-    else if (tid < 192) ((unsigned *)kcur_s)[tid - 128] = ll_wait(P.kcur + h * 64 + (tid - 128), tag_in);
-    else ((unsigned *)vcur_s)[tid - 192] = ll_wait(P.vcur + h * 64 + (tid - 192), tag_in);
+    if (tid < 128) qs[tid] = __uint_as_float(ll_wait(P.q + h * 128 + tid, tag_in, 0x400u));
+    else if (tid < 192) ((unsigned *)kcur_s)[tid - 128] = ll_wait(P.kcur + h * 64 + (tid - 128), tag_in, 0x401u);
+    else ((unsigned *)vcur_s)[tid - 192] = ll_wait(P.vcur + h * 64 + (tid - 192), tag_in, 0x402u);
     cta_sync<true>();
     if (tr) tr[1] = clock64();
     {
@@ -505,61 +552,41 @@ __device__ __noinline__ void attention5(const Params &P, int layer, int pos, int
     }
 }
 
-// ---- the producer thread: fills the ring with cp.async.bulk; while the ring is full it asks L2 for the chunks behind it ---------------
-__device__ __forceinline__ bool mb_test(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Chunk sequence of this CTA: for every op with weights, (units of the CTA) x sps chunks.  Two cursors walk it (fill, look-ahead); a cursor
-// is (op, chunk index within the op) and the chunk's address is recomputed from the op record in shared memory - a handful of scalars that
-// stay in registers (a stack frame here costs the producer an L1/L2 round trip per chunk and starves the ring: measured, first v5 build).
-struct Chunk { const unsigned char *src; unsigned bytes; };
-__device__ __forceinline__ int op_chunks(const Op5 &o, bool il, int cta, int G) { return o.w ? cta_units(il, cta, o.n_su, G) * (int)o.sps : 0; }
-__device__ __forceinline__ Chunk op_chunk(const Op5 &o, bool il, int cta, int G, int idx) {
-    const unsigned rb = o.row_bytes;
-    const int rpu = 2;
-    const int k = o.sps == 2 ? idx >> 1 : idx, j = o.sps == 2 ? idx & 1 : 0;
-    Chunk c;
-    c.src = o.w + ((size_t)cta_unit(il, cta, o.n_su, G, k) * rpu + j) * rb;
-    c.bytes = o.sps == 1 ? (unsigned)rpu * rb : rb;
-    return c;
-}
+// The producer thread: for every op with weights, the CTA's share of rows is one contiguous range; it is cut into groups of upg units and
+// every group is ONE bulk copy into the next ring slot.  The slot's "empty" barrier expects upg_max arrivals: the units of the group arrive as
+// they are consumed, the producer adds the difference for smaller groups.  Running pointers only: everything stays in registers.
+__device__ __forceinline__ void mb_arrive_n(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory"); }
 __device__ __noinline__ void producer5(const Params &P) {
     const Smem5 m = carve5(P);
     if ((threadIdx.x & 31) != 0) return;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
-    const bool il = (P.flags & 8) != 0;
-    int f_oi = 0, f_idx = 0, f_cnt = 0;   // fill cursor
-    while (f_oi < P.n_ops && (f_cnt = op_chunks(m.ops[f_oi], il, cta, G)) == 0) ++f_oi;
-    int a_oi = f_oi, a_idx = 0, a_cnt = f_cnt;  // look-ahead cursor
-    int ahead = 0;  // chunks at / after the fill cursor that L2 has already been asked for
-    unsigned s = 0, ph = 0;
+    unsigned s = 0, ph = 0, lap = 0;
     long long t_blocked = 0, t_begin = 0; unsigned n_chunks = 0;
     const bool stats = P.trace != nullptr && (cta == 0 || cta == G - 1);
     if (stats) t_begin = clock64();
-    while (f_oi < P.n_ops) {
-        long long t0 = 0;
-        if (stats) t0 = clock64();
-        if (P.l2_ahead > 0) {
-            while (!mb_test(&m.empty[s], ph ^ 1u)) {  // ring full: the consumers are stalled or slow, HBM would go idle
-                if (ahead < P.l2_ahead && a_oi < P.n_ops) {
-                    const Chunk c = op_chunk(m.ops[a_oi], il, cta, G, a_idx);
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c.src), "r"(c.bytes) : "memory");
-                    ++ahead;
-                    if (++a_idx >= a_cnt) { a_idx = 0; ++a_oi; while (a_oi < P.n_ops && (a_cnt = op_chunks(m.ops[a_oi], il, cta, G)) == 0) ++a_oi; }
-                } else __nanosleep(64);
-            }
-        } else mb_wait(&m.empty[s], ph ^ 1u);
-        if (stats) { t_blocked += clock64() - t0; ++n_chunks; }
-        const Chunk c = op_chunk(m.ops[f_oi], il, cta, G, f_idx);
-        mb_expect_tx(&m.full[s], c.bytes);
-        bulk_g2s(m.ring + (size_t)s * P.slot_bytes, c.src, c.bytes, &m.full[s]);
-        if (++f_idx >= f_cnt) { f_idx = 0; ++f_oi; while (f_oi < P.n_ops && (f_cnt = op_chunks(m.ops[f_oi], il, cta, G)) == 0) ++f_oi; }
-        if (ahead > 0) --ahead; else { a_oi = f_oi; a_idx = f_idx; a_cnt = f_cnt; }
-        if (++s == (unsigned)P.n_slots) { s = 0; ph ^= 1u; }
+    for (int oi = 0; oi < P.n_ops; ++oi) {
+        const unsigned char *w = m.ops[oi].w;
+        if (!w) continue;
+        const int n_su = m.ops[oi].n_su, upg = m.ops[oi].upg;
+        const unsigned ub = (unsigned)m.ops[oi].row_bytes * (unsigned)m.ops[oi].rpu;  // bytes per unit
+        const int lo = unit_begin(cta, n_su, G), hi = unit_begin(cta + 1, n_su, G);
+        const unsigned char *src = w + (size_t)lo * ub;
+        for (int left = hi - lo; left > 0; left -= upg) {
+            const int nu = left < upg ? left : upg;
+            const unsigned bytes = (unsigned)nu * ub;
+            long long t0 = 0;
+            if (stats) t0 = clock64();
+            mb_wait(&m.empty[s], ph ^ 1u);
+            if (stats) { t_blocked += clock64() - t0; ++n_chunks; }
+            uint64_t *const fb = &m.full[(lap & 1u) * (unsigned)P.n_slots + s];
+            mb_expect_tx(fb, bytes);
+            bulk_g2s(m.ring + (size_t)s * P.slot_bytes, src, bytes, fb);
+            if (nu < P.upg_max) mb_arrive_n(&m.empty[s], (uint32_t)(P.upg_max - nu));
+            src += bytes;
+            if (++s == (unsigned)P.n_slots) { s = 0; ph ^= 1u; ++lap; }
+        }
     }
-    if (stats) {  // after the per-op records: [2 CTAs][8]: cycles waiting for a free slot, total cycles, chunks, unused
+    if (stats) {  // after the per-op records: [2 CTAs][8]: cycles waiting for a free slot, total cycles, copies, unused
         long long *o = P.trace + (size_t)2 * P.n_ops * 8 + (cta == 0 ? 0 : 8);
         o[0] = t_blocked; o[1] = clock64() - t_begin; o[2] = (long long)n_chunks; o[3] = 0;
     }
@@ -580,14 +607,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel5(const __gr
     __shared__ __align__(16) __half kcur_s[128];
     __shared__ __align__(16) __half vcur_s[128];
     __shared__ float part[16 * 128];
+    __shared__ unsigned op_done;   // consumer warps that finished their units, all ops so far (the 15th of an op posts the CTA's completion hint)
     constexpr int ACT = act_of(WT);
     constexpr bool Q41 = WT == GG_Q4_1;
     const Smem5 m = carve5(P);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    if (tid == 0) { op_done = 0u; g_dbg_word = (unsigned *)P.dbg; }
 
     if (tid == 0) {
-        for (int s = 0; s < P.n_slots; ++s) { mb_init(&m.full[s], 1); mb_init(&m.empty[s], 1); }
+        for (int s = 0; s < P.n_slots; ++s) { mb_init(&m.full[s], 1); mb_init(&m.full[P.n_slots + s], 1); mb_init(&m.empty[s], (uint32_t)P.upg_max); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P.n_ops * 2; i += kMegaThreads) ((uint4 *)m.ops)[i] = ((const uint4 *)P.ops)[i];
@@ -597,7 +626,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel5(const __gr
 
     unsigned n_base = 0;
     const int pos = __ldcg(&P.state->n_past);
-    const unsigned tag0 = (__ldcg(P.seq) << 10) + 1u;  // tag of op oi in this launch = tag0 + oi
+    const unsigned seqv = __ldcg(P.seq);
+    const unsigned tag0 = (seqv << 10) + 1u;  // tag of op oi in this launch = tag0 + oi
+    const unsigned all_ctas = (seqv + 1u) * (unsigned)G, all_heads = (seqv + 1u) * (unsigned)P.n_head;  // hint targets (counters are monotonic)
     unsigned tag_x = 0, tag_att = 0, tag_act = 0, tag_qkv = 0;  // tag of the op that last produced each vector
     for (int oi = 0; oi < P.n_ops; ++oi) {
         const int kind = m.ops[oi].kind;
@@ -609,12 +640,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel5(const __gr
             const int token = __ldcg(&P.state->tokens[0]);
             const unsigned char *row = P.tok + (size_t)token * P.tok_row_bytes;
             for (int i = cta * kConsumerThreads + tid; i < P.E; i += G * kConsumerThreads) ll_store(P.x + i, dequant_elem(P.tok_type, row, i), tag);
+            if (tid == 0) hint_post(P.done + oi);
             tag_x = tag;
             continue;
         }
         if (kind == OP_ATTN) {
-            if (cta < P.n_head && tid < 256)
+            if (cta < P.n_head && tid < 256) {
+                hint_wait(P.done + (tag_qkv - tag0), all_ctas, 0x500u);
                 attention5<ACT>(P, m.ops[oi].layer, pos, cta, tag_qkv, tag, m.ff, red, redf, qs, kcur_s, vcur_s, part, TRACE ? tr : nullptr);
+                if (tid == 0) hint_post(P.done + oi);
+            }
             tag_att = tag;
             continue;
         }
@@ -637,14 +672,19 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel5(const __gr
         if (P.flags & 4) consumer_sync();
         if (kind == OP_DOWN) {
             actb = m.ff;
+            hint_wait(P.done + (tag_act - tag0), all_ctas, 0x501u);
             stage_plain5<ACT>(P.act, tag_act, cols, actb, TRACE ? tr : nullptr);
         } else {
             // qkv / gate-up / output stage into e0, wo into the ff region (the attention scratch is dead by then; `down` restages it two
             // CTA barriers later): between two uses of a buffer lies a barrier that every warp reaches only after it is done reading
             actb = kind == OP_WO ? m.ff : m.e0;
             if (tid < 256) {
-                if (kind == OP_WO) stage_att5(P.att, tag_att, cols, actb, TRACE ? tr : nullptr);
-                else { if (tid * 32 < cols) prefetch_l2(op.norm_w + tid * 32); stage_norm5<ACT>(P.x, tag_x, op.norm_w, cols, actb, red, TRACE ? tr : nullptr); }
+                if (kind == OP_WO) { hint_wait(P.done + (tag_att - tag0), all_heads, 0x502u); stage_att5(P.att, tag_att, cols, actb, TRACE ? tr : nullptr); }
+                else {
+                    if (tid * 32 < cols) prefetch_l2(op.norm_w + tid * 32);
+                    hint_wait(P.done + (tag_x - tag0), all_ctas, 0x503u);
+                    stage_norm5<ACT>(P.x, tag_x, op.norm_w, cols, actb, red, TRACE ? tr : nullptr);
+                }
             }
         }
         consumer_sync();
@@ -661,6 +701,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel5(const __gr
             default:        n_base = consume5<Q41, OP_OUTPUT, NBL, TRACE>(P, oi, n_base, pos, tag, actb, tr); break;
         }
         if (TRACE && tr) tr[3] = clock64();
+        if ((tid & 31) == 0) { const unsigned old = atomicAdd(&op_done, 1u); if (old % (unsigned)kConsumerWarps == (unsigned)kConsumerWarps - 1u) hint_post(P.done + oi); }
     }
 }
 

@@ -987,3 +987,38 @@ ORACLE_API int oracle_llama_n_vocab(void *l) { return ((Llama *)l)->n_vocab; }
 ORACLE_API int oracle_llama_n_embd(void *l) { return ((Llama *)l)->n_embd; }
 ORACLE_API int oracle_num_threads(void) { return omp_get_max_threads(); }
 ORACLE_API void oracle_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Host DRAM read bandwidth (bench.py prints it next to the CPU arm: a CPU decode cannot exceed read bandwidth / weight bytes per
+// token).  Streams a buffer much larger than the last-level cache with all threads; returns GB/s of the best pass.
+// ---------------------------------------------------------------------------------------------------------------------------
+ORACLE_API double oracle_host_read_gbs(long long bytes, int n_threads, int passes) {
+    const size_t n = (size_t)bytes / 32;
+    __m256i *buf = (__m256i *)aligned_alloc(64, n * 32);
+    if (!buf) return 0.0;
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; ++i) buf[i] = _mm256_set1_epi32((int)i);  // first touch by the reading thread
+    double best = 0.0; volatile long long sink = 0;
+    for (int p = 0; p < passes; ++p) {
+        const double t0 = omp_get_wtime();
+        long long tot = 0;
+#pragma omp parallel reduction(+ : tot)
+        {
+            __m256i a0 = _mm256_setzero_si256(), a1 = a0, a2 = a0, a3 = a0;
+#pragma omp for schedule(static) nowait
+            for (long long i = 0; i < (long long)(n / 4); ++i) {
+                a0 = _mm256_add_epi64(a0, _mm256_load_si256(buf + 4 * i)); a1 = _mm256_add_epi64(a1, _mm256_load_si256(buf + 4 * i + 1));
+                a2 = _mm256_add_epi64(a2, _mm256_load_si256(buf + 4 * i + 2)); a3 = _mm256_add_epi64(a3, _mm256_load_si256(buf + 4 * i + 3));
+            }
+            const __m256i s = _mm256_add_epi64(_mm256_add_epi64(a0, a1), _mm256_add_epi64(a2, a3));
+            tot += _mm256_extract_epi64(s, 0) + _mm256_extract_epi64(s, 1) + _mm256_extract_epi64(s, 2) + _mm256_extract_epi64(s, 3);
+        }
+        const double dt = omp_get_wtime() - t0;
+        sink += tot;
+        if (dt > 0) best = std::max(best, (double)(n * 32) / dt * 1e-9);
+    }
+    free(buf);
+    return best;
+}
+

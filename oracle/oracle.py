@@ -80,6 +80,7 @@ def lib() -> ctypes.CDLL:
         L.oracle_gelu.argtypes = [vp, vp, i32]
         L.oracle_silu.argtypes = [vp, vp, i32]
         L.oracle_table.argtypes = [i32]
+        L.oracle_host_read_gbs.argtypes = [i64, i32, i32]; L.oracle_host_read_gbs.restype = ctypes.c_double
         L.oracle_table.restype = ctypes.POINTER(ctypes.c_uint16)
         L.oracle_init()
         L.oracle_set_num_threads(usable_cpus())  # default team for the single-op entry points (mul_mat, ...)
