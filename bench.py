@@ -309,7 +309,7 @@ def main():
         # -- device-resident leg: 32-row prefix, then 128 greedy steps chained on the device (no host round trip)
         lib.minigpt4_reset_chat(ctx)
         rows = np.ctypeslib.as_array(emb.data, shape=(emb.n_embeddings,)).reshape(32, -1)
-        tp0 = time.perf_counter(); ext.eval_embd(ctx, rows); prefix_ms = (time.perf_counter() - tp0) * 1e3
+        tp0 = time.perf_counter(); ext.eval_embd(ctx, rows); ext.flush(ctx); prefix_ms = (time.perf_counter() - tp0) * 1e3
         ids, chain_ms = ext.decode_chain(ctx, N_GEN)
         lib.minigpt4_free_embedding(emb)
         return {"enc_dev": enc_dev, "enc_wall": (t_enc - t0) * 1e3, "chain_ms": chain_ms, "turn_s": t_end - t0, "ttft_s": t_first - t0,

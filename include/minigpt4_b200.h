@@ -34,6 +34,9 @@ MINIGPT4_API int minigpt4_b200_n_past(struct MiniGPT4Context *ctx);
 MINIGPT4_API int minigpt4_b200_tokenize(struct MiniGPT4Context *ctx, const char *text, int add_bos, int32_t *out, int max_tokens);
 MINIGPT4_API int minigpt4_b200_eval_tokens(struct MiniGPT4Context *ctx, const int32_t *ids, int n);
 MINIGPT4_API int minigpt4_b200_eval_embd(struct MiniGPT4Context *ctx, const float *rows, int n);
+/* Prompt pieces (minigpt4_begin_chat_image, minigpt4_system_prompt, the two calls above) are queued and evaluated together when the model
+   state is needed (sampling, logits, decode); this evaluates the queue now.  Returns 0 on success. */
+MINIGPT4_API int minigpt4_b200_flush(struct MiniGPT4Context *ctx);
 MINIGPT4_API int minigpt4_b200_get_logits(struct MiniGPT4Context *ctx, float *out_n_vocab);
 MINIGPT4_API int minigpt4_b200_greedy_id(struct MiniGPT4Context *ctx);
 MINIGPT4_API int minigpt4_b200_get_hidden(struct MiniGPT4Context *ctx, float *out, int n_rows);
@@ -53,7 +56,7 @@ struct MiniGPT4B200Stats {
     double last_encode_ms;              /* CUDA-event time of the last encode graph */
     unsigned long long kernel_launches; /* kernels of this library launched so far (both graphs) */
     int n_layer, n_embd, n_ff, n_vocab, n_ctx, tp_rank, tp_world, sm_count;
-    int decode_megakernel;              /* > 0: decode step = one persistent kernel per token (value = kernel generation: 1 or 5); 0: one launch per op (graph) */
+    int decode_megakernel;              /* > 0: decode step = one persistent kernel per token (value = kernel generation); 0: one launch per op (graph) */
     int prefill_gemm;                   /* 1: prompt / prefix rows (N >= 2) run through the tcgen05 kind::i8 prefill GEMM; 0: per-op matvec path */
 };
 MINIGPT4_API int minigpt4_b200_stats(struct MiniGPT4Context *ctx, struct MiniGPT4B200Stats *out);

@@ -142,12 +142,14 @@ int minigpt4_b200_tokenize(struct MiniGPT4Context *ctx, const char *text, int ad
 }
 int minigpt4_b200_eval_tokens(struct MiniGPT4Context *ctx, const int32_t *ids, int n) { return E(ctx)->add_tokens(std::vector<int32_t>(ids, ids + n)); }
 int minigpt4_b200_eval_embd(struct MiniGPT4Context *ctx, const float *rows, int n) { return E(ctx)->add_embedding(rows, n); }
-int minigpt4_b200_get_logits(struct MiniGPT4Context *ctx, float *out) { E(ctx)->llm().logits_to_host(out); return 0; }
-int minigpt4_b200_greedy_id(struct MiniGPT4Context *ctx) { return E(ctx)->llm().argmax(); }
-int minigpt4_b200_get_hidden(struct MiniGPT4Context *ctx, float *out, int n_rows) { E(ctx)->llm().hidden_to_host(out, n_rows); return 0; }
+int minigpt4_b200_flush(struct MiniGPT4Context *ctx) { return E(ctx)->flush() ? 0 : ErrFailedToAddString; }
+int minigpt4_b200_get_logits(struct MiniGPT4Context *ctx, float *out) { E(ctx)->flush(); E(ctx)->llm().logits_to_host(out); return 0; }
+int minigpt4_b200_greedy_id(struct MiniGPT4Context *ctx) { E(ctx)->flush(); return E(ctx)->llm().argmax(); }
+int minigpt4_b200_get_hidden(struct MiniGPT4Context *ctx, float *out, int n_rows) { E(ctx)->flush(); E(ctx)->llm().hidden_to_host(out, n_rows); return 0; }
 const char *minigpt4_b200_token_text(struct MiniGPT4Context *ctx, int32_t id) { return E(ctx)->id_to_token(id); }
 int minigpt4_b200_decode_chain(struct MiniGPT4Context *ctx, int steps, int32_t *ids_out, float *ms_out) {
     Engine *e = E(ctx);
+    if (!e->flush()) return ErrFailedToAddString;
     const float ms = e->llm().decode_chain(steps, e->n_past(), ids_out);
     if (ms < 0) return ErrFailedToAddString;
     e->advance(steps);
@@ -181,7 +183,7 @@ int minigpt4_b200_stats(struct MiniGPT4Context *ctx, struct MiniGPT4B200Stats *o
 int minigpt4_b200_time_matvec(struct MiniGPT4Context *ctx, int kind, int reps, float *avg_ms, double *bytes_per_launch) {
     *avg_ms = E(ctx)->llm().time_matvec(kind, reps, bytes_per_launch); return 0;
 }
-int minigpt4_b200_mega_trace(struct MiniGPT4Context *ctx, long long *out, int max_values) { return E(ctx)->llm().mega_trace(out, max_values); }
+int minigpt4_b200_mega_trace(struct MiniGPT4Context *ctx, long long *out, int max_values) { E(ctx)->flush(); return E(ctx)->llm().mega_trace(out, max_values); }
 int minigpt4_b200_op_matvec(int ggml_type, int rows, int cols, const void *w_blocks, const float *x, int n, float *y) {
     LlamaDevice::test_matvec(ggml_type, rows, cols, w_blocks, x, n, y); return 0;
 }

@@ -2,6 +2,7 @@
 #include "engine.h"
 #include "../../include/minigpt4.h"
 #include <string.h>
+#include <algorithm>
 
 namespace mg4 {
 
@@ -60,27 +61,68 @@ Error Engine::encode_image(const ::MiniGPT4Image *image, ::MiniGPT4Embedding *ou
     return ErrNone;
 }
 
-// add_tokens (minigpt4.cpp:2365-2382): the reference chunks by n_batch; results are batch invariant, so the device
-// path uses its own chunking.  A single token goes through the captured decode graph.
+// add_tokens (minigpt4.cpp:2365-2382) / add_embedding (:2399-2415).  The reference evaluates every piece of a chat turn separately
+// (system prompt, "Human: <Img>", the 32 image rows, "</Img> ", the question, "### Assistant:" = six passes over the weights).  Results are
+// batch invariant (every row is quantised and reduced on its own), so the pieces are only QUEUED here and evaluated together - one pass over
+// the weights per LlamaDevice::kPrefillMax rows - when something needs the model state (sampling, logits, a decode step, the hidden state).
+// Validation happens at queue time, so the error codes of the reference's call sites are unchanged.  A single token on an empty queue is
+// the decode loop: it goes straight through the captured decode graph.
 Error Engine::add_tokens(const std::vector<int32_t> &tokens) {
     if (tokens.empty()) return ErrNone;
-    bool ok;
-    if (tokens.size() == 1) { ok = llm_->decode_step(tokens[0], n_past_); if (ok) llm_->sync(); }
-    else ok = llm_->eval_tokens(tokens.data(), (int)tokens.size(), n_past_);
+    const int n = (int)tokens.size(), n_vocab = llm_->dims().n_vocab;
+    bool ok = n_past_ + n <= llm_->dims().n_ctx;
+    if (!ok) MG4_ERR("context overflow: %d + %d > n_ctx %d", n_past_, n, llm_->dims().n_ctx);
+    for (int i = 0; ok && i < n; ++i) if (tokens[(size_t)i] < 0 || tokens[(size_t)i] >= n_vocab) { MG4_ERR("token id %d out of range", tokens[(size_t)i]); ok = false; }
+    if (ok) {
+        if (n == 1 && pend_ids_.empty()) ok = llm_->decode_step(tokens[0], n_past_);   // asynchronous: the next sample / flush synchronises
+        else if (!llm_->rows_mergeable()) ok = flush() && llm_->eval_tokens(tokens.data(), n, n_past_);
+        else {
+            for (int i = 0; ok && i < n; i += kMaxPending) {   // a queue never exceeds kMaxPending rows
+                const int c = std::min(kMaxPending, n - i);
+                if ((int)pend_ids_.size() + c > kMaxPending) ok = flush();
+                if (pend_ids_.empty()) pend_base_ = n_past_ + i;
+                pend_ids_.insert(pend_ids_.end(), tokens.begin() + i, tokens.begin() + i + c);
+            }
+        }
+    }
     if (!ok) { MG4_ERR("Failed to add string"); return ErrFailedToAddString; }
-    n_past_ += (int)tokens.size();
+    n_past_ += n;
     return ErrNone;
 }
 // add_strings (minigpt4.cpp:2384-2397): add_bos is ALWAYS true
 Error Engine::add_strings(const char *s) { return add_tokens(tok_.encode(s ? s : "", true)); }
 
 Error Engine::add_embedding(const float *rows, int n_rows) {
-    if (!llm_->eval_embd(rows, n_rows, n_past_)) { MG4_ERR("Failed to add embedding"); return ErrFailedToAddEmbedding; }
+    if (n_rows <= 0) return ErrNone;
+    const size_t E = (size_t)llm_->dims().n_embd;
+    bool ok = n_rows <= kMaxPending && n_past_ + n_rows <= llm_->dims().n_ctx;
+    if (ok) {
+        if (!llm_->rows_mergeable()) ok = flush() && llm_->eval_embd(rows, n_rows, n_past_);
+        else {
+            if ((int)pend_ids_.size() + n_rows > kMaxPending) ok = flush();
+            if (ok) {
+                if (pend_ids_.empty()) pend_base_ = n_past_;
+                const int k0 = (int)(pend_emb_.size() / E);
+                for (int i = 0; i < n_rows; ++i) pend_ids_.push_back(-1 - (k0 + i));
+                pend_emb_.insert(pend_emb_.end(), rows, rows + (size_t)n_rows * E);
+            }
+        }
+    }
+    if (!ok) { MG4_ERR("Failed to add embedding"); return ErrFailedToAddEmbedding; }
     n_past_ += n_rows;
     return ErrNone;
 }
+// evaluate the queued rows (no-op when the queue is empty)
+bool Engine::flush() {
+    if (pend_ids_.empty()) return true;
+    const bool ok = llm_->eval_rows(pend_ids_.data(), (int)pend_ids_.size(), pend_emb_.data(), (int)(pend_emb_.size() / (size_t)llm_->dims().n_embd), pend_base_);
+    pend_ids_.clear(); pend_emb_.clear();
+    if (!ok) MG4_ERR("deferred evaluation of the queued prompt rows failed");
+    return ok;
+}
 
 int32_t Engine::sample_token(const SamplingParams &p) {
+    flush();
     if (p.temp <= 0) return llm_->argmax();  // greedy: arg-max was computed on device with the logits
     llm_->logits_to_host(logits_.data());
     return sampler_->sample(logits_.data(), (int)logits_.size(), p);

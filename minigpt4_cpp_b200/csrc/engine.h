@@ -27,7 +27,9 @@ public:
     Error add_embedding(const float *rows, int n_rows);
     int32_t sample_token(const SamplingParams &p);
     const char *id_to_token(int32_t id) const;
-    void reset() { n_past_ = 0; }
+    void reset() { n_past_ = 0; pend_ids_.clear(); pend_emb_.clear(); }
+    bool flush();                     // evaluate the queued prompt rows (see add_tokens)
+    static constexpr int kMaxPending = LlamaDevice::kPrefillMax;
 
     bool has_vision() const { return (bool)vis_; }
     VisionDevice *vision() { return vis_.get(); }
@@ -46,6 +48,9 @@ private:
     std::unique_ptr<Sampler> sampler_;
     std::vector<float> logits_;
     int n_past_ = 0;
+    std::vector<int32_t> pend_ids_;   // queued rows: token id, or -1 - k for row k of pend_emb_
+    std::vector<float> pend_emb_;
+    int pend_base_ = 0;               // position of the first queued row
     int n_batch_ = 512;
 };
 

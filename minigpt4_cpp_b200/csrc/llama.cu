@@ -1,8 +1,7 @@
 // llama.cu — host side of the device-resident LLaMA step (see llama.h, llama_kernels.cuh).
 #include "llama_kernels.cuh"
 #include "llama_mega.cuh"
-#include "llama_mega_ll.cuh"
-#include "llama_mega5.cuh"
+#include "llama_mega6.cuh"
 #include "llama_prefill.cuh"
 #include "tp.h"
 #include <stdlib.h>
@@ -157,10 +156,7 @@ LlamaDevice::~LlamaDevice() {
     if (mega_barrier_) cudaFree(mega_barrier_);
     if (mega_trace_) cudaFree(mega_trace_);
     delete (mk::MegaParams *)mega_params_;
-    delete (mk::MegaParamsLL *)mega_params_ll_;
-    delete (mk5::Params *)mega5_params_;
-    if (mega5_ops_) cudaFree(mega5_ops_);
-    if (mega_ll_buf_) cudaFree(mega_ll_buf_);
+    delete (mk6::Params6 *)mega6_params_;
     if (h_state_) cudaFreeHost(h_state_);
     if (h_argmax_) cudaFreeHost(h_argmax_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -350,25 +346,42 @@ void LlamaDevice::run_chunk(int n, bool want_logits, bool from_tokens) {
     CUDA_CHECK(cudaStreamSynchronize(stream_));  // h_state_ is rewritten by the next chunk
 }
 
-bool LlamaDevice::eval_tokens(const int32_t *ids, int n, int n_past) {
+// One or more passes over `n` mixed rows starting at position n_past: ids[i] >= 0 is a token, ids[i] < 0 is row -1 - ids[i] of emb_host
+// (n_emb rows of n_embd floats).  The engine collects consecutive add_tokens / add_embedding calls of a chat turn (reference call sites
+// minigpt4.cpp:2365-2382 and :2399-2415 evaluate each piece separately; results are batch invariant) and evaluates them together, so the
+// weights stream once per kPrefillMax rows instead of once per piece.
+bool LlamaDevice::rows_mergeable() const {
+    return tok_type_ == GG_F32 || tok_type_ == GG_F16 || tok_type_ == GG_Q4_0 || tok_type_ == GG_Q4_1 || tok_type_ == GG_Q5_K || tok_type_ == GG_Q6_K;
+}
+bool LlamaDevice::eval_rows(const int32_t *ids, int n, const float *emb_host, int n_emb, int n_past) {
     if (n <= 0) return true;
     if (n_past + n > d_.n_ctx) { MG4_ERR("context overflow: %d + %d > n_ctx %d", n_past, n, d_.n_ctx); return false; }
-    for (int i = 0; i < n; ++i) if (ids[i] < 0 || ids[i] >= d_.n_vocab) { MG4_ERR("token id %d out of range", ids[i]); return false; }
-    if (pf_ready_ && n >= 2) {   // tensor-core prefill: up to kPrefillMax rows per pass over the weights (reference: n_batch chunks, minigpt4.cpp:2369-2379)
-        for (int i = 0; i < n; i += kPrefillMax) {
-            const int c = std::min(kPrefillMax, n - i);
-            h_state_->n_past = n_past + i; h_state_->n_tok = c;
-            CUDA_CHECK(cudaStreamSynchronize(stream_));  // (h_state_ / the pinned id staging of the previous pass have been consumed)
-            CUDA_CHECK(cudaMemcpyAsync(state_, h_state_, offsetof(DeviceState, argmax_key), cudaMemcpyHostToDevice, stream_));
-            CUDA_CHECK(cudaMemcpyAsync(tok_ids_, ids + i, (size_t)c * 4, cudaMemcpyHostToDevice, stream_));
-            embed_ids_kernel<<<c, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, tok_ids_, x_);
-            ++launches_;
-            prefill_chunk(c, i + c == n);
-        }
-        CUDA_CHECK(cudaStreamSynchronize(stream_));
-        return true;
+    if (n_emb > 512) { MG4_ERR("eval_rows: at most 512 embedding rows per call"); return false; }
+    for (int i = 0; i < n; ++i) if (ids[i] >= d_.n_vocab || ids[i] < -n_emb) { MG4_ERR("token id %d out of range", ids[i]); return false; }
+    if (n_emb > 0) CUDA_CHECK(cudaMemcpyAsync(embd_in_, emb_host, (size_t)n_emb * d_.n_embd * 4, cudaMemcpyHostToDevice, stream_));
+    const int step = pf_ready_ ? kPrefillMax : 8;
+    for (int i = 0; i < n; i += step) {
+        const int c = std::min(step, n - i);
+        const bool last = i + c == n;
+        CUDA_CHECK(cudaStreamSynchronize(stream_));  // h_state_ (pinned) of the previous pass / decode step has been consumed
+        h_state_->n_past = n_past + i; h_state_->n_tok = c;
+        for (int j = 0; j < std::min(c, 8); ++j) h_state_->tokens[j] = ids[i + j] >= 0 ? ids[i + j] : 0;
+        CUDA_CHECK(cudaMemcpyAsync(state_, h_state_, offsetof(DeviceState, argmax_key), cudaMemcpyHostToDevice, stream_));
+        CUDA_CHECK(cudaMemcpyAsync(tok_ids_, ids + i, (size_t)c * 4, cudaMemcpyHostToDevice, stream_));
+        embed_rows_kernel<<<c, 256, 0, stream_>>>(tok_type_, (const unsigned char *)tok_raw_, gg_row_bytes(tok_type_, (size_t)d_.n_embd), d_.n_embd, tok_ids_, embd_in_, x_);
+        ++launches_;
+        if (pf_ready_ && c >= 2) prefill_chunk(c, last);
+        else launch_layers(nt_for(c), c, last);
     }
-    for (int i = 0; i < n; i += 8) {
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return true;
+}
+bool LlamaDevice::eval_tokens(const int32_t *ids, int n, int n_past) {
+    if (n <= 0) return true;
+    if (rows_mergeable()) return eval_rows(ids, n, nullptr, 0, n_past);
+    if (n_past + n > d_.n_ctx) { MG4_ERR("context overflow: %d + %d > n_ctx %d", n_past, n, d_.n_ctx); return false; }
+    for (int i = 0; i < n; ++i) if (ids[i] < 0 || ids[i] >= d_.n_vocab) { MG4_ERR("token id %d out of range", ids[i]); return false; }
+    for (int i = 0; i < n; i += 8) {   // token-embedding types outside dequant_elem (experimental block types): per-op path, 8 rows per pass
         const int c = std::min(8, n - i);
         h_state_->n_past = n_past + i; h_state_->n_tok = c;
         for (int j = 0; j < c; ++j) h_state_->tokens[j] = ids[i + j];
@@ -376,49 +389,37 @@ bool LlamaDevice::eval_tokens(const int32_t *ids, int n, int n_past) {
     }
     return true;
 }
-bool LlamaDevice::eval_embd_device(const float *rows_dev, int n, int n_past) {
-    if (n <= 0) return true;
-    if (n_past + n > d_.n_ctx) { MG4_ERR("context overflow: %d + %d > n_ctx %d", n_past, n, d_.n_ctx); return false; }
-    if (pf_ready_ && n >= 2) {   // e.g. the 32 image-embedding rows in ONE batch (reference add_embedding, minigpt4.cpp:2405-2412)
-        for (int i = 0; i < n; i += kPrefillMax) {
-            const int c = std::min(kPrefillMax, n - i);
-            h_state_->n_past = n_past + i; h_state_->n_tok = c;
-            CUDA_CHECK(cudaStreamSynchronize(stream_));
-            CUDA_CHECK(cudaMemcpyAsync(state_, h_state_, offsetof(DeviceState, argmax_key), cudaMemcpyHostToDevice, stream_));
-            CUDA_CHECK(cudaMemcpyAsync(x_, rows_dev + (size_t)i * d_.n_embd, (size_t)c * d_.n_embd * 4, cudaMemcpyDeviceToDevice, stream_));
-            prefill_chunk(c, i + c == n);
-        }
-        CUDA_CHECK(cudaStreamSynchronize(stream_));
-        return true;
-    }
-    for (int i = 0; i < n; i += 8) {
-        const int c = std::min(8, n - i);
-        h_state_->n_past = n_past + i; h_state_->n_tok = c;
-        CUDA_CHECK(cudaMemcpyAsync(x_, rows_dev + (size_t)i * d_.n_embd, (size_t)c * d_.n_embd * 4, cudaMemcpyDeviceToDevice, stream_));
-        run_chunk(c, i + c == n, false);
-    }
-    return true;
-}
 bool LlamaDevice::eval_embd(const float *rows_host, int n, int n_past) {
     if (n <= 0) return true;
     if (n > 512) { MG4_ERR("eval_embd: at most 512 rows per call"); return false; }
+    if (n_past + n > d_.n_ctx) { MG4_ERR("context overflow: %d + %d > n_ctx %d", n_past, n, d_.n_ctx); return false; }
+    if (rows_mergeable()) {
+        std::vector<int32_t> ids((size_t)n);
+        for (int i = 0; i < n; ++i) ids[(size_t)i] = -1 - i;
+        return eval_rows(ids.data(), n, rows_host, n, n_past);
+    }
     CUDA_CHECK(cudaMemcpyAsync(embd_in_, rows_host, (size_t)n * d_.n_embd * 4, cudaMemcpyHostToDevice, stream_));
-    return eval_embd_device(embd_in_, n, n_past);
+    for (int i = 0; i < n; i += 8) {
+        const int c = std::min(8, n - i);
+        h_state_->n_past = n_past + i; h_state_->n_tok = c;
+        CUDA_CHECK(cudaMemcpyAsync(x_, embd_in_ + (size_t)i * d_.n_embd, (size_t)c * d_.n_embd * 4, cudaMemcpyDeviceToDevice, stream_));
+        run_chunk(c, i + c == n, false);
+    }
+    return true;
 }
 void LlamaDevice::logits_to_host(float *dst) {
     CUDA_CHECK(cudaMemcpyAsync(dst, logits_, (size_t)d_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 void LlamaDevice::sync_decode() {
-    const cudaError_t e = cudaStreamSynchronize(stream_);
-    if (e != cudaSuccess && mega_gen_ == 5) fprintf(stderr, "[minigpt4-b200][fatal] decode megakernel stopped; spin-guard reason code 0x%x (0 = not a guard trap)\n", (unsigned)h_argmax_[4]);
-    CUDA_CHECK(e);
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    h_state_busy_ = false;
 }
 int32_t LlamaDevice::argmax() {
     sync_decode();
     return *h_argmax_;
 }
-void LlamaDevice::sync() { CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+void LlamaDevice::sync() { CUDA_CHECK(cudaStreamSynchronize(stream_)); h_state_busy_ = false; }
 void LlamaDevice::hidden_to_host(float *dst, int n) {
     CUDA_CHECK(cudaMemcpyAsync(dst, x_, (size_t)n * d_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -544,38 +545,112 @@ void LlamaDevice::prefill_chunk(int n, bool want_logits) {
 // positions and the token come from *state_, so the same graph serves every step
 // ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
-// persistent megakernel program (llama_mega.cuh)
+// persistent megakernel program (llama_mega6.cuh; generation 4 = llama_mega.cuh kept for A/B runs behind MINIGPT4_B200_MEGA_GEN=4)
 // ------------------------------------------------------------------------------------------------
 bool LlamaDevice::build_mega() {
-    using namespace mk;
     if (getenv("MINIGPT4_B200_NO_MEGAKERNEL")) return false;
     if (tp_ && tp_->world > 1) return false;
     const int wt = output_.type;
     if (wt != GG_Q4_0 && wt != GG_Q4_1) return false;
     for (auto &L : layers_) if (!L.fused_qkv || L.qkv.type != wt || L.wo.type != wt || L.w13.type != wt || L.w2.type != wt) return false;
-    if (d_.n_embd % 256 || d_.n_ff % 256 || d_.n_embd > 1024 * mk::kNormItems || d_.n_ff > 4 * mk::kConsumerThreads * mk::kPlainItems) return false;
+    if (d_.n_embd % 256 || d_.n_ff % 256 || d_.n_embd > 1024 * mk6::kNormItems || d_.n_ff > 4 * mk6::kConsumerThreads * mk6::kPlainItems) return false;
+    if (d_.head_dim != 128 || d_.n_head > sm_count_ || 5 * d_.n_layer + 3 > mk6::kMaxOps) return false;
     int coop = 0, dev = 0; CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     if (!coop) return false;
+    mega_type_ = wt;
+    CUDA_CHECK(cudaMalloc((void **)&mega_barrier_, 64)); CUDA_CHECK(cudaMemset(mega_barrier_, 0, 64));
+    mega_n_ops_ = 5 * d_.n_layer + 3;
+    if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, (size_t)(mega_n_ops_ + 1) * 32 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, (size_t)(mega_n_ops_ + 1) * 32 * sizeof(long long))); }
+    mega_gen_ = getenv("MINIGPT4_B200_MEGA_GEN") && atoi(getenv("MINIGPT4_B200_MEGA_GEN")) == 4 ? 4 : 6;
+    const bool ok = mega_gen_ == 4 ? build_mega4() : build_mega6();
+    if (!ok) return false;
+    const void *fn = mega_fn();
+    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_));
+    int occ = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, mk6::kThreads, mega_smem_));
+    if (occ < 1) { MG4_ERR("megakernel does not fit on an SM (smem %zu)", mega_smem_); return false; }
+    return true;
+}
+
+// generation 6: self-refilled per-warp streams (llama_mega6.cuh)
+bool LlamaDevice::build_mega6() {
+    using namespace mk6;
+    const int E = d_.n_embd, FF = d_.n_ff;
+    size_t act_b = std::max(act6_bytes(FF), act6_bytes(E));
+    act_b = std::max(act_b, (size_t)d_.n_ctx * 6);  // the attention op (which stages no activations) uses the region as its scratch
+    act_b = (act_b + 127) & ~(size_t)127;
+    const int rb_e = layers_[0].qkv.row_bytes, rb_ff = layers_[0].w2.row_bytes;
+    // a slot holds a row pair of an n_embd-wide matrix or ONE row of an n_ff-wide matrix (whose pair then takes both slots of the warp)
+    int slot = std::max(2 * rb_e, rb_ff);
+    slot = (slot + 15) & ~15;
+    cudaDeviceProp prop; int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    const size_t stat = 10240;  // static shared memory of decode_megakernel6 (red, redf, qh, part) + slack
+    const long long room = (long long)prop.sharedMemPerBlockOptin - (long long)stat - (long long)act_b - 2 * kConsumerWarps * 8;
+    int W = (int)std::min<long long>(kConsumerWarps, room / (2LL * slot));
+    if (getenv("MINIGPT4_B200_MEGA_W")) W = std::min(W, atoi(getenv("MINIGPT4_B200_MEGA_W")));
+    if (W < 4) return false;
+    Params6 *P = new Params6();
+    memset(P, 0, sizeof(Params6));
+    int n = 0; bool uniform = true;   // every layer's matrices have the same shapes (the CTA's share of a kind is computed once)
+    auto add = [&](int kind, int layer, const QMat *m, const float *norm) {
+        Op6 &o = P->ops[n++]; o.kind = kind; o.layer = layer; o.norm_w = norm;
+        if (m) {
+            o.cols = m->cols; o.row_bytes = m->row_bytes; o.w = (const unsigned char *)m->p0;
+            o.parts = 2 * m->row_bytes <= slot ? 1 : 2;
+            o.n_su = m->rows / 2;
+            if (P->n_su_kind[kind] && P->n_su_kind[kind] != o.n_su) uniform = false;
+            P->n_su_kind[kind] = o.n_su;
+        }
+    };
+    add(OP_EMBED, 0, nullptr, nullptr);
+    for (int il = 0; il < d_.n_layer; ++il) {
+        Layer &L = layers_[(size_t)il];
+        add(OP_QKV, il, &L.qkv, L.attn_norm);
+        add(OP_ATTN, il, nullptr, nullptr);
+        add(OP_WO, il, &L.wo, nullptr);
+        add(OP_GATEUP, il, &L.w13, L.ffn_norm);
+        add(OP_DOWN, il, &L.w2, nullptr);
+    }
+    add(OP_OUTPUT, 0, &output_, final_norm_);
+    add(OP_FINAL, 0, nullptr, nullptr);
+    if (!uniform) { delete P; return false; }
+    P->n_ops = n; P->W = W; P->slot_bytes = slot; P->act_bytes = (int)act_b;
+    P->E = E; P->FF = FF; P->n_head = d_.n_head; P->n_ctx = d_.n_ctx; P->n_vocab = d_.n_vocab;
+    P->flags = getenv("MINIGPT4_B200_MEGA_FLAGS") ? atoi(getenv("MINIGPT4_B200_MEGA_FLAGS")) : 1;
+    P->kq_scale = 1.0f / sqrtf((float)d_.n_embd / (float)d_.n_head);
+    P->l2_window = getenv("MINIGPT4_B200_L2_WINDOW") ? atoi(getenv("MINIGPT4_B200_L2_WINDOW")) : 196608;
+    P->E_pow2 = (E & (E - 1)) == 0; P->inv_E = 1.0 / (double)E;
+    P->x = x_; P->q = q_; P->att = att_; P->act = act_; P->logits = logits_; P->kcache = kcache_; P->vcache = vcache_;
+    P->rope = rope_; P->tab_exp = tab_exp_; P->tab_silu = tab_silu_;
+    P->tok = (const unsigned char *)tok_raw_; P->tok_type = tok_type_; P->tok_row_bytes = gg_row_bytes(tok_type_, (size_t)E);
+    P->state = state_; P->barrier = mega_barrier_; P->trace = mega_trace_;
+    mega6_params_ = P;
+    mega6_nbl_ = getenv("MINIGPT4_B200_MEGA_NOREG") ? 0 : E == 4096 ? 4 : E == 5120 ? 5 : 0;
+    mega_smem_ = (size_t)2 * W * slot + act_b + (size_t)2 * W * 8;
+    MG4_INFO("decode megakernel (generation 6): %d ops/token, %d stream warps x 2 slots x %d B, act %zu B, %zu B dynamic shared per CTA, register-resident blocks per lane %d, grid %d",
+             n, W, slot, act_b, mega_smem_, mega6_nbl_, sm_count_);
+    return true;
+}
+
+// generation 4 (llama_mega.cuh): single producer warp + shared ring
+bool LlamaDevice::build_mega4() {
+    using namespace mk;
+    const int wt = mega_type_;
     const int E = d_.n_embd, FF = d_.n_ff;
     const int act = act_of(wt);
     size_t act_b = std::max(act_bytes(act, FF), act_bytes(act, E));
-    act_b = std::max(act_b, (size_t)d_.n_ctx * 6);  // the attention op (which stages no activations) uses the region as its scratch
+    act_b = std::max(act_b, (size_t)d_.n_ctx * 6);
     act_b = (act_b + 127) & ~(size_t)127;
-    const size_t xs_b = 0;
     const int rb_e = layers_[0].qkv.row_bytes, rb_ff = layers_[0].w2.row_bytes;
-    // one ring slot holds a row pair of an n_embd-wide matrix or ONE row of an n_ff-wide matrix (its pair uses two slots)
     int slot = std::max(2 * rb_e, rb_ff);
     slot = (slot + 127) & ~127;
-    cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-    const size_t budget = prop.sharedMemPerBlockOptin - 2048;  // slack
-    const size_t ops_b = (size_t)(5 * d_.n_layer + 3) * sizeof(MegaOp);  // the op program lives in shared memory too
-    const int n_slots = (int)std::min<size_t>(48, (budget - 9216 - act_b - xs_b - ops_b - 1024) / (size_t)slot);  // 9 KB of static shared memory
+    cudaDeviceProp prop; int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    const size_t budget = prop.sharedMemPerBlockOptin - 2048;
+    const size_t ops_b = (size_t)(5 * d_.n_layer + 3) * sizeof(MegaOp);
+    const int n_slots = (int)std::min<long long>(48, ((long long)budget - 9216 - (long long)act_b - (long long)ops_b - 1024) / (long long)slot);
     if (n_slots < 12) return false;
-    const int inflight = getenv("MINIGPT4_B200_INFLIGHT") ? atoi(getenv("MINIGPT4_B200_INFLIGHT")) : 10;  // slots kept free of consumers so that ~bandwidth x latency worth of fills is always in flight
-    // n_ff-wide matrices (down): a CTA's whole share (rows/2/grid row pairs x 2 slots) fits the ring, so every pair can have its own warp and
-    // the op is ONE round of dot products instead of two; the fills behind it come out of L2 (the look-ahead lane keeps running)
-    const int inflight2 = getenv("MINIGPT4_B200_INFLIGHT2") ? atoi(getenv("MINIGPT4_B200_INFLIGHT2")) : 0;
+    const int inflight = 10;
     std::vector<MegaOp> ops;
     auto add = [&](int kind, int layer, const QMat *m, const float *norm) {
         MegaOp o{}; o.kind = kind; o.layer = layer; o.norm_w = norm;
@@ -583,7 +658,7 @@ bool LlamaDevice::build_mega() {
             o.rows = m->rows; o.cols = m->cols; o.row_bytes = m->row_bytes; o.w = (const unsigned char *)m->p0;
             o.sps = 2 * m->row_bytes <= slot ? 1 : 2;
             o.n_su = m->rows / 2;
-            o.n_warps = std::max(1, std::min(kConsumerWarps, (n_slots - (o.sps == 2 ? inflight2 : inflight)) / o.sps));
+            o.n_warps = std::max(1, std::min(kConsumerWarps, (n_slots - (o.sps == 2 ? 0 : inflight)) / o.sps));
         }
         ops.push_back(o);
     };
@@ -600,129 +675,44 @@ bool LlamaDevice::build_mega() {
     add(OP_FINAL, 0, nullptr, nullptr);
     CUDA_CHECK(cudaMalloc(&mega_ops_, ops.size() * sizeof(MegaOp)));
     CUDA_CHECK(cudaMemcpy(mega_ops_, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMalloc((void **)&mega_barrier_, 64)); CUDA_CHECK(cudaMemset(mega_barrier_, 0, 64));
     MegaParams *P = new MegaParams();
     P->ops = (const MegaOp *)mega_ops_; P->n_ops = (int)ops.size();
-    P->n_slots = n_slots; P->slot_bytes = slot; P->act_bytes = (int)act_b; P->xs_bytes = (int)xs_b;
+    P->n_slots = n_slots; P->slot_bytes = slot; P->act_bytes = (int)act_b; P->xs_bytes = 0;
     P->E = E; P->FF = FF; P->n_head = d_.n_head; P->n_ctx = d_.n_ctx; P->n_vocab = d_.n_vocab;
     P->kq_scale = 1.0f / sqrtf((float)d_.n_embd / (float)d_.n_head);
     P->x = x_; P->q = q_; P->att = att_; P->act = act_; P->logits = logits_; P->kcache = kcache_; P->vcache = vcache_;
     P->rope = rope_; P->tab_exp = tab_exp_; P->tab_silu = tab_silu_;
     P->tok = (const unsigned char *)tok_raw_; P->tok_type = tok_type_; P->tok_row_bytes = gg_row_bytes(tok_type_, (size_t)E);
     P->state = state_; P->barrier = mega_barrier_;
-    P->trace = nullptr;
-    // L2 look-ahead lane of the producer warp: OFF by default.  Measured (profiles/r1_v3_summary.md): with the lane on, a 7B token took 1750 us
-    // and read 8.1 GB from DRAM for 4.13 GB of weights (requests landing behind the fill cursor); restricted to requests ahead of the
-    // cursor the traffic was right but the token still took 1750 us, because the lane shares a warp with the fill lane and its polling
-    // delays the fills; with the lane off: 1459 us.  The 28-slot ring alone keeps ~28 MB in flight chip-wide.
-    P->l2_ahead = getenv("MINIGPT4_B200_L2_AHEAD") ? atoi(getenv("MINIGPT4_B200_L2_AHEAD")) : 0;
+    P->trace = mega_trace_;
+    P->l2_ahead = 0;
     P->flags = getenv("MINIGPT4_B200_MEGA_FLAGS") ? atoi(getenv("MINIGPT4_B200_MEGA_FLAGS")) : 1;
-    if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, (ops.size() + 1) * 16 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, (ops.size() + 1) * 16 * sizeof(long long))); P->trace = mega_trace_; }
-    mega_n_ops_ = (int)ops.size();
     mega_params_ = P;
-    // experimental flag-in-data variant (llama_mega_ll.cuh): the exchanged activation vectors as {value, tag} pairs, one zeroed allocation
-    if (getenv("MINIGPT4_B200_MEGA_LL") && atoi(getenv("MINIGPT4_B200_MEGA_LL")) && ops.size() < 1023 && d_.n_head <= sm_count_) {
-        const size_t nE = (size_t)E, nF = (size_t)FF;
-        const size_t bytes = (3 * nE + nF + nE) * sizeof(LLf) + 256;  // x, q, att | act | kcur + vcur (E/2 each) | seq
-        CUDA_CHECK(cudaMalloc(&mega_ll_buf_, bytes)); CUDA_CHECK(cudaMemset(mega_ll_buf_, 0, bytes));
-        MegaParamsLL *PL = new MegaParamsLL();
-        PL->p = *P;
-        LLf *b = (LLf *)mega_ll_buf_;
-        PL->ll.x = b; PL->ll.q = b + nE; PL->ll.att = b + 2 * nE; PL->ll.act = b + 3 * nE; PL->ll.kcur = b + 3 * nE + nF; PL->ll.vcur = PL->ll.kcur + nE / 2;
-        PL->ll.seq = (unsigned *)(PL->ll.vcur + nE / 2);
-        mega_params_ll_ = PL; mega_ll_ = true;
-        MG4_INFO("decode megakernel: EXPERIMENTAL flag-in-data variant enabled (MINIGPT4_B200_MEGA_LL)");
-    }
-    mega_smem_ = (size_t)n_slots * slot + xs_b + act_b + (size_t)n_slots * 16 + ops.size() * sizeof(MegaOp) + 64;
-    mega_type_ = wt;
-    // generation 5 (llama_mega5.cuh): register-resident activations, flag-in-data exchange, quantised attention output, L2 look-ahead
-    if (getenv("MINIGPT4_B200_MEGA5") && atoi(getenv("MINIGPT4_B200_MEGA5")) && ops.size() < 1023 && d_.n_head <= sm_count_ && E <= 256 * 4 * mk::kNormItems) {
-        using mk5::LLf; using mk5::Op5;
-        const size_t e_b = (mk5::act5_bytes(E) + 127) & ~(size_t)127;
-        size_t ff_b = std::max(mk5::act5_bytes(FF), std::max(mk5::act5_bytes(E), (size_t)d_.n_ctx * 6));
-        ff_b = (ff_b + 127) & ~(size_t)127;
-        const size_t ops_b5 = ops.size() * sizeof(Op5);
-        const size_t fixed = ff_b + e_b + ops_b5 + 64;
-        const size_t stat5 = 10752;  // static shared memory of decode_megakernel5 (red, redf, qs, kcur, vcur, part)
-        const long long room = (long long)budget - (long long)stat5 - (long long)fixed - 1024;
-        // group slots: one bulk copy brings 4 row pairs of an n_embd-wide matrix or 3 rows of the n_ff-wide one (7B: 20 480 / 20 640 B)
-        const int ub_e = 2 * rb_e, ub_f = rb_ff;
-        const int slot5 = (std::max(4 * ub_e, 3 * ub_f) + 127) & ~127;
-        const int n_slots5 = (int)std::min<long long>(48, room / (long long)(slot5 + 24));
-        const int free_slots = getenv("MINIGPT4_B200_INFLIGHT") ? atoi(getenv("MINIGPT4_B200_INFLIGHT")) : 4;  // slots kept free of consumers: the fills in flight
-        if (n_slots5 >= 5) {
-            std::vector<Op5> ops5; int upg_max = 1;
-            for (auto &o : ops) {
-                Op5 q{}; q.kind = (unsigned char)o.kind; q.layer = (unsigned short)o.layer; q.cols = o.cols; q.row_bytes = (unsigned short)o.row_bytes;
-                q.w = o.w; q.norm_w = o.norm_w;
-                if (o.w) {
-                    if (o.row_bytes > 65535) return false;
-                    q.rpu = o.kind == OP_DOWN ? 1 : 2;
-                    q.n_su = o.rows / q.rpu;
-                    q.upg = (unsigned char)std::max(1, std::min(15, slot5 / (o.row_bytes * q.rpu)));
-                    q.n_warps = (unsigned char)std::max(1, std::min(kConsumerWarps, std::max(1, n_slots5 - free_slots) * q.upg));
-                    upg_max = std::max(upg_max, (int)q.upg);
-                }
-                ops5.push_back(q);
-            }
-            CUDA_CHECK(cudaMalloc(&mega5_ops_, ops5.size() * sizeof(Op5)));
-            CUDA_CHECK(cudaMemcpy(mega5_ops_, ops5.data(), ops5.size() * sizeof(Op5), cudaMemcpyHostToDevice));
-            const size_t nE = (size_t)E, nF = (size_t)FF, nbE = nE / 32;
-            const size_t n_ll = 2 * nE + nF + nE + nbE * 10;  // x, q | act | kcur + vcur (E/2 each) | att words
-            const size_t bytes = n_ll * sizeof(LLf) + 256 + ops.size() * 4;
-            CUDA_CHECK(cudaMalloc(&mega_ll_buf_, bytes)); CUDA_CHECK(cudaMemset(mega_ll_buf_, 0, bytes));
-            mk5::Params *Q = new mk5::Params();
-            LLf *b = (LLf *)mega_ll_buf_;
-            Q->ops = (const Op5 *)mega5_ops_; Q->n_ops = (int)ops.size();
-            Q->n_slots = n_slots5; Q->slot_bytes = slot5; Q->ff_bytes = (int)ff_b; Q->e_bytes = (int)e_b; Q->upg_max = upg_max;
-            Q->E = E; Q->FF = FF; Q->n_head = d_.n_head; Q->n_ctx = d_.n_ctx; Q->n_vocab = d_.n_vocab; Q->kq_scale = P->kq_scale;
-            Q->x = b; Q->q = b + nE; Q->act = b + 2 * nE; Q->kcur = b + 2 * nE + nF; Q->vcur = Q->kcur + nE / 2; Q->att = Q->vcur + nE / 2;
-            Q->seq = (unsigned *)(Q->att + nbE * 10);
-            Q->done = Q->seq + 64;                                  // [n_ops] completion-hint counters (zeroed with the buffer)
-            h_argmax_[4] = 0; Q->dbg = (volatile unsigned *)(h_argmax_ + 4);   // pinned host word (unified addressing): trap reason
-            Q->logits = logits_; Q->kcache = kcache_; Q->vcache = vcache_; Q->rope = rope_; Q->tab_exp = tab_exp_; Q->tab_silu = tab_silu_;
-            Q->tok = P->tok; Q->tok_type = P->tok_type; Q->tok_row_bytes = P->tok_row_bytes; Q->state = state_; Q->barrier = mega_barrier_;
-            Q->flags = P->flags; Q->trace = P->trace;
-            mega5_params_ = Q; mega_gen_ = 5; mega_ll_ = false;
-            mega5_nbl_ = (E == 4096 && !getenv("MINIGPT4_B200_MEGA5_NOREG")) ? 4 : (E == 5120 && !getenv("MINIGPT4_B200_MEGA5_NOREG")) ? 5 : 0;
-            mega_smem_ = (size_t)n_slots5 * slot5 + fixed + (size_t)n_slots5 * 24;
-            MG4_INFO("decode megakernel generation 5: ring %d x %d B (up to %d units per copy), act buffers %zu + %zu B, register-resident blocks per lane %d, flags %d",
-                     n_slots5, slot5, upg_max, ff_b, e_b, mega5_nbl_, Q->flags);
-        }
-    }
-    mega_stk_ = (std::max(E, FF) + 2047) / 2048;
-    const void *fn = mega_fn();
-    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_));
-    int occ = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kMegaThreads, mega_smem_));
-    if (occ < 1) { MG4_ERR("megakernel does not fit on an SM (smem %zu)", mega_smem_); return false; }
-    MG4_INFO("decode megakernel: %d ops/token, ring %d x %d B, xs %zu B, act %zu B, %zu B shared per CTA, grid %d", (int)ops.size(), n_slots, slot, xs_b, act_b, mega_smem_, sm_count_);
+    mega_smem_ = (size_t)n_slots * slot + act_b + (size_t)n_slots * 16 + ops.size() * sizeof(MegaOp) + 64;
+    MG4_INFO("decode megakernel (generation 4): %d ops/token, ring %d x %d B, act %zu B, %zu B shared per CTA, grid %d", (int)ops.size(), n_slots, slot, act_b, mega_smem_, sm_count_);
     return true;
 }
 const void *LlamaDevice::mega_fn() const {
-    using namespace mk;
-    if (mega_gen_ == 5) {
-        using namespace mk5;
-        const bool t = mega_trace_ != nullptr, q41 = mega_type_ == GG_Q4_1;
-#define MG4_M5(NBL) (q41 ? (t ? (const void *)decode_megakernel5<GG_Q4_1, NBL, true> : (const void *)decode_megakernel5<GG_Q4_1, NBL, false>) \
-                         : (t ? (const void *)decode_megakernel5<GG_Q4_0, NBL, true> : (const void *)decode_megakernel5<GG_Q4_0, NBL, false>))
-        return mega5_nbl_ == 4 ? MG4_M5(4) : mega5_nbl_ == 5 ? MG4_M5(5) : MG4_M5(0);
-#undef MG4_M5
+    const bool t = mega_trace_ != nullptr, q41 = mega_type_ == GG_Q4_1;
+    if (mega_gen_ == 4) {
+        using namespace mk;
+        if (t) return q41 ? (const void *)decode_megakernel<GG_Q4_1, true> : (const void *)decode_megakernel<GG_Q4_0, true>;
+        return q41 ? (const void *)decode_megakernel<GG_Q4_1, false> : (const void *)decode_megakernel<GG_Q4_0, false>;
     }
-    if (mega_ll_ && mega_trace_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel_ll<GG_Q4_1, true> : (const void *)decode_megakernel_ll<GG_Q4_0, true>;
-    if (mega_ll_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel_ll<GG_Q4_1, false> : (const void *)decode_megakernel_ll<GG_Q4_0, false>;
-    if (mega_trace_) return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1, true> : (const void *)decode_megakernel<GG_Q4_0, true>;
-    return mega_type_ == GG_Q4_1 ? (const void *)decode_megakernel<GG_Q4_1, false> : (const void *)decode_megakernel<GG_Q4_0, false>;
+    using namespace mk6;
+#define MG4_M6(NBL) (q41 ? (t ? (const void *)decode_megakernel6<GG_Q4_1, NBL, true> : (const void *)decode_megakernel6<GG_Q4_1, NBL, false>) \
+                         : (t ? (const void *)decode_megakernel6<GG_Q4_0, NBL, true> : (const void *)decode_megakernel6<GG_Q4_0, NBL, false>))
+    return mega6_nbl_ == 4 ? MG4_M6(4) : mega6_nbl_ == 5 ? MG4_M6(5) : MG4_M6(0);
+#undef MG4_M6
 }
 void LlamaDevice::launch_mega() {
-    using namespace mk;
     CUDA_CHECK(cudaMemsetAsync(mega_barrier_, 0, 4, stream_));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)sm_count_); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = mega_smem_; cfg.stream = stream_;
+    cfg.gridDim = dim3((unsigned)sm_count_); cfg.blockDim = dim3(mk6::kThreads); cfg.dynamicSmemBytes = mega_smem_; cfg.stream = stream_;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    void *args[1] = {mega_gen_ == 5 ? mega5_params_ : mega_ll_ ? mega_params_ll_ : mega_params_};
+    void *args[1] = {mega_gen_ == 4 ? mega_params_ : mega6_params_};
     CUDA_CHECK(cudaLaunchKernelExC(&cfg, mega_fn(), args));
     ++launches_;
     CUDA_CHECK(cudaMemcpyAsync(h_argmax_, &state_->argmax_id, 4, cudaMemcpyDeviceToHost, stream_));
@@ -749,8 +739,10 @@ void LlamaDevice::build_graph() {
 bool LlamaDevice::decode_step(int32_t id, int n_past) {
     if (n_past + 1 > d_.n_ctx) { MG4_ERR("context overflow at %d", n_past); return false; }
     if (id >= 0) {
+        if (h_state_busy_) CUDA_CHECK(cudaStreamSynchronize(stream_));  // the previous step's copy out of the pinned state may not have run yet
         h_state_->n_past = n_past; h_state_->n_tok = 1; h_state_->tokens[0] = id;
         CUDA_CHECK(cudaMemcpyAsync(state_, h_state_, offsetof(DeviceState, argmax_key), cudaMemcpyHostToDevice, stream_));
+        h_state_busy_ = true;
     }
     CUDA_CHECK(cudaGraphLaunch(graph_, stream_));
     launches_ += (unsigned long long)graph_kernels_;
@@ -777,7 +769,7 @@ float LlamaDevice::decode_chain(int steps, int n_past, int32_t *ids_out) {
 
 int LlamaDevice::mega_trace(long long *out, int max_values) {
     if (!mega_trace_) return 0;
-    const int n = std::min(max_values, (mega_n_ops_ + (mega_gen_ == 5 ? 1 : 0)) * 16);  // generation 5 appends [2 CTAs][8] producer counters
+    const int n = std::min(max_values, mega_n_ops_ * (mega_gen_ == 4 ? 16 : 32));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaMemcpy(out, mega_trace_, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
     return n;

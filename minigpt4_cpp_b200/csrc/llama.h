@@ -51,7 +51,8 @@ public:
     // on device and the arg-max id is known.  Returns false if the context would overflow.
     bool eval_tokens(const int32_t *ids, int n, int n_past);
     bool eval_embd(const float *rows_host, int n, int n_past);
-    bool eval_embd_device(const float *rows_dev, int n, int n_past);
+    bool eval_rows(const int32_t *ids, int n, const float *emb_host, int n_emb, int n_past);  // mixed token / embedding rows (ids < 0: row -1 - id of emb_host)
+    bool rows_mergeable() const;     // eval_rows supports this file's token-embedding type
     void logits_to_host(float *dst);   // n_vocab floats, synchronous
     int32_t argmax();                  // greedy id of the current logits (already in pinned host memory after a sync)
     void sync();
@@ -60,7 +61,7 @@ public:
     bool uses_megakernel() const { return mega_; }
     bool uses_prefill_gemm() const { return pf_ready_; }
     static constexpr int kPrefillMax = 512;   // rows per prefill pass (the reference's default n_batch)
-    int mega_generation() const { return mega_ ? (mega_gen_ == 5 ? 5 : 1) : 0; }
+    int mega_generation() const { return mega_ ? mega_gen_ : 0; }
     int mega_trace(long long *out, int max_values);  // debug: per-op clock64 stamps of the last megakernel launch (env MINIGPT4_B200_MEGA_TRACE)
     // one decode step through the captured CUDA graph: feeds `id` (or, if id < 0, the on-device arg-max of the
     // previous step), leaves new logits/arg-max on device.
@@ -91,6 +92,8 @@ private:
     void launch_layers(int nt, int ntok, bool want_logits);
     void build_graph();
     bool build_mega();               // persistent one-launch-per-token decode (homogeneous Q4_0/Q4_1, single GPU)
+    bool build_mega6();
+    bool build_mega4();
     void launch_mega();
     const void *mega_fn() const;
     LlamaDims d_{};
@@ -117,8 +120,8 @@ private:
     int graph_kernels_ = 0;
     long long *mega_trace_ = nullptr; int mega_n_ops_ = 0;
     int mega_stk_ = 7;
-    int mega_gen_ = 4; void *mega5_params_ = nullptr; void *mega5_ops_ = nullptr; int mega5_nbl_ = 0;  // generation 5 (llama_mega5.cuh)
-    bool mega_ll_ = false; void *mega_params_ll_ = nullptr; void *mega_ll_buf_ = nullptr;  // experimental flag-in-data variant (llama_mega_ll.cuh)
+    int mega_gen_ = 6; void *mega6_params_ = nullptr; int mega6_nbl_ = 0;  // generation 6 (llama_mega6.cuh)
+    bool h_state_busy_ = false;
     bool mega_ = false; void *mega_ops_ = nullptr; unsigned *mega_barrier_ = nullptr; void *mega_params_ = nullptr; size_t mega_smem_ = 0; int mega_type_ = -1;
     int sm_count_ = 148;
 };

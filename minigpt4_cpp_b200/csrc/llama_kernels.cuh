@@ -806,6 +806,17 @@ __global__ void embed_ids_kernel(int type, const unsigned char *tok, size_t row_
     const unsigned char *row = tok + (size_t)ids[t] * row_bytes;
     for (int i = threadIdx.x; i < E; i += blockDim.x) x[(size_t)t * E + i] = dequant_elem(type, row, i);
 }
+// mixed rows of one prefill pass: ids[t] >= 0 = token (gather + dequantise), ids[t] < 0 = embedding row -1 - ids[t] of `emb` (the 32 image rows)
+__global__ void embed_rows_kernel(int type, const unsigned char *tok, size_t row_bytes, int E, const int *ids, const float *emb, float *x) {
+    const int t = blockIdx.x, id = ids[t];
+    if (id >= 0) {
+        const unsigned char *row = tok + (size_t)id * row_bytes;
+        for (int i = threadIdx.x; i < E; i += blockDim.x) x[(size_t)t * E + i] = dequant_elem(type, row, i);
+    } else {
+        const float *src = emb + (size_t)(-1 - id) * E;
+        for (int i = threadIdx.x; i < E; i += blockDim.x) x[(size_t)t * E + i] = src[i];
+    }
+}
 // Q4_K token-embedding rows (EXPERIMENTAL, with the Q4_K matvec): kept out of dequant_elem so that the kernels which inline it
 // (embed_kernel, the decode megakernel) stay byte-identical to the measured build
 __global__ void embed_q4k_kernel(const unsigned char *tok, size_t row_bytes, int E, const DeviceState *st, float *x) {

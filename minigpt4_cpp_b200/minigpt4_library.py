@@ -207,6 +207,7 @@ _EXT = {
     "minigpt4_b200_tokenize": ([_CTX, _S, _I, _VP, _I], _I),
     "minigpt4_b200_eval_tokens": ([_CTX, _VP, _I], _I),
     "minigpt4_b200_eval_embd": ([_CTX, _VP, _I], _I),
+    "minigpt4_b200_flush": ([_CTX], _I),
     "minigpt4_b200_get_logits": ([_CTX, _VP], _I),
     "minigpt4_b200_greedy_id": ([_CTX], _I),
     "minigpt4_b200_get_hidden": ([_CTX, _VP, _I], _I),
@@ -267,6 +268,10 @@ class B200:
         a = np.ascontiguousarray(rows, np.float32)
         self._chk(self.L.minigpt4_b200_eval_embd(ctx.ptr, _ptr(a), a.shape[0]))
 
+    def flush(self, ctx) -> None:
+        """evaluate the queued prompt rows now (they are otherwise evaluated together when the model state is first needed)"""
+        self._chk(self.L.minigpt4_b200_flush(ctx.ptr))
+
     def logits(self, ctx) -> np.ndarray:
         out = np.empty(self.L.minigpt4_b200_n_vocab(ctx.ptr), np.float32)
         self._chk(self.L.minigpt4_b200_get_logits(ctx.ptr, _ptr(out)))
@@ -295,16 +300,11 @@ class B200:
         return ms.value, nb.value
 
     def mega_trace(self, ctx) -> np.ndarray:
-        """per-op clock stamps [2 CTAs][n_ops][8]; generation 5 appends [2 CTAs][8] producer counters (see mega_trace_producer)"""
-        buf = np.zeros(2 * 401 * 8, np.int64)
+        """per-op clock stamps [2 CTAs][n_ops][16] (generation 4: [8]) of the last megakernel launch (needs MINIGPT4_B200_MEGA_TRACE=1 at load)"""
+        buf = np.zeros(2 * 403 * 16, np.int64)
         n = self.L.minigpt4_b200_mega_trace(ctx.ptr, _ptr(buf), buf.size)
-        self._trace_tail = buf[n - 16:n].reshape(2, 8).copy() if n and self.stats(ctx).decode_megakernel == 5 else None
-        if self._trace_tail is not None: n -= 16
-        return buf[:n].reshape(2, -1, 8) if n else buf[:0]
-
-    def mega_trace_producer(self):
-        """generation 5: per traced CTA {cycles the producer waited for a free ring slot, cycles total, chunks} of the last mega_trace() call"""
-        return getattr(self, "_trace_tail", None)
+        slots = 16 if self.stats(ctx).decode_megakernel >= 6 else 8
+        return buf[:n].reshape(2, -1, slots) if n else buf[:0]
 
     def stats(self, ctx) -> Stats:
         s = Stats()
