@@ -43,7 +43,7 @@ def metric_name(size: str, wtype: str) -> str:
 
 
 def workload(size: str, wtype: str, blocks: int) -> str:
-    return (f"configs[1]: Vicuna-{size} {wtype} decode-only, {N_PREFIX}-row image prefix + {N_GEN} generated tokens; "
+    return (f"configs[{1 if (wtype, N_GEN) == ('q4_1', 128) else 2 if wtype == 'q5_k' else '-'}]: Vicuna-{size} {wtype} decode-only, {N_PREFIX}-row image prefix + {N_GEN} generated tokens; "
             f"plus ViT-g f16 224x224 encode ({blocks} blocks) per step")
 
 
@@ -245,6 +245,7 @@ def main():
     ap.add_argument("--size", default="7b", choices=["7b", "13b"])
     ap.add_argument("--wtype", default="q4_1")
     ap.add_argument("--blocks", type=int, default=39)
+    ap.add_argument("--tokens", type=int, default=128, help="generated tokens per step (BASELINE configs[1]: 128; configs[2]: 256)")
     ap.add_argument("--cpu-tokens", type=int, default=0, help="decode tokens of the CPU legs (default: 32)")
     ap.add_argument("--cpu-encode-every-step", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -252,6 +253,8 @@ def main():
                     help="N>1: 'replicas' = one independent decode stream per GPU, no data-path collective (weak scaling, default); "
                          "'tp' = one stream, LLaMA layers tensor-parallel over the GPUs with an NCCL sum per row-split matmul (strong scaling)")
     args = ap.parse_args()
+    global N_GEN
+    N_GEN = args.tokens
     if args.impl == "reference":
         return run_reference(args)
 
@@ -263,17 +266,24 @@ def main():
     assert ext.L.minigpt4_b200_device_count() > 0, "bench.py needs a CUDA device: the engine has no CPU path"
     ext.L.minigpt4_b200_set_device(local)
     dist = None
+
+    def tp_configure(on: bool):
+        """engine contexts loaded after this call are tensor-parallel over all ranks (NCCL id from rank 0) / single-GPU again"""
+        import torch
+        uid = np.zeros(128, np.uint8)
+        if on:
+            if rank == 0:
+                ext.L.minigpt4_b200_tp_unique_id(uid.ctypes.data_as(ctypes.c_void_p))
+            t = torch.from_numpy(uid).cuda(); dist.broadcast(t, 0); uid = t.cpu().numpy()
+        ext.L.minigpt4_b200_tp_configure(rank if on else 0, world if on else 1, uid.ctypes.data_as(ctypes.c_void_p))
+
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         if args.mode == "tp":
-            uid = np.zeros(128, np.uint8)
-            if rank == 0:
-                ext.L.minigpt4_b200_tp_unique_id(uid.ctypes.data_as(ctypes.c_void_p))
-            t = torch.from_numpy(uid).cuda(); dist.broadcast(t, 0); uid = t.cpu().numpy()
-            ext.L.minigpt4_b200_tp_configure(rank, world, uid.ctypes.data_as(ctypes.c_void_p))
+            tp_configure(True)
     if rank == 0:
         paths = ensure_models(args.size, args.wtype, args.blocks)
     if dist:
@@ -383,6 +393,49 @@ def main():
                     "decode_calls_only": e2e_decode, "ttft_ms": ttft_ms, "prefill_ms": prefill_ms, "prompt_tokens_incl_system": n_prompt},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "engine": {"decode_megakernel_generation": int(st.decode_megakernel), "prefill_gemm": int(getattr(st, "prefill_gemm", 0))}}
+
+    if world > 1:
+        # the tensor-parallel LLaMA step of north_star on the same GPUs (strong scaling: ONE stream over all ranks), measured next to the
+        # replica number: 32-row prefix + N_GEN chained greedy tokens, CUDA events, max over ranks; parity against this rank's own 1-GPU context
+        import torch
+        rows = np.random.default_rng(11).standard_normal((N_PREFIX, st.n_embd)).astype(np.float32)
+        if args.mode == "tp":
+            c1, c_tp = None, ctx
+        else:
+            tp_configure(True)
+            c_tp = ext.llm_load(llm, n_ctx=2048)
+            tp_configure(False)
+            c1 = ctx
+        lib.minigpt4_reset_chat(c_tp)
+        ext.eval_embd(c_tp, rows); lg_tp = ext.logits(c_tp)
+        ids_tp, _ = ext.decode_chain(c_tp, N_GEN)                      # warm-up pass (also the parity ids)
+        tp_ms = []
+        for _ in range(max(1, args.steps)):
+            lib.minigpt4_reset_chat(c_tp)
+            ext.eval_embd(c_tp, rows); ext.flush(c_tp)
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            _, ms = ext.decode_chain(c_tp, N_GEN); tp_ms.append(ms)
+        ar_us, peer = ext.tp_time_allreduce(c_tp, 64)
+        t = torch.tensor([sum(tp_ms), ar_us], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tp_total_ms, ar_us = t.tolist()
+        tp_rec = {"world": world, "value": len(tp_ms) * N_GEN / (tp_total_ms * 1e-3), "unit": "tokens/s", "scaling": "strong",
+                  "ms_per_token": tp_total_ms / (len(tp_ms) * N_GEN),
+                  "collective": ("one-shot peer-memory all-reduce fused with the residual add (CUDA IPC mappings, loads over NVLink; 2 per layer)" if peer
+                                 else "ncclAllReduce + add kernel (2 per layer)"),
+                  "allreduce_us": ar_us, "allreduce_us_per_token": ar_us * 2 * st.n_layer,
+                  "weight_bytes_per_token_per_gpu": ext.stats(c_tp).llm_weight_bytes_per_token}
+        if c1 is not None:   # parity of TP against the 1-GPU engine on identical inputs (float order of the partial sums differs: tolerance, not bits)
+            lib.minigpt4_reset_chat(c1)
+            ext.eval_embd(c1, rows); lg1 = ext.logits(c1)
+            ids1, _ = ext.decode_chain(c1, N_GEN)
+            n_same = 0
+            for a, b in zip(ids_tp.tolist(), ids1.tolist()):
+                if a != b: break
+                n_same += 1
+            tp_rec["parity_vs_1gpu"] = {"logits_rel_err_after_prefix": float(np.abs(lg_tp - lg1).max() / np.abs(lg1).max()), "bar": 1e-2,
+                                        "leading_greedy_ids_equal": n_same, "of": N_GEN}
+            lib.minigpt4_free(c_tp)
+        line["tp"] = tp_rec
 
     if rank == 0 and not args.no_cpu:
         n_cpu = args.cpu_tokens or REF_TOKENS

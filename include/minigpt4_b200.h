@@ -21,6 +21,9 @@ MINIGPT4_API int minigpt4_b200_device_count(void);
 MINIGPT4_API int minigpt4_b200_set_device(int device);                    /* before minigpt4_model_load */
 MINIGPT4_API int minigpt4_b200_tp_unique_id(void *out128);                /* rank 0: NCCL unique id (128 bytes) */
 MINIGPT4_API int minigpt4_b200_tp_configure(int rank, int world, const void *id128); /* applies to later loads */
+/* tensor-parallel contexts: average device time (us) of one all-reduce of a [1, n_embd] partial on the path in use; *peer_path = 1 for the one-shot
+   peer-memory kernel, 0 for ncclAllReduce + add.  Collective: every rank calls it with the same (even) reps. */
+MINIGPT4_API int minigpt4_b200_tp_time_allreduce(struct MiniGPT4Context *ctx, int reps, float *us_out, int *peer_path);
 
 /* language model only (config "decode-only"): path = ggjt v3 file; replaces llama_load_model_from_file +
  * llama_new_context_with_model (reference minigpt4.cpp:1783-1784) */

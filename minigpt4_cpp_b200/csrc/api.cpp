@@ -183,6 +183,12 @@ int minigpt4_b200_stats(struct MiniGPT4Context *ctx, struct MiniGPT4B200Stats *o
 int minigpt4_b200_time_matvec(struct MiniGPT4Context *ctx, int kind, int reps, float *avg_ms, double *bytes_per_launch) {
     *avg_ms = E(ctx)->llm().time_matvec(kind, reps, bytes_per_launch); return 0;
 }
+int minigpt4_b200_tp_time_allreduce(struct MiniGPT4Context *ctx, int reps, float *us_out, int *peer_path) {
+    E(ctx)->flush();
+    *us_out = E(ctx)->llm().time_allreduce(reps);
+    if (peer_path) *peer_path = E(ctx)->llm().tp_peer_path() ? 1 : 0;
+    return 0;
+}
 int minigpt4_b200_mega_trace(struct MiniGPT4Context *ctx, long long *out, int max_values) { E(ctx)->flush(); return E(ctx)->llm().mega_trace(out, max_values); }
 int minigpt4_b200_op_matvec(int ggml_type, int rows, int cols, const void *w_blocks, const float *x, int n, float *y) {
     LlamaDevice::test_matvec(ggml_type, rows, cols, w_blocks, x, n, y); return 0;

@@ -151,7 +151,7 @@ LlamaDevice::~LlamaDevice() {
     for (void *p : {(void *)final_norm_, tok_raw_, (void *)kcache_, (void *)vcache_, (void *)rope_, (void *)tab_exp_, (void *)tab_silu_, (void *)x_, (void *)q_, (void *)att_,
                     (void *)act_, (void *)logits_, (void *)partial_, (void *)qact_, (void *)embd_in_, (void *)state_}) if (p) cudaFree(p);
     for (auto &L : layers_) for (PQMat *m : {&L.pqkv, &L.pwo, &L.pw13, &L.pw2}) { if (m->q) cudaFree(m->q); if (m->sc) cudaFree(m->sc); }
-    for (void *p : {(void *)pf_q8_, pf_sc_, (void *)tok_ids_}) if (p) cudaFree(p);
+    for (void *p : {(void *)pf_q8_, pf_sc_, (void *)tok_ids_, pf_part_}) if (p) cudaFree(p);
     if (mega_ops_) cudaFree(mega_ops_);
     if (mega_barrier_) cudaFree(mega_barrier_);
     if (mega_trace_) cudaFree(mega_trace_);
@@ -268,6 +268,7 @@ bool LlamaDevice::load(const LlamaFile &f, int n_ctx, TPLink *tp) {
     CUDA_CHECK(cudaHostAlloc((void **)&h_state_, sizeof(DeviceState), cudaHostAllocDefault)); memset(h_state_, 0, sizeof(DeviceState));
     CUDA_CHECK(cudaHostAlloc((void **)&h_argmax_, 64, cudaHostAllocDefault)); *h_argmax_ = 0;
     CUDA_CHECK(cudaDeviceSynchronize());
+    if (tp_ && tp_->world > 1) tp_->setup_peers(E, stream_);
     pf_ready_ = build_prefill();
     build_graph();
     MG4_INFO("LLaMA on device: %d layers, n_embd %d, n_ff %d, vocab %d, %.1f MB streamed per token, tp %d/%d", d_.n_layer, E, FF, d_.n_vocab,
@@ -303,7 +304,10 @@ void LlamaDevice::launch_layers(int nt, int ntok, bool want_logits) {
         MatvecArgs b{};
         b.w = L.wo; b.x = att_; b.x_stride = El; b.norm_w = nullptr; b.ntok = ntok; b.n_valid = b.w.rows; b.state = state_; b.tab_silu = tab_silu_; b.staged = qact_;
         if (!tp) { b.epi = EPI_RESID; b.out = x_; b.out_stride = E; b.resid = x_; launch_matvec(b, nt, sm_count_, stream_, &launches_); }
-        else {
+        else if (tp_->peers_ready()) {   // partial -> this rank's exchange buffer; ONE kernel: signal peers, wait, sum all partials + residual out of peer memory
+            b.epi = EPI_PLAIN; b.out = tp_->partial_out(); b.out_stride = E; launch_matvec(b, nt, sm_count_, stream_, &launches_);
+            tp_->all_reduce_resid(x_, x_, (size_t)ntok * E, stream_); ++launches_;
+        } else {
             b.epi = EPI_PLAIN; b.out = partial_; b.out_stride = E; launch_matvec(b, nt, sm_count_, stream_, &launches_);
             tp_->all_reduce_sum(partial_, (size_t)ntok * E, stream_);
             add_kernel<<<(ntok * E + 255) / 256, 256, 0, stream_>>>(x_, partial_, ntok * E); ++launches_;
@@ -315,7 +319,10 @@ void LlamaDevice::launch_layers(int nt, int ntok, bool want_logits) {
         MatvecArgs e{};
         e.w = L.w2; e.x = act_; e.x_stride = FFl; e.norm_w = nullptr; e.ntok = ntok; e.n_valid = e.w.rows; e.state = state_; e.tab_silu = tab_silu_; e.staged = qact_;
         if (!tp) { e.epi = EPI_RESID; e.out = x_; e.out_stride = E; e.resid = x_; launch_matvec(e, nt, sm_count_, stream_, &launches_); }
-        else {
+        else if (tp_->peers_ready()) {   // partial -> this rank's exchange buffer; ONE kernel: signal peers, wait, sum all partials + residual out of peer memory
+            e.epi = EPI_PLAIN; e.out = tp_->partial_out(); e.out_stride = E; launch_matvec(e, nt, sm_count_, stream_, &launches_);
+            tp_->all_reduce_resid(x_, x_, (size_t)ntok * E, stream_); ++launches_;
+        } else {
             e.epi = EPI_PLAIN; e.out = partial_; e.out_stride = E; launch_matvec(e, nt, sm_count_, stream_, &launches_);
             tp_->all_reduce_sum(partial_, (size_t)ntok * E, stream_);
             add_kernel<<<(ntok * E + 255) / 256, 256, 0, stream_>>>(x_, partial_, ntok * E); ++launches_;
@@ -485,6 +492,8 @@ bool LlamaDevice::build_prefill() {
     make_map_u8(pf_tmS_e_, pf_sc_, R, pitch_e / 4, 32, pf::kTok, false);
     make_map_u8(pf_tmB_ff_, pf_q8_, R, pitch_ff, 128, pf::kTok, true);
     make_map_u8(pf_tmS_ff_, pf_sc_, R, pitch_ff / 4, 32, pf::kTok, false);
+    pf_part_bytes_ = (size_t)48 << 20;   // roots of K-split slices: [slice][token][row] {d-tree, m-tree}
+    CUDA_CHECK(cudaMalloc(&pf_part_, pf_part_bytes_));
     const size_t smem = 1024 + (size_t)pf::kStages * pf::kStageBytes + pf::kStackBytes + 256;
     CUDA_CHECK(cudaFuncSetAttribute(pf::prefill_gemm_q4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_CHECK(cudaFuncSetAttribute(pf::prefill_gemm_q4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -510,10 +519,17 @@ void LlamaDevice::prefill_chunk(int n, bool want_logits) {
     auto gemm = [&](const PQMat &p, bool ff_wide, pf::PrefillArgs a) {
         a.rows = p.rows; a.n_tok = n; a.nb = p.nb; a.S = p.S; a.wsc = (const __half2 *)p.sc; a.state = state_; a.tab_silu = tab_silu_;
         const CUtensorMap *tb = (const CUtensorMap *)(ff_wide ? pf_tmB_ff_ : pf_tmB_e_), *ts = (const CUtensorMap *)(ff_wide ? pf_tmS_ff_ : pf_tmS_e_);
-        const dim3 grid((unsigned)(p.rows_pad / pf::kRows), ty);
+        // K split over subtrees of the class butterfly so that matrices with few 128-row tiles (wo / down: 32) still fill the machine
+        const int tiles = p.rows_pad / pf::kRows;
+        int nz = 1;
+        if (!getenv("MINIGPT4_B200_PREFILL_NO_KSPLIT"))
+            while (nz < 8 && tiles * (int)ty * nz * 2 <= sm_count_ && (size_t)(nz * 2) * n * p.rows_pad * sizeof(float2) <= pf_part_bytes_) nz *= 2;
+        a.jr_per_z = 32 / nz; a.partial = (float2 *)pf_part_; a.part_tok = n; a.part_rows = p.rows_pad;
+        const dim3 grid((unsigned)tiles, ty, (unsigned)nz);
         if (p.q41) pf::prefill_gemm_q4<true><<<grid, pf::kThreads, smem, stream_>>>(*(const CUtensorMap *)p.tm, *tb, *ts, a);
         else pf::prefill_gemm_q4<false><<<grid, pf::kThreads, smem, stream_>>>(*(const CUtensorMap *)p.tm, *tb, *ts, a);
         ++launches_;
+        if (nz > 1) { const size_t work = (size_t)n * (p.rows / 2); pf::prefill_combine<<<(unsigned)((work + 255) / 256), 256, 0, stream_>>>(a, nz); ++launches_; }
     };
     for (int il = 0; il < d_.n_layer; ++il) {
         Layer &L = layers_[(size_t)il];
@@ -549,20 +565,22 @@ void LlamaDevice::prefill_chunk(int n, bool want_logits) {
 // ------------------------------------------------------------------------------------------------
 bool LlamaDevice::build_mega() {
     if (getenv("MINIGPT4_B200_NO_MEGAKERNEL")) return false;
-    if (tp_ && tp_->world > 1) return false;
+    const bool tp = tp_ && tp_->world > 1;
+    if (tp && (!tp_->peers_ready() || getenv("MINIGPT4_B200_TP_PER_OP"))) return false;   // the in-kernel all-reduce needs the peer mappings
     const int wt = output_.type;
     if (wt != GG_Q4_0 && wt != GG_Q4_1) return false;
     for (auto &L : layers_) if (!L.fused_qkv || L.qkv.type != wt || L.wo.type != wt || L.w13.type != wt || L.w2.type != wt) return false;
-    if (d_.n_embd % 256 || d_.n_ff % 256 || d_.n_embd > 1024 * mk6::kNormItems || d_.n_ff > 4 * mk6::kConsumerThreads * mk6::kPlainItems) return false;
-    if (d_.head_dim != 128 || d_.n_head > sm_count_ || 5 * d_.n_layer + 3 > mk6::kMaxOps) return false;
+    if (d_.n_embd % 256 || d_.n_ff % 32 || d_.n_embd > 1024 * mk6::kNormItems || d_.n_ff > 4 * mk6::kConsumerThreads * mk6::kPlainItems) return false;
+    if (d_.head_dim != 128 || d_.n_head > sm_count_ || 7 * d_.n_layer + 3 > mk6::kMaxOps) return false;
+    if (tp && (n_embd_local_ % 32 || n_ff_local_ % 32)) return false;
     int coop = 0, dev = 0; CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     if (!coop) return false;
     mega_type_ = wt;
     CUDA_CHECK(cudaMalloc((void **)&mega_barrier_, 64)); CUDA_CHECK(cudaMemset(mega_barrier_, 0, 64));
-    mega_n_ops_ = 5 * d_.n_layer + 3;
+    mega_n_ops_ = (tp ? 7 : 5) * d_.n_layer + 3;
     if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, (size_t)(mega_n_ops_ + 1) * 32 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, (size_t)(mega_n_ops_ + 1) * 32 * sizeof(long long))); }
-    mega_gen_ = getenv("MINIGPT4_B200_MEGA_GEN") && atoi(getenv("MINIGPT4_B200_MEGA_GEN")) == 4 ? 4 : 6;
+    mega_gen_ = !tp && getenv("MINIGPT4_B200_MEGA_GEN") && atoi(getenv("MINIGPT4_B200_MEGA_GEN")) == 4 ? 4 : 6;
     const bool ok = mega_gen_ == 4 ? build_mega4() : build_mega6();
     if (!ok) return false;
     const void *fn = mega_fn();
@@ -576,7 +594,8 @@ bool LlamaDevice::build_mega() {
 // generation 6: self-refilled per-warp streams (llama_mega6.cuh)
 bool LlamaDevice::build_mega6() {
     using namespace mk6;
-    const int E = d_.n_embd, FF = d_.n_ff;
+    const bool tp = tp_ && tp_->world > 1;
+    const int E = d_.n_embd, FF = n_ff_local_;   // (tensor parallel: this rank's feed-forward columns)
     size_t act_b = std::max(act6_bytes(FF), act6_bytes(E));
     act_b = std::max(act_b, (size_t)d_.n_ctx * 6);  // the attention op (which stages no activations) uses the region as its scratch
     act_b = (act_b + 127) & ~(size_t)127;
@@ -599,6 +618,7 @@ bool LlamaDevice::build_mega6() {
             o.cols = m->cols; o.row_bytes = m->row_bytes; o.w = (const unsigned char *)m->p0;
             o.parts = 2 * m->row_bytes <= slot ? 1 : 2;
             o.n_su = m->rows / 2;
+            if ((2 * m->row_bytes / o.parts) % 16) uniform = false;   // every slot-load is a 16-byte aligned, 16-byte multiple bulk copy
             if (P->n_su_kind[kind] && P->n_su_kind[kind] != o.n_su) uniform = false;
             P->n_su_kind[kind] = o.n_su;
         }
@@ -609,17 +629,20 @@ bool LlamaDevice::build_mega6() {
         add(OP_QKV, il, &L.qkv, L.attn_norm);
         add(OP_ATTN, il, nullptr, nullptr);
         add(OP_WO, il, &L.wo, nullptr);
+        if (tp) add(OP_REDUCE, 0, nullptr, nullptr);   // (`layer` = exchange buffer: 0 after wo, 1 after down)
         add(OP_GATEUP, il, &L.w13, L.ffn_norm);
         add(OP_DOWN, il, &L.w2, nullptr);
+        if (tp) add(OP_REDUCE, 1, nullptr, nullptr);
     }
     add(OP_OUTPUT, 0, &output_, final_norm_);
     add(OP_FINAL, 0, nullptr, nullptr);
     if (!uniform) { delete P; return false; }
     P->n_ops = n; P->W = W; P->slot_bytes = slot; P->act_bytes = (int)act_b;
-    P->E = E; P->FF = FF; P->n_head = d_.n_head; P->n_ctx = d_.n_ctx; P->n_vocab = d_.n_vocab;
+    P->E = E; P->FF = FF; P->n_head = n_head_local_; P->n_ctx = d_.n_ctx; P->n_vocab = d_.n_vocab;
+    P->El = n_embd_local_;
+    if (tp) { P->tp = tp_->peers; P->tp_seq = tp_->seq_dev; } else { P->tp.world = 1; P->tp.rank = 0; }
     P->flags = getenv("MINIGPT4_B200_MEGA_FLAGS") ? atoi(getenv("MINIGPT4_B200_MEGA_FLAGS")) : 1;
     P->kq_scale = 1.0f / sqrtf((float)d_.n_embd / (float)d_.n_head);
-    P->l2_window = getenv("MINIGPT4_B200_L2_WINDOW") ? atoi(getenv("MINIGPT4_B200_L2_WINDOW")) : 196608;
     P->E_pow2 = (E & (E - 1)) == 0; P->inv_E = 1.0 / (double)E;
     P->x = x_; P->q = q_; P->att = att_; P->act = act_; P->logits = logits_; P->kcache = kcache_; P->vcache = vcache_;
     P->rope = rope_; P->tab_exp = tab_exp_; P->tab_silu = tab_silu_;
@@ -767,6 +790,25 @@ float LlamaDevice::decode_chain(int steps, int n_past, int32_t *ids_out) {
     return ms;
 }
 
+// measurement seam: average CUDA-event duration (us) of one all-reduce of a [1, n_embd] partial on the tensor-parallel path in use
+// (one-shot peer kernel, or ncclAllReduce + add); every rank must call it with the same reps (even)
+bool LlamaDevice::tp_peer_path() const { return tp_ && tp_->world > 1 && tp_->peers_ready(); }
+float LlamaDevice::time_allreduce(int reps) {
+    if (!tp_ || tp_->world <= 1) return 0.f;
+    reps = std::max(2, reps & ~1);
+    const int E = d_.n_embd;
+    auto one = [&]() {
+        if (tp_->peers_ready()) { CUDA_CHECK(cudaMemsetAsync(tp_->partial_out(), 0, (size_t)E * 4, stream_)); tp_->all_reduce_resid(partial_, partial_, (size_t)E, stream_); }
+        else { tp_->all_reduce_sum(partial_, (size_t)E, stream_); add_kernel<<<(E + 255) / 256, 256, 0, stream_>>>(partial_, partial_, E); }
+    };
+    for (int i = 0; i < 4; ++i) one();
+    CUDA_CHECK(cudaEventRecord(ev0_, stream_));
+    for (int i = 0; i < reps; ++i) one();
+    CUDA_CHECK(cudaEventRecord(ev1_, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    return ms * 1e3f / (float)reps;
+}
 int LlamaDevice::mega_trace(long long *out, int max_values) {
     if (!mega_trace_) return 0;
     const int n = std::min(max_values, mega_n_ops_ * (mega_gen_ == 4 ? 16 : 32));

@@ -71,6 +71,8 @@ public:
     // measurement seam: average CUDA-event duration (ms) of one launch of the decode matvec of `kind`
     // (0 qkv, 1 wo, 2 gate/up, 3 down, 4 output) cycling through all layers so every launch streams cold weights.
     float time_matvec(int kind, int reps, double *bytes_per_launch);
+    float time_allreduce(int reps);   // us per [1, n_embd] all-reduce on the tensor-parallel path in use (0 without tensor parallelism)
+    bool tp_peer_path() const;
     // test taps
     void hidden_to_host(float *dst, int n);  // residual stream after the last evaluated chunk (n rows)
     size_t weight_bytes_per_token() const { return bytes_per_token_; }
@@ -86,7 +88,7 @@ private:
     bool build_prefill();            // tensor-core prefill (llama_prefill.cuh): homogeneous Q4_0 / Q4_1 layers, single GPU
     void prefill_chunk(int n, bool want_logits);   // n <= kPrefillMax rows that sit in x_
     bool pf_ready_ = false; int pf_S_e_ = 0, pf_S_ff_ = 0;
-    signed char *pf_q8_ = nullptr; void *pf_sc_ = nullptr; int32_t *tok_ids_ = nullptr;
+    signed char *pf_q8_ = nullptr; void *pf_sc_ = nullptr; int32_t *tok_ids_ = nullptr; void *pf_part_ = nullptr; size_t pf_part_bytes_ = 0;
     alignas(64) unsigned char pf_tmB_e_[128], pf_tmS_e_[128], pf_tmB_ff_[128], pf_tmS_ff_[128];
     void run_chunk(int n, bool want_logits, bool from_tokens);
     void launch_layers(int nt, int ntok, bool want_logits);

@@ -16,15 +16,20 @@
 //   * per op: [grid barrier -> stage activations (RMSNorm + Q8 quantise) -> per owned row pair: wait slot, dp4a dots, re-arm slot,
 //     warp-shuffle reductions, fused epilogue].  Ops exchange x / q / att / act through L2 (ld.global.cg); a grid barrier (atomic counter)
 //     separates dependent ops.
+//   * NO deeper prefetch than the slots.  A look-ahead warp that asked L2 for the stream beyond the slots while the stream warps were stalled
+//     (cp.async.bulk.prefetch.L2, or cp.async into a scratch line) was measured and removed: 192 KB per CTA changed nothing, 384 KB cost 20 %
+//     (profiles/r2_v6_lookahead_ab.log) - the barrier / staging / attention phases between two matvecs are chains of L2 round trips, and every
+//     byte of weight traffic in flight during them lengthens those round trips.
 // Reduction orders are the canonical ones of llama_kernels.cuh / oracle.cpp: logits are bit-identical to the per-op kernels and the CPU oracle.
 #pragma once
 #include "llama_kernels.cuh"
+#include "tp.h"
 
 namespace mg4 {
 namespace mk6 {
 using namespace k;
 
-enum OpKind : int { OP_EMBED = 0, OP_QKV = 1, OP_ATTN = 2, OP_WO = 3, OP_GATEUP = 4, OP_DOWN = 5, OP_OUTPUT = 6, OP_FINAL = 7 };
+enum OpKind : int { OP_EMBED = 0, OP_QKV = 1, OP_ATTN = 2, OP_WO = 3, OP_GATEUP = 4, OP_DOWN = 5, OP_OUTPUT = 6, OP_FINAL = 7, OP_REDUCE = 8 };
 
 struct Op6 {                 // 48 bytes, lives in the kernel's parameter (constant) space
     int kind, layer, cols, n_su;   // n_su = row pairs (units) of the matrix over the whole grid
@@ -33,14 +38,20 @@ struct Op6 {                 // 48 bytes, lives in the kernel's parameter (const
     const float *norm_w;
     long long pad_;
 };
-constexpr int kMaxOps = 5 * 80 + 3;   // up to 80 layers (parameter space: 32 764 bytes)
+constexpr int kMaxOps = 7 * 80 + 3;   // up to 80 layers, tensor-parallel program (7 ops per layer); parameter space: 32 764 bytes
 
 struct Params6 {
     int n_ops, W, slot_bytes, act_bytes;   // shared memory: [2 W slots][act: staged Q8 activations / attention scratch][2 W mbarriers]
     int n_su_kind[8];                      // row pairs per op kind (all layers have the same shapes): the CTA's share of each is computed once
-    int E, FF, n_head, n_ctx, n_vocab, flags;   // flags bit 0: request the head's K/V history into L2 while the qkv weights are consumed
+    int E, FF, n_head, n_ctx, n_vocab, flags;   // flags bit 0: pull the head's K/V history into L2 while the qkv weights are consumed
+    // tensor parallel (world > 1): this rank holds n_head heads (El = 128 n_head columns of q / att / the KV cache), FF / world columns of the
+    // feed-forward; wo / down write PARTIAL sums into the rank's exchange buffer and an OP_REDUCE op sums the partials of all ranks straight out
+    // of peer memory (NVLink) into x.  The compute and the collective are ONE kernel.
+    int El;            // local q / att / KV row width (== E on one GPU)
+    TPPeers tp;        // peer mappings of the exchange buffers (tp.h); tp.world <= 1: single GPU
+    unsigned *tp_seq;  // all-reduces completed so far by this rank (shared with the per-op path's all-reduce kernel)
+
     float kq_scale;
-    int l2_window;     // look-ahead warp: bytes of this CTA's weight stream that may be asked into L2 beyond the slots while the stream warps are stalled (0 = off)
     int E_pow2;        // n_embd is a power of two: sum / n_embd == sum * (1 / n_embd) exactly
     double inv_E;
     float *x, *q, *att, *act, *logits;
@@ -54,6 +65,7 @@ struct Params6 {
     Op6 ops[kMaxOps];
 };
 static_assert(sizeof(Params6) <= 32764, "kernel parameter space");
+constexpr int kReduceCtas = 16;   // CTAs that pull the peers' partial sums in an OP_REDUCE op (n_embd / 16 elements each)
 
 constexpr int kConsumerWarps = 15, kConsumerThreads = 480, kThreads = 512;
 // named barriers: 1 = the 256 threads of warps 0-7 (activation staging, attention); 2 = all 480 threads of warps 0-14
@@ -326,10 +338,9 @@ __device__ __forceinline__ void fill_seek(const Params6 &P, const int2 *share, F
         return;
     }
 }
-__device__ __forceinline__ void fill_one(const Params6 &P, const Smem6 &m, const int2 *share, Fill &f, int warp, int lane, unsigned *fillb) {
+__device__ __forceinline__ void fill_one(const Params6 &P, const Smem6 &m, const int2 *share, Fill &f, int warp, int lane) {
     if (f.left == 0) return;
     if (lane == 0) {
-        if (P.l2_window > 0) atomicAdd(fillb, f.bytes);   // progress of the CTA's stream, read by the look-ahead warp
         const unsigned j = 2u * (unsigned)warp + (f.cnt & 1u);
         mb_expect_tx(&m.full[j], f.bytes);
         bulk_g2s(m.slots + (size_t)j * P.slot_bytes, f.src, f.bytes, &m.full[j]);
@@ -341,7 +352,7 @@ __device__ __forceinline__ void fill_one(const Params6 &P, const Smem6 &m, const
 // The matvec phase of one op for one stream warp: for each of its row pairs wait for the slot(s), dot, re-arm the slot(s), reduce, epilogue.
 //   cc = slot-loads this warp has consumed so far: load n sits in slot n & 1 and completes phase (n >> 1) & 1 of that slot's barrier.
 template <bool Q41, int KIND, int NBL, bool TRACE>
-__device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const int2 *share, unsigned *fillb, int oi, Fill &f, unsigned &cc, int pos, long long *tr) {
+__device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const int2 *share, int oi, Fill &f, unsigned &cc, int pos, long long *tr) {
     const Op6 &op = P.ops[oi];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int W = P.W;
@@ -350,7 +361,9 @@ __device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const
     const int lo = lh.x, hi = lh.y;
     const int cols = op.cols, nb = cols >> 5, parts = op.parts;
     const unsigned rb = (unsigned)op.row_bytes;
-    constexpr bool REG = NBL > 0 && KIND != OP_DOWN;  // n_embd-wide input held in registers
+    // n_embd-wide RMS-normed inputs (qkv, gate/up, output) are held in registers; wo (8 % of the bytes; El wide under tensor parallelism) and
+    // down read the staged vector from shared memory
+    constexpr bool REG = NBL > 0 && KIND != OP_DOWN && KIND != OP_WO;
     ActRegs<REG ? NBL : 1> ar;
     if (REG) load_act_regs<REG ? NBL : 1>(m.actb, cols, lane, ar);
     unsigned char *const slot0 = m.slots + (size_t)(2 * warp) * P.slot_bytes;
@@ -363,10 +376,10 @@ __device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const
     long long t_wait = 0, t_dot = 0, t_epi = 0; int n_units = 0;
     for (int u = lo + warp; u < hi; u += W) {
         const int r0 = u * 2;
-        // QKV: rows [0, E) = q, [E, 2E) = k, [2E, 3E) = v; rr = row inside the part (head_dim 128: RoPE pair index (rr & 127) / 2)
-        const int partn = KIND == OP_QKV ? (r0 >= P.E) + (r0 >= 2 * P.E) : 0, rr = r0 - partn * P.E;
+        // QKV: rows [0, El) = q, [El, 2 El) = k, [2 El, 3 El) = v (El = this rank's heads); rr = row inside the part (head_dim 128: RoPE pair index (rr & 127) / 2)
+        const int partn = KIND == OP_QKV ? (r0 >= P.El) + (r0 >= 2 * P.El) : 0, rr = r0 - partn * P.El;
         float2 rs = make_float2(0.f, 0.f);  // residual rows of this pair / RoPE (cos, sin) of this pair: fetched before the wait
-        if (KIND == OP_WO || KIND == OP_DOWN) rs = __ldcg((const float2 *)(P.x + r0));
+        if ((KIND == OP_WO || KIND == OP_DOWN) && P.tp.world <= 1) rs = __ldcg((const float2 *)(P.x + r0));
         if (KIND == OP_QKV) { if (partn < 2) rs = __ldg(&P.rope[(size_t)pos * 64 + ((rr & 127) >> 1)]); }
         long long tw0 = 0, tw1 = 0, tw2 = 0;
         if (TRACE && tr) tw0 = clock64();
@@ -386,8 +399,8 @@ __device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const
         float x = hi16 ? a.d1 : a.d0, y = hi16 ? a.m1 : a.m0;
         x += __shfl_xor_sync(0xffffffffu, hi16 ? a.d0 : a.d1, 16);
         y += __shfl_xor_sync(0xffffffffu, hi16 ? a.m0 : a.m1, 16);
-        fill_one(P, m, share, f, warp, lane, fillb);
-        if (parts == 2) fill_one(P, m, share, f, warp, lane, fillb);
+        fill_one(P, m, share, f, warp, lane);
+        if (parts == 2) fill_one(P, m, share, f, warp, lane);
         if (TRACE && tr) { tw2 = clock64(); t_wait += tw1 - tw0; t_dot += tw2 - tw1; ++n_units; }
         float z = hi8 ? y : x;
         z += __shfl_xor_sync(0xffffffffu, hi8 ? x : y, 8);
@@ -398,7 +411,7 @@ __device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const
         const float v1 = __shfl_xor_sync(0xffffffffu, v, 16), v0 = v;
         if (lane == 0) {
             if (KIND == OP_QKV) {
-                const size_t kvo = ((size_t)op.layer * P.n_ctx + pos) * P.E + rr;
+                const size_t kvo = ((size_t)op.layer * P.n_ctx + pos) * P.El + rr;
                 if (partn == 2) { *(__half2 *)(P.vcache + kvo) = __floats2half2_rn(v0, v1); }
                 else {
                     const float2 cs = rs;
@@ -407,7 +420,8 @@ __device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const
                     else *(__half2 *)(P.kcache + kvo) = __floats2half2_rn(o0, o1);
                 }
             } else if (KIND == OP_WO || KIND == OP_DOWN) {
-                *(float2 *)(P.x + r0) = make_float2(v0 + rs.x, v1 + rs.y);
+                if (P.tp.world <= 1) *(float2 *)(P.x + r0) = make_float2(v0 + rs.x, v1 + rs.y);
+                else *(float2 *)(P.tp.partial[P.tp.rank][KIND == OP_WO ? 0 : 1] + r0) = make_float2(v0, v1);   // partial sum over this rank's columns
             } else if (KIND == OP_GATEUP) {
                 if (pend_i >= 0) P.act[pend_i] = __half2float(pend_h) * pend_up;
                 pend_h = P.tab_silu[__half_as_ushort(__float2half_rn(v0))]; pend_up = v1; pend_i = r0 >> 1;
@@ -548,49 +562,12 @@ __device__ __noinline__ void attention6(const float *__restrict__ q, const __hal
     if (tr) tr[11] = clock64();
 }
 
-// ---- the look-ahead warp (warp 15, one thread).  While the stream warps sit in a grid barrier / staging / the attention op, their 2 W slots
-// fill up and the CTA stops requesting: HBM idles.  This thread watches the CTA's request counter; when it has not moved for a poll interval
-// (= the stream is stalled) it asks L2 for the next chunks of the CTA's stream BEYOND what the slots hold (cp.async.bulk.prefetch.L2), at most
-// l2_window bytes ahead.  The later slot fills of that range are L2 hits.  It never runs while the stream moves: with every byte passing
-// through L2 twice the L2 slices, not HBM, become the limit (tools/ubench_stream.cu: 7.0 -> 5.6 TB/s).
-__device__ __noinline__ void lookahead6(const Params6 &P, const int2 *share, volatile unsigned *fillb) {
-    const int window = P.l2_window;
-    unsigned lin = 0;   // bytes of the CTA's stream (ops in order, the share of each is contiguous) before the current op
-    unsigned last = *fillb;
-    for (int oi = 0; oi < P.n_ops; ++oi) {
-        const Op6 &op = P.ops[oi];
-        if (!op.w) continue;
-        const int2 lh = share[op.kind];
-        const unsigned ub = 2u * (unsigned)op.row_bytes, total = (unsigned)(lh.y - lh.x) * ub;
-        const unsigned char *base = op.w + (size_t)lh.x * ub;
-        for (unsigned off = 0; off < total; ) {
-            const unsigned chunk = min(total - off, 16384u);
-            const unsigned end = lin + off + chunk;     // stream position of the end of this chunk
-            for (;;) {
-                const unsigned fb = *fillb;              // the stream warps have requested (about) everything before fb
-                const int ahead = (int)(end - fb);
-                if (ahead <= 0) break;                   // already requested by the slots: skip
-                if (fb == last && ahead <= window) {     // stalled, and inside the window: ask L2 for it
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(chunk) : "memory");
-                    break;
-                }
-                last = fb;
-                __nanosleep(200);
-            }
-            off += chunk;
-        }
-        lin += total;
-    }
-}
-
 template <int WT, int NBL, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) decode_megakernel6(const __grid_constant__ Params6 P) {
     __shared__ double red[34];
     __shared__ float redf[34];
     __shared__ float part[16 * 128];
     __shared__ int2 share[8];   // this CTA's contiguous share [lo, hi) of the row pairs of each op kind
-    __shared__ unsigned fillb_s; // bytes requested by the stream warps so far (look-ahead warp)
-    unsigned *const fillb = &fillb_s;
     constexpr int ACT = act_of(WT);
     constexpr bool Q41 = WT == GG_Q4_1;
     const Smem6 m = carve6(P);
@@ -601,21 +578,21 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel6(const __grid_c
         for (int s = 0; s < 2 * P.W; ++s) mb_init(&m.full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid == 0) fillb_s = 0u;
     if (tid < 8) share[tid] = make_int2(unit_begin(cta, P.n_su_kind[tid], G), unit_begin(cta + 1, P.n_su_kind[tid], G));
     __syncthreads();  // the only CTA-wide barrier; afterwards warps 0-14 use named barriers 2 (480 threads) and 1 (256 threads)
-    if (warp >= kConsumerWarps) { if (P.l2_window > 0 && lane == 0) lookahead6(P, share, fillb); return; }
+    if (warp >= kConsumerWarps) return;   // (warp 15 only pads the CTA to four warps per scheduler)
 
     // start the stream: the first two slot-loads of this warp
     Fill f{nullptr, 0u, 0u, 0u, 0, 0, 0u};
     unsigned cc = 0;
     if (warp < P.W) {
         fill_seek(P, share, f, warp);
-        fill_one(P, m, share, f, warp, lane, fillb);
-        fill_one(P, m, share, f, warp, lane, fillb);
+        fill_one(P, m, share, f, warp, lane);
+        fill_one(P, m, share, f, warp, lane);
     }
 
-    unsigned bar_target = 0;
+    unsigned bar_target = 0, n_reduce = 0;
+    const unsigned tp_seq0 = P.tp.world > 1 ? __ldcg(P.tp_seq) : 0u;
     const int pos = __ldcg(&P.state->n_past);  // position of the token being decoded (state only changes in OP_FINAL)
     for (int oi = 0; oi < P.n_ops; ++oi) {
         const int kind = P.ops[oi].kind;
@@ -632,8 +609,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel6(const __grid_c
                 for (int i = cta * kConsumerThreads + tid; i < P.E; i += G * kConsumerThreads) P.x[i] = dequant_elem(P.tok_type, row, i);
             } else if (kind == OP_ATTN) {
                 if (cta < P.n_head && tid < 256) {  // one head per CTA, 256 threads (named barrier 1)
-                    const size_t lo = (size_t)P.ops[oi].layer * P.n_ctx * P.E;
-                    attention6(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, P.E, P.n_ctx, P.kq_scale, P.tab_exp, m.actb, red, redf, part, TRACE ? tr : nullptr);
+                    const size_t lo = (size_t)P.ops[oi].layer * P.n_ctx * P.El;
+                    attention6(P.q, P.kcache + lo, P.vcache + lo, P.att, pos, cta, P.El, P.n_ctx, P.kq_scale, P.tab_exp, m.actb, red, redf, part, TRACE ? tr : nullptr);
                 }
             } else if (cta == 0 && tid == 0) {
                 DeviceState *st = P.state;
@@ -641,6 +618,47 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel6(const __grid_c
                 const int id = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
                 st->argmax_id = id; st->tokens[0] = id; st->argmax_key = 0ull;
                 st->n_past += 1; st->n_tok = 1;
+                if (P.tp.world > 1) *P.tp_seq = tp_seq0 + n_reduce;   // (every reduce of this launch has completed on this rank)
+            }
+            if (TRACE && tr) tr[3] = clock64();
+            continue;
+        }
+        if (kind == OP_REDUCE) {
+            // Tensor-parallel sum of the partial vectors of the row-split matmul that just ran (wo: exchange buffer 0, down: buffer 1):
+            //   x += sum over ranks, in rank order, of partial_r          (the same additions in the same order on every rank)
+            // [grid barrier: this rank's partial is complete] -> CTA 0 publishes a sequence number into every rank's flag words (one store per peer
+            // over NVLink) -> kReduceCtas CTAs wait for all ranks' flags, then read their slice of every partial straight out of peer memory.
+            // A buffer is rewritten two reduces later; by then every peer has passed the reduce in between, i.e. finished reading this one.
+            const unsigned seq = tp_seq0 + (++n_reduce);
+            const int buf = P.ops[oi].layer;   // (the op's `layer` field carries the buffer index: 0 after wo, 1 after down)
+            grid_barrier(P.barrier, bar_target);
+            if (TRACE && tr) tr[1] = clock64();
+            if (cta == 0 && tid < P.tp.world) {
+                asm volatile("fence.acq_rel.sys;" ::: "memory");
+                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(P.tp.flags[tid] + P.tp.rank), "r"(seq) : "memory");
+            }
+            if (cta < kReduceCtas) {
+                if (tid < P.tp.world) {
+                    unsigned v, spins = 0; const unsigned *fl = P.tp.flags[P.tp.rank] + tid;
+                    for (;;) {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+                        if ((int)(v - seq) >= 0) break;
+                        if (++spins > (1u << 24)) asm volatile("trap;");   // a lost peer must end in a failed launch, never in a hung GPU
+                        __nanosleep(64);
+                    }
+                }
+                consumer_sync();
+                if (TRACE && tr) tr[2] = clock64();
+                const int per = P.E / kReduceCtas;   // (n_embd % 256 == 0: a multiple of 16)
+                for (int i = cta * per + tid * 4; i < (cta + 1) * per; i += kConsumerThreads * 4) {
+                    float4 acc = __ldcg((const float4 *)(P.x + i));
+                    for (int r = 0; r < P.tp.world; ++r) {
+                        float4 v;
+                        asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(P.tp.partial[r][buf] + i) : "memory");
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    }
+                    *(float4 *)(P.x + i) = acc;
+                }
             }
             if (TRACE && tr) tr[3] = clock64();
             continue;
@@ -660,15 +678,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel6(const __grid_c
             if (TRACE && tr) tr[2] = clock64();
         }
         if (kind == OP_QKV && (P.flags & 1) && cta < P.n_head) {   // (the loads are in flight while this CTA consumes its qkv rows)
-            const size_t lo = (size_t)P.ops[oi].layer * P.n_ctx * P.E;
-            touch_kv_head(P.kcache + lo, P.vcache + lo, P.tab_exp, pos, cta, P.E);
+            const size_t lo = (size_t)P.ops[oi].layer * P.n_ctx * P.El;
+            touch_kv_head(P.kcache + lo, P.vcache + lo, P.tab_exp, pos, cta, P.El);
         }
         switch (kind) {
-            case OP_QKV:    consume6<Q41, OP_QKV, NBL, TRACE>(P, m, share, fillb, oi, f, cc, pos, tr); break;
-            case OP_WO:     consume6<Q41, OP_WO, NBL, TRACE>(P, m, share, fillb, oi, f, cc, pos, tr); break;
-            case OP_GATEUP: consume6<Q41, OP_GATEUP, NBL, TRACE>(P, m, share, fillb, oi, f, cc, pos, tr); break;
-            case OP_DOWN:   consume6<Q41, OP_DOWN, NBL, TRACE>(P, m, share, fillb, oi, f, cc, pos, tr); break;
-            default:        consume6<Q41, OP_OUTPUT, NBL, TRACE>(P, m, share, fillb, oi, f, cc, pos, tr); break;
+            case OP_QKV:    consume6<Q41, OP_QKV, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
+            case OP_WO:     consume6<Q41, OP_WO, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
+            case OP_GATEUP: consume6<Q41, OP_GATEUP, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
+            case OP_DOWN:   consume6<Q41, OP_DOWN, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
+            default:        consume6<Q41, OP_OUTPUT, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
         }
         if (TRACE && tr) tr[3] = clock64();  // (thread 0 = warp 0 only; other warps may still be consuming)
     }

@@ -43,6 +43,9 @@ struct PrefillArgs {
     float *q_out; __half *kcache; __half *vcache; const float2 *rope; int e_local; int half_dim;
     const DeviceState *state;
     const __half *tab_silu;
+    // K split (grid.z > 1): slice z covers the classes of the leaves jr in [z * jr_per_z, (z + 1) * jr_per_z) of the butterfly tree - a complete
+    // subtree - and writes its root {d-tree, m-tree} to partial[(z * part_tok + t) * part_rows + r]; prefill_combine folds the roots and runs the epilogue
+    int jr_per_z; float2 *partial; int part_tok, part_rows;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,6 +87,12 @@ __device__ __forceinline__ void tmem_ld16i(uint32_t taddr, int (&v)[16]) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16i_nowait(uint32_t taddr, int (&v)[16]) {   // the caller issues tcgen05.wait::ld before the first use
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ uint4 ldg_nc16(const void *p) {
     uint4 r;
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -95,6 +104,29 @@ __host__ __device__ __forceinline__ int tile_blocks(int nb, int l, int j) {
     const int n_l = nb > l ? (nb - l + 31) / 32 : 0;
     const int v = n_l - 4 * j;
     return v < 0 ? 0 : (v > 4 ? 4 : v);
+}
+
+// fused output of one result (row r, token t): res = this row, other = the adjacent row of the pair (RoPE / SwiGLU pair adjacent rows);
+// the epilogues of k::matvec_kernel
+__device__ __forceinline__ void prefill_epilogue(const PrefillArgs &g, int r, int t, int n_past, float res, float other) {
+    if (g.epi == EPI_QKV) {
+        const int E = g.e_local, part = r / E, rr = r % E, pos = n_past + t;
+        if (part == 2) g.vcache[(size_t)pos * E + rr] = __float2half_rn(res);
+        else {
+            const float2 cs = g.rope[(size_t)pos * g.half_dim + (rr % (2 * g.half_dim)) / 2];
+            const float v0 = (rr & 1) ? other : res, v1 = (rr & 1) ? res : other;
+            const float o = (rr & 1) ? (v0 * cs.y + v1 * cs.x) : (v0 * cs.x - v1 * cs.y);
+            if (part == 0) g.q_out[(size_t)t * E + rr] = o;
+            else g.kcache[(size_t)pos * E + rr] = __float2half_rn(o);
+        }
+    } else if (g.epi == EPI_RESID) {
+        const size_t o = (size_t)t * g.out_stride + r;
+        g.out[o] = res + g.resid[o];
+    } else if (g.epi == EPI_SWIGLU) {  // rows are interleaved: even = gate(ff), odd = up(ff)
+        if ((r & 1) == 0) g.out[(size_t)t * g.out_stride + (r >> 1)] = lut_f16(g.tab_silu, res) * other;
+    } else {
+        g.out[(size_t)t * g.out_stride + r] = res;
+    }
 }
 
 // grid (rows_pad / 128, ceil(n_tok / 32)); block 320; dynamic smem = 1024 (alignment) + 4 stages + stack + barriers
@@ -112,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, t_tile = blockIdx.y;
     const int tpc = g.S >> 2;  // tiles per class
+    const int jr0 = (int)blockIdx.z * g.jr_per_z, jr1 = jr0 + g.jr_per_z;   // leaves (classes in bit-reversed order) of this CTA's subtree
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -134,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             unsigned cnt = 0;
-            for (int jr = 0; jr < 32; ++jr) {
+            for (int jr = jr0; jr < jr1; ++jr) {
                 const int l = bitrev5(jr);
                 for (int j = 0; j < tpc; ++j) {
                     if (tile_blocks(g.nb, l, j) == 0) continue;
@@ -153,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
         // ---------------- MMA issuer ----------------
         const uint32_t idesc = umma_idesc_i8(kTok);
         unsigned cnt = 0;
-        for (int jr = 0; jr < 32; ++jr) {
+        for (int jr = jr0; jr < jr1; ++jr) {
             const int l = bitrev5(jr);
             for (int j = 0; j < tpc; ++j) {
                 const int v = tile_blocks(g.nb, l, j);
@@ -183,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
 #pragma unroll
         for (int c = 0; c < 16; ++c) { accd[c] = 0.f; accm[c] = 0.f; l0d[c] = 0.f; l0m[c] = 0.f; }
         unsigned cnt = 0;
-        for (int jr = 0; jr < 32; ++jr) {
+        for (int jr = jr0; jr < jr1; ++jr) {
             const int l = bitrev5(jr);
             for (int j = 0; j < tpc; ++j) {
                 const int v = tile_blocks(g.nb, l, j);
@@ -196,17 +229,26 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
                 tc_fence_after();
                 const float2 *asc = (const float2 *)(smem + (size_t)s * kStageBytes + 16384 + 4096);  // [token][4] {d, s}
                 const unsigned wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                // the block dots are requested from TMEM two blocks at a time (one wait per pair), then scaled block by block in increasing order
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (i < v) {
-                        int isum[16];
-                        tmem_ld16i(tmem_base + tlane + (uint32_t)(gq * 128 + i * 32 + c0), isum);
-                        const float2 f = __half22float2(*(const __half2 *)&wv[i]);
+                for (int i0 = 0; i0 < 4; i0 += 2) {
+                    if (i0 < v) {
+                        int isum[2][16];
+                        tmem_ld16i_nowait(tmem_base + tlane + (uint32_t)(gq * 128 + i0 * 32 + c0), isum[0]);
+                        if (i0 + 1 < v) tmem_ld16i_nowait(tmem_base + tlane + (uint32_t)(gq * 128 + (i0 + 1) * 32 + c0), isum[1]);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const float2 ds = asc[(c0 + c) * 4 + i];
-                            if (Q41) { accd[c] = fmaf(f.x * ds.x, (float)isum[c], accd[c]); accm[c] = fmaf(f.y, ds.y, accm[c]); }
-                            else accd[c] += ((float)isum[c] * f.x) * ds.x;
+                        for (int k = 0; k < 2; ++k) {
+                            const int i = i0 + k;
+                            if (i < v) {
+                                const float2 f = __half22float2(*(const __half2 *)&wv[i]);
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) {
+                                    const float2 ds = asc[(c0 + c) * 4 + i];
+                                    if (Q41) { accd[c] = fmaf(f.x * ds.x, (float)isum[k][c], accd[c]); accm[c] = fmaf(f.y, ds.y, accm[c]); }
+                                    else accd[c] += ((float)isum[k][c] * f.x) * ds.x;
+                                }
+                            }
                         }
                     }
                 }
@@ -215,11 +257,12 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
                 if (lane == 0) { mbar_arrive(&rempty[gq]); mbar_arrive(&empty[s]); }
             }
             // class l is complete: fold it into the butterfly tree (post-order walk, jr = leaf number in bit-reversed class order)
-            if ((jr & 1) == 0) {
+            const int jl = jr - jr0;   // leaf number inside this CTA's subtree (jr0 is a multiple of the subtree size)
+            if ((jl & 1) == 0) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c) { l0d[c] = accd[c]; l0m[c] = accm[c]; accd[c] = 0.f; accm[c] = 0.f; }
             } else {
-                int ones = 1; while (ones < 5 && ((jr >> ones) & 1)) ++ones;  // trailing ones of jr (>= 1)
+                int ones = 1; while (ones < 5 && ((jl >> ones) & 1)) ++ones;  // trailing ones of jl (>= 1)
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     float vd = l0d[c] + accd[c], vm = l0m[c] + accm[c];
@@ -228,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
                         const float2 o = stack[((size_t)(lev - 1) * kTok + (c0 + c)) * kRows + row_in];
                         vd = o.x + vd; vm = o.y + vm;
                     }
-                    if (jr != 31) stack[((size_t)(ones - 1) * kTok + (c0 + c)) * kRows + row_in] = make_float2(vd, vm);
+                    if (jr != jr1 - 1) stack[((size_t)(ones - 1) * kTok + (c0 + c)) * kRows + row_in] = make_float2(vd, vm);
                     else { l0d[c] = vd; l0m[c] = vm; }
                 }
             }
@@ -238,32 +281,40 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
             const int t = t_tile * kTok + c0 + c;
+            if (gridDim.z > 1) {   // K split: the root of this CTA's subtree; prefill_combine finishes the tree
+                if (t < g.n_tok && r < g.rows) g.partial[((size_t)blockIdx.z * g.part_tok + t) * g.part_rows + r] = make_float2(l0d[c], l0m[c]);
+                continue;
+            }
             const float res = l0d[c] + l0m[c];
             const float other = __shfl_xor_sync(0xffffffffu, res, 1);   // the pair row (RoPE / SwiGLU pair adjacent rows)
             if (t >= g.n_tok || r >= g.rows) continue;
-            if (g.epi == EPI_QKV) {
-                const int E = g.e_local, part = r / E, rr = r % E, pos = n_past + t;
-                if (part == 2) g.vcache[(size_t)pos * E + rr] = __float2half_rn(res);
-                else {
-                    const float2 cs = g.rope[(size_t)pos * g.half_dim + (rr % (2 * g.half_dim)) / 2];
-                    const float v0 = (rr & 1) ? other : res, v1 = (rr & 1) ? res : other;
-                    const float o = (rr & 1) ? (v0 * cs.y + v1 * cs.x) : (v0 * cs.x - v1 * cs.y);
-                    if (part == 0) g.q_out[(size_t)t * E + rr] = o;
-                    else g.kcache[(size_t)pos * E + rr] = __float2half_rn(o);
-                }
-            } else if (g.epi == EPI_RESID) {
-                const size_t o = (size_t)t * g.out_stride + r;
-                g.out[o] = res + g.resid[o];
-            } else if (g.epi == EPI_SWIGLU) {  // rows are interleaved: even = gate(ff), odd = up(ff)
-                if ((r & 1) == 0) g.out[(size_t)t * g.out_stride + (r >> 1)] = lut_f16(g.tab_silu, res) * other;
-            } else {
-                g.out[(size_t)t * g.out_stride + r] = res;
-            }
+            prefill_epilogue(g, r, t, n_past, res, other);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// K-split GEMMs: fold the subtree roots of the grid.z slices (pairwise, in leaf order = the upper levels of the butterfly tree), then the epilogue.
+// One thread per (token, row pair); nz = 2, 4 or 8.
+__global__ void __launch_bounds__(256) prefill_combine(const PrefillArgs g, int nz) {
+    const int pairs = g.rows >> 1;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)g.n_tok * pairs) return;
+    const int t = (int)(idx / pairs), r0 = 2 * (int)(idx % pairs);
+    float res[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float d[8], m[8];
+        for (int z = 0; z < nz; ++z) { const float2 p = g.partial[((size_t)z * g.part_tok + t) * g.part_rows + r0 + k]; d[z] = p.x; m[z] = p.y; }
+        for (int st = 1; st < nz; st <<= 1)
+            for (int z = 0; z < nz; z += 2 * st) { d[z] = d[z] + d[z + st]; m[z] = m[z] + m[z + st]; }
+        res[k] = d[0] + m[0];
+    }
+    const int n_past = g.state->n_past;
+    prefill_epilogue(g, r0, t, n_past, res[0], res[1]);
+    prefill_epilogue(g, r0 + 1, t, n_past, res[1], res[0]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------

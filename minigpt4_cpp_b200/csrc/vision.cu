@@ -8,7 +8,7 @@
 namespace mg4 {
 using namespace vk;
 
-struct GemmPlan { CUtensorMap tmW, tmX; GemmArgs a; size_t smem; int grid; int grid_y; int grid_z; SplitKArgs sk; };  // grid_y > 0: token-split variant; grid_z > 1: + split-K
+struct GemmPlan { CUtensorMap tmW, tmX; GemmArgs a; size_t smem; int grid; int grid_y; int grid_z; };  // grid_y > 1: token split; grid_z > 1: + split-K
 
 // ---- TMA descriptor encoding through the driver entry point (no libcuda link dependency) ----------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -49,8 +49,9 @@ static GemmPlan *make_plan(const __half *W, int M, int K, const __half *X, int T
     a.tmem_cols = next_pow2_cols(a.t_pad);
     p->smem = (size_t)a.stages * a.stage_bytes + 1024 + 256;
     p->grid = M / 128;
-    // EXPERIMENTAL (MINIGPT4_B200_VISION_TSPLIT=1): split the tokens of the 257-token GEMMs over grid.y CTAs so that ~132-144 SMs work
-    const bool tsplit = getenv("MINIGPT4_B200_VISION_TSPLIT") && atoi(getenv("MINIGPT4_B200_VISION_TSPLIT"));  // (read per plan: a test loads both variants)
+    p->grid_y = 1; p->grid_z = 1;
+    // split the tokens of the 257-token GEMMs over grid.y CTAs so that ~132-144 SMs work (MINIGPT4_B200_VISION_TSPLIT=0: one CTA per weight slab, for A/B runs)
+    const bool tsplit = !(getenv("MINIGPT4_B200_VISION_TSPLIT") && atoi(getenv("MINIGPT4_B200_VISION_TSPLIT")) == 0);  // (read per plan: a test loads both variants)
     if (tsplit && T > 128 && epi != GE_PATCH) {
         const int splits = std::max(2, std::min(4, 148 / p->grid));            // 33 tiles -> 4, 48 -> 3, 11 / 12 -> 4
         const int tt = (((T + splits - 1) / splits) + 15) & ~15;               // tokens per CTA, multiple of 16 (UMMA N)
@@ -61,9 +62,9 @@ static GemmPlan *make_plan(const __half *W, int M, int K, const __half *X, int T
         p->smem = (size_t)a.stages * a.stage_bytes + 1024 + 256;
         p->grid_y = (T + tt - 1) / tt;
         if (ksplit > 1 && ksplit <= K / 64) {                                  // split-K: grid.z slices of whole k-blocks, raw partials out (GE_PARTIAL)
-            p->sk.k_split_blocks = (K / 64 + ksplit - 1) / ksplit;
-            p->grid_z = (K / 64 + p->sk.k_split_blocks - 1) / p->sk.k_split_blocks;
-            if (p->grid_z > 1) a.epi = GE_PARTIAL; else { p->sk.k_split_blocks = 0; p->grid_z = 0; }
+            a.k_split_blocks = (K / 64 + ksplit - 1) / ksplit;
+            p->grid_z = (K / 64 + a.k_split_blocks - 1) / a.k_split_blocks;
+            if (p->grid_z > 1) a.epi = GE_PARTIAL; else { a.k_split_blocks = 0; p->grid_z = 1; }
         }
     }
     make_map_f16(&p->tmW, W, M, K, 128);
@@ -73,16 +74,10 @@ static GemmPlan *make_plan(const __half *W, int M, int K, const __half *X, int T
 static void launch_plan(const GemmPlan *p, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         configured = true;
     }
-    if (p->grid_z > 1) {
-        static bool sk = false;
-        if (!sk) { CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05_splitk, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024)); sk = true; }
-        gemm_f16_tcgen05_splitk<<<dim3((unsigned)p->grid, (unsigned)p->grid_y, (unsigned)p->grid_z), 192, p->smem, s>>>(p->tmW, p->tmX, p->a, p->sk);
-    } else if (p->grid_y > 0) gemm_f16_tcgen05<true><<<dim3((unsigned)p->grid, (unsigned)p->grid_y), 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
-    else gemm_f16_tcgen05<false><<<p->grid, 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
+    gemm_f16_tcgen05<<<dim3((unsigned)p->grid, (unsigned)p->grid_y, (unsigned)p->grid_z), 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -177,9 +172,10 @@ Error VisionDevice::load(const VisionFile &f) {
     img_ = (float *)dalloc((size_t)3 * 224 * 224 * 4);
     patches_ = (__half *)dalloc((size_t)256 * 640 * 2);
     x_ = (float *)dalloc((size_t)T * D * 4);
-    // EXPERIMENTAL (MINIGPT4_B200_VISION_SPLITK=n, needs MINIGPT4_B200_VISION_TSPLIT=1; never run): proj / fc2 as n split-K slices whose partial
+    // proj / fc2 as n split-K slices (default 3; MINIGPT4_B200_VISION_SPLITK=1 turns it off for A/B runs) whose partial
     // sums the following LayerNorm folds into x in slice order
-    splitk_ = (getenv("MINIGPT4_B200_VISION_TSPLIT") && atoi(getenv("MINIGPT4_B200_VISION_TSPLIT")) && getenv("MINIGPT4_B200_VISION_SPLITK")) ? std::max(1, std::min(4, atoi(getenv("MINIGPT4_B200_VISION_SPLITK")))) : 1;
+    const bool tsplit = !(getenv("MINIGPT4_B200_VISION_TSPLIT") && atoi(getenv("MINIGPT4_B200_VISION_TSPLIT")) == 0);
+    splitk_ = !tsplit ? 1 : getenv("MINIGPT4_B200_VISION_SPLITK") ? std::max(1, std::min(4, atoi(getenv("MINIGPT4_B200_VISION_SPLITK")))) : 3;
     parts_ = splitk_ > 1 ? (float *)dalloc((size_t)splitk_ * T * D * 4) : nullptr;
     ln16_ = (__half *)dalloc((size_t)T * D * 2);
     qkv_ = (float *)dalloc((size_t)T * 3 * D * 4);
@@ -231,12 +227,12 @@ Error VisionDevice::load(const VisionFile &f) {
         b.qkv->a.bias = b.qkv_bias; b.qkv->a.qscale = 1.0f / sqrtf((float)d_.dh); b.qkv->a.qscale_rows = D; b.qkv->a.out_f32 = qkv_; b.qkv->a.ld_out = 3 * D;
         b.proj = add_plan(make_plan(w16(f, VE, p + "attn.proj.weight", D, D), D, D, ctx16_, T, GE_RESID, splitk_));
         b.proj->a.bias = w32(f, VE, p + "attn.proj.bias", D); b.proj->a.out_f32 = x_; b.proj->a.resid = x_; b.proj->a.ld_out = D;
-        b.proj->sk.partial = parts_; b.proj->sk.partial_stride = (long long)T * D;
+        b.proj->a.partial = parts_; b.proj->a.partial_stride = (long long)T * D;
         b.fc1 = add_plan(make_plan(w16(f, VE, p + "mlp.fc1.weight", FF, D), FF, D, ln16_, T, GE_GELU_F16));
         b.fc1->a.bias = w32(f, VE, p + "mlp.fc1.bias", FF); b.fc1->a.out_f16 = h16_; b.fc1->a.ld_out = FF; b.fc1->a.tab_gelu = tab_gelu_;
         b.fc2 = add_plan(make_plan(w16(f, VE, p + "mlp.fc2.weight", D, FF), D, FF, h16_, T, GE_RESID, splitk_));
         b.fc2->a.bias = w32(f, VE, p + "mlp.fc2.bias", D); b.fc2->a.out_f32 = x_; b.fc2->a.resid = x_; b.fc2->a.ld_out = D;
-        b.fc2->sk.partial = parts_; b.fc2->sk.partial_stride = (long long)T * D;
+        b.fc2->a.partial = parts_; b.fc2->a.partial_stride = (long long)T * D;
         flops_ += 4.0 * d_.H * (double)T * T * d_.dh;
     }
     lnv_w_ = w32(f, "ln_vision", "weight", D); lnv_b_ = w32(f, "ln_vision", "bias", D);

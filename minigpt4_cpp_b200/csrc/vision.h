@@ -61,7 +61,7 @@ private:
     const float *cls_ = nullptr, *pos_ = nullptr, *lnv_w_ = nullptr, *lnv_b_ = nullptr, *qtok_ = nullptr, *qln_w_ = nullptr, *qln_b_ = nullptr;
     // activations
     float *img_ = nullptr, *x_ = nullptr, *qkv_ = nullptr, *proj_out_ = nullptr;
-    int splitk_ = 1; float *parts_ = nullptr;  // experimental split-K of the residual GEMMs (MINIGPT4_B200_VISION_SPLITK)
+    int splitk_ = 1; float *parts_ = nullptr;  // split-K slices of the residual GEMMs proj / fc2 (default 3)
     __half *patches_ = nullptr, *ln16_ = nullptr, *ctx16_ = nullptr, *h16_ = nullptr, *img_emb16_ = nullptr;
     float *qtmp_ = nullptr;
     float *hs_ = nullptr, *qa_ = nullptr, *qc_ = nullptr, *qqkv_ = nullptr, *qq_ = nullptr, *qkv_cross_ = nullptr;

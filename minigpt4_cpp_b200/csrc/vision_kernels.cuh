@@ -29,11 +29,9 @@ struct GemmArgs {
     const float *resid;       // GE_RESID: out = resid + (acc + bias)   (may alias out_f32)
     const float *pos;         // GE_PATCH: out[t+1] = acc + bias + pos[t+1]
     const __half *tab_gelu;
-    int t_tile;               // token-split variant only (gemm_f16_tcgen05<true>): tokens per CTA, grid.y = ceil(T / t_tile); t_pad == n1 == t_tile, n2 == 0
-};
-struct SplitKArgs {           // extra launch parameters of gemm_f16_tcgen05_splitk (kept out of GemmArgs: the measured kernels' parameter block must not change)
-    int k_split_blocks;       // 64-wide k-blocks per grid.z slice
-    float *partial; long long partial_stride;  // slice z writes acc (+ bias if z == 0) to partial[z * partial_stride + t * ld_out + m]
+    int t_tile;               // token split: tokens per CTA, grid.y = ceil(T / t_tile), t_pad == n1 == t_tile, n2 == 0 (0: one CTA takes all tokens)
+    int k_split_blocks;       // split-K: 64-wide k-blocks per grid.z slice (0: no split)
+    float *partial; long long partial_stride;  // GE_PARTIAL: slice z writes acc (+ bias if z == 0) to partial[z * partial_stride + t * ld_out + m]
 };
 
 // ---- raw PTX wrappers ---------------------------------------------------------------------------------
@@ -83,120 +81,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // out[t][m] = epi( sum_k W[m][k] * X[t][k] )      W: F16 [M_out][K] (TMA map tmW), X: F16 [T][K] (TMA map tmX)
 // grid = M_out/128 CTAs of 192 threads: warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue
 // ---------------------------------------------------------------------------------------------
-// TS = true: EXPERIMENTAL token-split variant (MINIGPT4_B200_VISION_TSPLIT=1, not the default, not yet run - DESIGN.md §7): grid.y CTAs share
-// one 128-feature weight slab and take t_tile tokens each, so the T = 257 GEMMs run on 44-144 SMs instead of 11-48 (r1_v3 ncu: an 11-CTA
-// GEMM is bound by what ONE SM can pull through TMA, 70 GB/s).  Rows past T come back from TMA as zeros and are masked in the epilogue.
-template <bool TS>
+// TOKEN SPLIT (grid.y): the CTAs of one 128-feature weight slab take t_tile tokens each, so the T = 257 GEMMs run on 44-144 SMs instead of 11-48
+// (r1_v3 ncu: an 11-CTA GEMM is bound by what ONE SM can pull through TMA, 70 GB/s); rows past T come back from TMA as zeros and are masked in
+// the epilogue.  t_tile == 0: one CTA takes all tokens.
+// SPLIT-K (grid.z, the two residual GEMMs proj / fc2 whose M is only 1408): a CTA covers the k-blocks [z * k_split_blocks, ...) of its tile and
+// writes raw partial sums (GE_PARTIAL, bias on slice 0); layernorm_fold_kernel folds the slices into the residual stream in slice order
+// (deterministic).  Measured on the 39-block ViT-g + Q-Former encode: 8.69 ms (one CTA per slab) -> 6.57 ms (token split) -> 5.72 ms (+ split-K 3).
 __global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmArgs g) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = (uint64_t *)(smem + (size_t)g.stages * g.stage_bytes);
-    uint64_t *empty = full + 8;
-    uint64_t *tmem_full = empty + 8;
-    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x;
-    const int t0 = TS ? (int)blockIdx.y * g.t_tile : 0;  // first token of this CTA
-    const int num_k = g.K / 64;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-        for (int i = 0; i < g.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(tmem_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            const uint32_t tx = 16384u + (uint32_t)g.t_pad * 128u;
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % g.stages; const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                unsigned char *sa = smem + (size_t)s * g.stage_bytes, *sb = sa + 16384;
-                mbar_expect_tx(&full[s], tx);
-                tma_load_2d(sa, &tmW, kb * 64, m_tile * 128, &full[s]);
-                for (int b = 0; b < g.n_box; ++b) tma_load_2d(sb + (size_t)b * g.box_rows * 128, &tmX, kb * 64, t0 + b * g.box_rows, &full[s]);
-            }
-        }
-    } else if (warp == 1) {
-        const uint32_t id1 = umma_idesc_f16(g.n1), id2 = umma_idesc_f16(g.n2 ? g.n2 : 16);
-        for (int kb = 0; kb < num_k; ++kb) {
-            const int s = kb % g.stages; const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
-            mbar_wait(&full[s], ph);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(smem + (size_t)s * g.stage_bytes), sb = sa + 16384u;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t ad = umma_desc_sw128(sa + k * 32), bd = umma_desc_sw128(sb + k * 32);
-                    tc_mma_f16(tmem_base, ad, bd, id1, (uint32_t)((kb | k) != 0));
-                    if (g.n2) tc_mma_f16(tmem_base + 256u, ad, umma_desc_sw128(sb + 256u * 128u + k * 32), id2, (uint32_t)((kb | k) != 0));
-                }
-                tc_commit(&empty[s]);
-                if (kb == num_k - 1) tc_commit(tmem_full);
-            }
-            __syncwarp();
-        }
-    } else {
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int quarter = warp & 3;
-        const int m = m_tile * 128 + quarter * 32 + lane;
-        const float bias = g.bias ? g.bias[m] : 0.f;
-        const float qs = (g.epi == GE_QSCALE && m < g.qscale_rows) ? g.qscale : 1.0f;
-        for (int c0 = 0; c0 < g.t_pad; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            // No early exit inside the 16-token batch: every load of the batch (residual / positional embedding) is issued
-            // before its first use, so the epilogue pays one L2 round trip per batch instead of one per token.
-            float aux[16];
-            if (g.epi == GE_RESID || g.epi == GE_PATCH) {
-                const float *src = g.epi == GE_RESID ? g.resid : g.pos;
-                const int off = g.epi == GE_PATCH ? 1 : 0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { const int t = t0 + c0 + j; aux[j] = t < g.T ? src[(size_t)(t + off) * g.ld_out + m] : 0.f; }
-            }
-            if (g.epi == GE_GELU_F16) {
-                __half hv[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) hv[j] = g.tab_gelu[__half_as_ushort(__float2half_rn(bias + v[j]))];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { const int t = t0 + c0 + j; if (t < g.T) g.out_f16[(size_t)t * g.ld_out + m] = hv[j]; }
-                continue;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int t = t0 + c0 + j;
-                if (t < g.T) {
-                    float r = bias + v[j];
-                    switch (g.epi) {
-                        case GE_QSCALE: r *= qs; g.out_f32[(size_t)t * g.ld_out + m] = r; break;
-                        case GE_RESID: g.out_f32[(size_t)t * g.ld_out + m] = aux[j] + r; break;
-                        case GE_PATCH: g.out_f32[(size_t)(t + 1) * g.ld_out + m] = (0.0f + r) + aux[j]; break;
-                        default: g.out_f32[(size_t)t * g.ld_out + m] = r; if (g.out_f16) g.out_f16[(size_t)t * g.ld_out + m] = __float2half_rn(r); break;
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
-}
-
-// EXPERIMENTAL split-K companion of gemm_f16_tcgen05<true> (MINIGPT4_B200_VISION_SPLITK, never run): the same pipeline, but a CTA covers only the
-// k-blocks [z * k_split_blocks, ...) of its (128-feature, t_tile-token) tile and writes raw partial sums (GE_PARTIAL); layernorm_fold_kernel folds
-// the slices into the residual stream in slice order.  A separate kernel so that the measured gemm_f16_tcgen05<false> stays byte-identical.
-__global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05_splitk(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmArgs g, const SplitKArgs sk) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full = (uint64_t *)(smem + (size_t)g.stages * g.stage_bytes);
@@ -207,8 +98,8 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05_splitk(const __grid_c
     const int m_tile = blockIdx.x;
     const int t0 = (int)blockIdx.y * g.t_tile;  // first token of this CTA
     const int num_k_all = g.K / 64;
-    const int kb0 = (sk.k_split_blocks != 0) ? (int)blockIdx.z * sk.k_split_blocks : 0;          // first k-block of this CTA (split-K)
-    const int num_k = (sk.k_split_blocks != 0) ? min(sk.k_split_blocks, num_k_all - kb0) : num_k_all;
+    const int kb0 = (g.k_split_blocks != 0) ? (int)blockIdx.z * g.k_split_blocks : 0;          // first k-block of this CTA (split-K)
+    const int num_k = (g.k_split_blocks != 0) ? min(g.k_split_blocks, num_k_all - kb0) : num_k_all;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -268,7 +159,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tcgen05_splitk(const __grid_c
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
             if (g.epi == GE_PARTIAL) {  // split-K slice: raw partial sums (bias rides on slice 0); the following LayerNorm folds the slices into x
-                float *dst = sk.partial + (size_t)blockIdx.z * (size_t)sk.partial_stride;
+                float *dst = g.partial + (size_t)blockIdx.z * (size_t)g.partial_stride;
                 const float b0 = blockIdx.z == 0 ? bias : 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { const int t = t0 + c0 + j; if (t < g.T) dst[(size_t)t * g.ld_out + m] = b0 + v[j]; }

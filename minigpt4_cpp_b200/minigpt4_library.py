@@ -208,6 +208,7 @@ _EXT = {
     "minigpt4_b200_eval_tokens": ([_CTX, _VP, _I], _I),
     "minigpt4_b200_eval_embd": ([_CTX, _VP, _I], _I),
     "minigpt4_b200_flush": ([_CTX], _I),
+    "minigpt4_b200_tp_time_allreduce": ([_CTX, _I, C.POINTER(C.c_float), C.POINTER(C.c_int)], _I),
     "minigpt4_b200_get_logits": ([_CTX, _VP], _I),
     "minigpt4_b200_greedy_id": ([_CTX], _I),
     "minigpt4_b200_get_hidden": ([_CTX, _VP, _I], _I),
@@ -267,6 +268,11 @@ class B200:
     def eval_embd(self, ctx, rows: np.ndarray):
         a = np.ascontiguousarray(rows, np.float32)
         self._chk(self.L.minigpt4_b200_eval_embd(ctx.ptr, _ptr(a), a.shape[0]))
+
+    def tp_time_allreduce(self, ctx, reps: int = 64) -> tuple[float, bool]:
+        us, peer = C.c_float(0), C.c_int(0)
+        self._chk(self.L.minigpt4_b200_tp_time_allreduce(ctx.ptr, reps, C.byref(us), C.byref(peer)))
+        return us.value, bool(peer.value)
 
     def flush(self, ctx) -> None:
         """evaluate the queued prompt rows now (they are otherwise evaluated together when the model state is first needed)"""

@@ -114,6 +114,47 @@ def test_megakernel_equals_per_op_path(ext, orc, tiny, monkeypatch):
         ext.base.minigpt4_free(c1); ext.base.minigpt4_free(c2)
 
 
+def test_vision_gemm_grid_variants(lib, ext, mg, tiny, big_llm, monkeypatch):
+    """The encode runs its 257-token GEMMs token-split over grid.y (each output element keeps its K order: bit-identical to one CTA per weight
+    slab) and proj / fc2 as three split-K slices folded into the residual stream by the following LayerNorm in slice order (a different float
+    association: equal to a few ulps, deterministic).  MINIGPT4_B200_VISION_TSPLIT=0 / _SPLITK=1 select the plain grids."""
+    img = mg.synth_image(5)
+    c_def = lib.minigpt4_model_load(tiny["vision"], big_llm, 1, 1, 64, 8, 0)
+    monkeypatch.setenv("MINIGPT4_B200_VISION_SPLITK", "1")
+    c_ts = lib.minigpt4_model_load(tiny["vision"], big_llm, 1, 1, 64, 8, 0)        # token split only
+    monkeypatch.setenv("MINIGPT4_B200_VISION_TSPLIT", "0")
+    c_plain = lib.minigpt4_model_load(tiny["vision"], big_llm, 1, 1, 64, 8, 0)     # one CTA per 128-feature slab
+    monkeypatch.delenv("MINIGPT4_B200_VISION_TSPLIT"); monkeypatch.delenv("MINIGPT4_B200_VISION_SPLITK")
+    a, b, c = ext.encode_array(c_plain, img), ext.encode_array(c_ts, img), ext.encode_array(c_def, img)
+    assert np.array_equal(a, b), float(np.abs(a - b).max())
+    assert rel_err(c, a) < 1e-4, rel_err(c, a)
+    assert np.array_equal(c, ext.encode_array(c_def, img))   # no atomics: the same bits every time
+    for x in (c_def, c_ts, c_plain): lib.minigpt4_free(x)
+
+
+def test_queued_prompt_pieces_equal_piecewise_evaluation(ext, tiny):
+    """The engine queues consecutive add_tokens / add_embedding calls and evaluates them in one pass (the reference evaluates each piece on its own,
+    minigpt4.cpp:2365-2415).  Rows are batch invariant, so the logits must not change by a single bit; errors are still raised at queue time."""
+    for wt in ("q4_1", "q5_k"):
+        c1, c2 = ext.llm_load(tiny[wt], n_ctx=512), ext.llm_load(tiny[wt], n_ctx=512)
+        rng = np.random.default_rng(3)
+        rows = rng.standard_normal((32, ext.L.minigpt4_b200_n_embd(c1.ptr))).astype(np.float32)
+        pieces = [("t", list(range(5, 25))), ("t", [7, 9, 11]), ("e", rows), ("t", [4]), ("t", list(range(30, 47))), ("t", [3, 3, 8])]
+        for kind, p in pieces:
+            (ext.eval_tokens if kind == "t" else ext.eval_embd)(c1, p)                      # queued: one pass over the weights at the end
+            (ext.eval_tokens if kind == "t" else ext.eval_embd)(c2, p); ext.flush(c2)      # forced: one pass per piece
+        assert ext.n_past(c1) == ext.n_past(c2) == sum(len(p) for _, p in pieces)
+        assert np.array_equal(ext.logits(c1), ext.logits(c2))
+        a, b = [], []
+        for _ in range(6):
+            t1, t2 = ext.greedy_id(c1), ext.greedy_id(c2); a.append(t1); b.append(t2)
+            ext.eval_tokens(c1, [t1]); ext.eval_tokens(c2, [t2])
+        assert a == b
+        with pytest.raises(RuntimeError, match="FailedToAddString"):   # validated when queued, not when flushed
+            ext.eval_tokens(c1, [10 ** 9])
+        ext.base.minigpt4_free(c1); ext.base.minigpt4_free(c2)
+
+
 def test_context_overflow_is_an_error(ext, tiny):
     c = ext.llm_load(tiny["q4_1"], n_ctx=16)
     with pytest.raises(RuntimeError, match="FailedToAddString"):
