@@ -158,9 +158,7 @@ int minigpt4_b200_decode_chain(struct MiniGPT4Context *ctx, int steps, int32_t *
 }
 int minigpt4_b200_encode_images(struct MiniGPT4Context *ctx, struct MiniGPT4Images *images, struct MiniGPT4Embeddings *embeddings) {
     if (embeddings->n_embeddings < images->n_images) return ErrImageSize;
-    for (size_t i = 0; i < images->n_images; ++i)
-        if (int err = E(ctx)->encode_image(&images->images[i], &embeddings->embeddings[i])) return err;
-    return 0;
+    return E(ctx)->encode_images(images->images, images->n_images, embeddings->embeddings, nullptr);
 }
 int minigpt4_b200_stats(struct MiniGPT4Context *ctx, struct MiniGPT4B200Stats *out) {
     Engine *e = E(ctx);

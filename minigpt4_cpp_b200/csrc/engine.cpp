@@ -10,6 +10,7 @@ TPConfig g_tp_config;
 
 Engine::~Engine() {
     llm_.reset();
+    vis_lanes_.clear();   // (lanes borrow the first lane's weights)
     vis_.reset();
     tp.destroy();
 }
@@ -35,7 +36,8 @@ Error Engine::init(const std::string &path, const std::string &llm_path, int ver
     }
     if (!path.empty()) {
         const double t0 = now_ms();
-        VisionFile vf;
+        vfile_.reset(new VisionFile());   // (kept mapped: further encode lanes are built from it on demand)
+        VisionFile &vf = *vfile_;
         if (Error e = vf.load(path)) return e;
         vis_.reset(new VisionDevice());
         if (Error e = vis_->load(vf)) return e;
@@ -58,6 +60,37 @@ Error Engine::encode_image(const ::MiniGPT4Image *image, ::MiniGPT4Embedding *ou
     out->data = new float[n];
     last_encode_ms = vis_->encode((const float *)image->data, out->data);
     MG4_INFO("Encoding image took %.3f ms on device", last_encode_ms);
+    return ErrNone;
+}
+
+// Batched encode (extension; the reference encodes one image per call, minigpt4.cpp:2094): up to kEncodeLanes images are in flight at once, each on
+// its own lane = its own activations, CUDA graph and stream over the SHARED weights.  One image's graph leaves most SMs idle most of the time
+// (its GEMMs are 44-144 CTAs, its attention 144, the Q-Former a handful), so concurrent graphs interleave on the machine; every image goes
+// through exactly the single-image graph, so each embedding is bit-identical to minigpt4_encode_image's.
+Error Engine::encode_images(const ::MiniGPT4Image *images, size_t n, ::MiniGPT4Embedding *out, float *total_ms) {
+    if (!vis_) MG4_PANIC("encode_images on a context loaded without a vision model");
+    for (size_t i = 0; i < n; ++i) {
+        if ((long)images[i].width * images[i].height * images[i].channels != 224L * 224 * 3) return ErrImageNot224_244_3;
+        if (images[i].format != MINIGPT4_IMAGE_FORMAT_F32) return ErrImageNotF32;
+    }
+    const size_t lanes = std::min<size_t>(n, (size_t)kEncodeLanes);
+    while (vis_lanes_.size() + 1 < lanes) {
+        std::unique_ptr<VisionDevice> l(new VisionDevice());
+        if (Error e = l->load(*vfile_, vis_.get())) return e;
+        vis_lanes_.push_back(std::move(l));
+    }
+    auto lane = [&](size_t k) { return k == 0 ? vis_.get() : vis_lanes_[k - 1].get(); };
+    const size_t ne = (size_t)32 * vis_->dims().n_embd_llm;
+    const double t0 = now_ms();
+    for (size_t base = 0; base < n; base += lanes) {
+        const size_t c = std::min(lanes, n - base);
+        for (size_t k = 0; k < c; ++k) lane(k)->encode_begin((const float *)images[base + k].data);
+        for (size_t k = 0; k < c; ++k) {
+            out[base + k].elements = ne; out[base + k].data = new float[ne];
+            last_encode_ms = lane(k)->encode_end(out[base + k].data);
+        }
+    }
+    if (total_ms) *total_ms = (float)(now_ms() - t0);
     return ErrNone;
 }
 

@@ -22,6 +22,8 @@ public:
     // path may be empty (language model only, extension entry point)
     Error init(const std::string &path, const std::string &llm_path, int verbosity, int seed, int n_ctx, int n_batch, bool numa);
     Error encode_image(const ::MiniGPT4Image *image, ::MiniGPT4Embedding *out);
+    static constexpr int kEncodeLanes = 8;
+    Error encode_images(const ::MiniGPT4Image *images, size_t n, ::MiniGPT4Embedding *out, float *total_ms);   // batched: concurrent lanes
     Error add_tokens(const std::vector<int32_t> &tokens);
     Error add_strings(const char *s);
     Error add_embedding(const float *rows, int n_rows);
@@ -42,7 +44,9 @@ public:
     TPLink tp;
 
 private:
+    std::unique_ptr<VisionFile> vfile_;
     std::unique_ptr<VisionDevice> vis_;
+    std::vector<std::unique_ptr<VisionDevice>> vis_lanes_;   // lanes 1.. of the batched encode (lane 0 = vis_)
     std::unique_ptr<LlamaDevice> llm_;
     Tokenizer tok_;
     std::unique_ptr<Sampler> sampler_;

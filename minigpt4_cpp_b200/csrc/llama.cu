@@ -76,7 +76,7 @@ static void launch_matvec(MatvecArgs a, int nt, int sm_count, cudaStream_t s, un
 // ------------------------------------------------------------------------------------------------
 // weight upload + repack
 // ------------------------------------------------------------------------------------------------
-static bool type_supported(int t) {  // (Q4_K, Q5_0, Q5_1, Q8_0: experimental device paths, not yet run - tests/test_experimental_gpu.py)
+static bool type_supported(int t) {  // (Q4_K, Q5_0, Q5_1, Q8_0: tests/test_block_types_gpu.py)
     return t == GG_Q4_0 || t == GG_Q4_1 || t == GG_Q4_K || t == GG_Q5_K || t == GG_Q6_K || t == GG_F16 || t == GG_Q5_0 || t == GG_Q5_1 || t == GG_Q8_0;
 }
 
@@ -613,10 +613,10 @@ bool LlamaDevice::build_mega6() {
     memset(P, 0, sizeof(Params6));
     int n = 0; bool uniform = true;   // every layer's matrices have the same shapes (the CTA's share of a kind is computed once)
     auto add = [&](int kind, int layer, const QMat *m, const float *norm) {
-        Op6 &o = P->ops[n++]; o.kind = kind; o.layer = layer; o.norm_w = norm;
+        Op6 &o = P->ops[n++]; o.kind = (unsigned char)kind; o.layer = (unsigned short)layer; o.norm_w = norm;
         if (m) {
             o.cols = m->cols; o.row_bytes = m->row_bytes; o.w = (const unsigned char *)m->p0;
-            o.parts = 2 * m->row_bytes <= slot ? 1 : 2;
+            o.parts = (unsigned char)(2 * m->row_bytes <= slot ? 1 : 2);
             o.n_su = m->rows / 2;
             if ((2 * m->row_bytes / o.parts) % 16) uniform = false;   // every slot-load is a 16-byte aligned, 16-byte multiple bulk copy
             if (P->n_su_kind[kind] && P->n_su_kind[kind] != o.n_su) uniform = false;

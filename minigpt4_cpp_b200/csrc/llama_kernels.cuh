@@ -330,7 +330,7 @@ __device__ __forceinline__ void dot2_q5k(const QMat &w, int r0, const unsigned c
         for (int t = 0; t < NT; ++t) res[r][t] = warp_sum(accd[r][t]) - warp_sum(accm[r][t]);
 }
 
-// Q5_0 / Q5_1 / Q8_0 (EXPERIMENTAL, never run on a GPU yet - reached only by loading a ggjt file that holds such tensors).  Device layout
+// Q5_0 / Q5_1 / Q8_0 (reached by loading a ggjt file that holds such tensors; tests/test_block_types_gpu.py).  Device layout
 // (planes, [row][block]): p0 = payload (Q8_0: 32 int8; Q5_x: 16 B of nibbles), p1 = Q5_x fifth bits (32-bit qh), p2 = half d (Q5_0, Q8_0) or
 // half2 {d, m} (Q5_1).  Canonical order = oracle.cpp dot_canon_q5_0 / q5_1 / q8_0: lane l owns blocks l, l+32, ...; xor butterflies.
 __device__ __forceinline__ unsigned spread4_to_bit4(unsigned n) { return ((n * 0x00204081u) & 0x01010101u) << 4; }  // bit i of n (< 16) -> bit 4 of byte i
@@ -388,7 +388,7 @@ __device__ __forceinline__ void dot2_b32(const QMat &w, int r0, const unsigned c
         for (int t = 0; t < NT; ++t) res[r][t] = warp_sum(accd[r][t]) + warp_sum(accm[r][t]);
 }
 
-// Q4_K (EXPERIMENTAL, never run on a GPU yet - reached only by loading a ggjt file that holds Q4_K tensors): Q5_K without the fifth bits;
+// Q4_K (reached by loading a ggjt file that holds Q4_K tensors; tests/test_block_types_gpu.py): Q5_K without the fifth bits;
 // device layout p0 = qs (128 B / super-block), p2 = {scales[12], d, dmin}; canonical order = oracle.cpp dot_canon_q4_K
 template <int NT>
 __device__ __forceinline__ void dot2_q4k(const QMat &w, int r0, const unsigned char *act, size_t astride, int lane, float (&res)[2][NT]) {
@@ -817,7 +817,7 @@ __global__ void embed_rows_kernel(int type, const unsigned char *tok, size_t row
         for (int i = threadIdx.x; i < E; i += blockDim.x) x[(size_t)t * E + i] = src[i];
     }
 }
-// Q4_K token-embedding rows (EXPERIMENTAL, with the Q4_K matvec): kept out of dequant_elem so that the kernels which inline it
+// Q4_K token-embedding rows: kept out of dequant_elem so that the kernels which inline it
 // (embed_kernel, the decode megakernel) stay byte-identical to the measured build
 __global__ void embed_q4k_kernel(const unsigned char *tok, size_t row_bytes, int E, const DeviceState *st, float *x) {
     const int t = blockIdx.x;

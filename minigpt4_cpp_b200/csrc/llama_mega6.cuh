@@ -31,14 +31,15 @@ using namespace k;
 
 enum OpKind : int { OP_EMBED = 0, OP_QKV = 1, OP_ATTN = 2, OP_WO = 3, OP_GATEUP = 4, OP_DOWN = 5, OP_OUTPUT = 6, OP_FINAL = 7, OP_REDUCE = 8 };
 
-struct Op6 {                 // 48 bytes, lives in the kernel's parameter (constant) space
-    int kind, layer, cols, n_su;   // n_su = row pairs (units) of the matrix over the whole grid
-    int row_bytes, parts;          // a unit = 2 * row_bytes contiguous bytes, brought by `parts` slot-loads (1: the pair in one slot; 2: one row per slot)
+struct Op6 {                 // 32 bytes, lives in the kernel's parameter (constant) space
+    unsigned char kind, parts;     // a unit = 2 * row_bytes contiguous bytes, brought by `parts` slot-loads (1: the pair in one slot; 2: one row per slot)
+    unsigned short layer;          // (OP_REDUCE: exchange buffer index)
+    int cols, n_su, row_bytes;     // n_su = row pairs (units) of the matrix over the whole grid
     const unsigned char *w;        // row-packed Q4 weights (null for non-matvec ops)
     const float *norm_w;
-    long long pad_;
 };
-constexpr int kMaxOps = 7 * 80 + 3;   // up to 80 layers, tensor-parallel program (7 ops per layer); parameter space: 32 764 bytes
+static_assert(sizeof(Op6) == 32, "Op6");
+constexpr int kMaxOps = 7 * 80 + 3;   // up to 80 layers, tensor-parallel program (7 ops per layer): 18 KB of the 32 764-byte parameter space
 
 struct Params6 {
     int n_ops, W, slot_bytes, act_bytes;   // shared memory: [2 W slots][act: staged Q8 activations / attention scratch][2 W mbarriers]

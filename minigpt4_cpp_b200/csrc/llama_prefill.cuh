@@ -87,12 +87,6 @@ __device__ __forceinline__ void tmem_ld16i(uint32_t taddr, int (&v)[16]) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld16i_nowait(uint32_t taddr, int (&v)[16]) {   // the caller issues tcgen05.wait::ld before the first use
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr));
-}
 __device__ __forceinline__ uint4 ldg_nc16(const void *p) {
     uint4 r;
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -229,26 +223,17 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
                 tc_fence_after();
                 const float2 *asc = (const float2 *)(smem + (size_t)s * kStageBytes + 16384 + 4096);  // [token][4] {d, s}
                 const unsigned wv[4] = {w4.x, w4.y, w4.z, w4.w};
-                // the block dots are requested from TMEM two blocks at a time (one wait per pair), then scaled block by block in increasing order
 #pragma unroll
-                for (int i0 = 0; i0 < 4; i0 += 2) {
-                    if (i0 < v) {
-                        int isum[2][16];
-                        tmem_ld16i_nowait(tmem_base + tlane + (uint32_t)(gq * 128 + i0 * 32 + c0), isum[0]);
-                        if (i0 + 1 < v) tmem_ld16i_nowait(tmem_base + tlane + (uint32_t)(gq * 128 + (i0 + 1) * 32 + c0), isum[1]);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int i = 0; i < 4; ++i) {
+                    if (i < v) {
+                        int isum[16];
+                        tmem_ld16i(tmem_base + tlane + (uint32_t)(gq * 128 + i * 32 + c0), isum);
+                        const float2 f = __half22float2(*(const __half2 *)&wv[i]);
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int i = i0 + k;
-                            if (i < v) {
-                                const float2 f = __half22float2(*(const __half2 *)&wv[i]);
-#pragma unroll
-                                for (int c = 0; c < 16; ++c) {
-                                    const float2 ds = asc[(c0 + c) * 4 + i];
-                                    if (Q41) { accd[c] = fmaf(f.x * ds.x, (float)isum[k][c], accd[c]); accm[c] = fmaf(f.y, ds.y, accm[c]); }
-                                    else accd[c] += ((float)isum[k][c] * f.x) * ds.x;
-                                }
-                            }
+                        for (int c = 0; c < 16; ++c) {
+                            const float2 ds = asc[(c0 + c) * 4 + i];
+                            if (Q41) { accd[c] = fmaf(f.x * ds.x, (float)isum[c], accd[c]); accm[c] = fmaf(f.y, ds.y, accm[c]); }
+                            else accd[c] += ((float)isum[c] * f.x) * ds.x;
                         }
                     }
                 }

@@ -1,5 +1,6 @@
 // vision.cu — host side of the vision graph (see vision.h, vision_kernels.cuh).
 #include "vision.h"
+#include <functional>
 #include "vision_kernels.cuh"
 #include <math.h>
 #include <string.h>
@@ -100,8 +101,6 @@ VisionDevice::~VisionDevice() {
     if (graph_) cudaGraphExecDestroy(graph_);
     for (GemmPlan *p : plans_) delete p;
     for (void *p : allocs_) cudaFree(p);
-    if (tab_gelu_) cudaFree(tab_gelu_);
-    if (tab_exp_) cudaFree(tab_exp_);
     if (h_out_) cudaFreeHost(h_out_);
     if (h_img_) cudaFreeHost(h_img_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -130,24 +129,30 @@ void VisionDevice::put16(const HostTensor &t, __half *dst) {
     CUDA_CHECK(cudaDeviceSynchronize());
     cudaFree(raw);
 }
+// Weights live once per model: a lane created for batched encoding (Engine::encode_images) finds every weight of the first lane under its key
+// and only allocates its own activations, plans and graph.
+void *VisionDevice::cached(const std::string &key, size_t bytes, const std::function<void(void *)> &fill) {
+    auto it = wcache_->find(key);
+    if (it != wcache_->end()) { weight_bytes_ += bytes; return it->second; }
+    void *d = dalloc(bytes);
+    fill(d);
+    (*wcache_)[key] = d;
+    weight_bytes_ += bytes;
+    return d;
+}
 const __half *VisionDevice::w16(const VisionFile &f, const std::string &model, const std::string &name, int rows, int cols) {
     const HostTensor &t = f.get(model, name);
     if (t.nelements() != (int64_t)rows * cols) MG4_PANIC("tensor %s.%s: expected %d x %d", model.c_str(), name.c_str(), rows, cols);
-    __half *d = (__half *)dalloc((size_t)rows * cols * 2);
-    put16(t, d);
-    weight_bytes_ += (size_t)rows * cols * 2;
-    return d;
+    return (const __half *)cached("h:" + model + "/" + name, (size_t)rows * cols * 2, [&](void *d) { put16(t, (__half *)d); });
 }
 const float *VisionDevice::w32(const VisionFile &f, const std::string &model, const std::string &name, int n) {
     const HostTensor &t = f.get(model, name);
     if (t.gg != GG_F32 || t.nelements() != n) MG4_PANIC("tensor %s.%s: expected %d F32 values", model.c_str(), name.c_str(), n);
-    void *d = dalloc(t.nbytes);
-    CUDA_CHECK(cudaMemcpy(d, t.data, t.nbytes, cudaMemcpyHostToDevice));
-    weight_bytes_ += t.nbytes;
-    return (const float *)d;
+    return (const float *)cached("f:" + model + "/" + name, t.nbytes, [&](void *d) { CUDA_CHECK(cudaMemcpy(d, t.data, t.nbytes, cudaMemcpyHostToDevice)); });
 }
 
-Error VisionDevice::load(const VisionFile &f) {
+Error VisionDevice::load(const VisionFile &f, const VisionDevice *share) {
+    wcache_ = share ? share->wcache_ : std::make_shared<std::map<std::string, void *>>();
     long v = 0;
     if (json_find_int(f.config_json, "Qformer", "encoder_width", &v)) d_.D = (int)v;
     if (json_find_int(f.config_json, "Qformer", "query_length", &v)) d_.n_q = (int)v;
@@ -166,7 +171,9 @@ Error VisionDevice::load(const VisionFile &f) {
 
     CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreate(&ev0_)); CUDA_CHECK(cudaEventCreate(&ev1_));
-    tab_gelu_ = upload_table(0); tab_exp_ = upload_table(1);
+    tab_gelu_ = (__half *)cached("tab:gelu", 131072, [&](void *d) { __half *t = upload_table(0); CUDA_CHECK(cudaMemcpy(d, t, 131072, cudaMemcpyDeviceToDevice)); cudaFree(t); });
+    tab_exp_ = (__half *)cached("tab:exp", 131072, [&](void *d) { __half *t = upload_table(1); CUDA_CHECK(cudaMemcpy(d, t, 131072, cudaMemcpyDeviceToDevice)); cudaFree(t); });
+    weight_bytes_ = 0;
 
     // activations
     img_ = (float *)dalloc((size_t)3 * 224 * 224 * 4);
@@ -202,11 +209,12 @@ Error VisionDevice::load(const VisionFile &f) {
     {   // patch embedding: [D][3*14*14] -> [D][640]
         const HostTensor &pw = f.get(VE, "patch_embed.proj.weight");
         if (pw.nelements() != (int64_t)D * 588) MG4_PANIC("patch_embed.proj.weight must be [14,14,3,%d]", D);
-        __half *raw = (__half *)dalloc((size_t)D * 588 * 2); put16(pw, raw);
-        __half *padded = (__half *)dalloc((size_t)D * 640 * 2);
-        pad_rows_f16_kernel<<<(unsigned)(((size_t)D * 640 + 255) / 256), 256>>>(raw, D, 588, padded, 640);
-        CUDA_CHECK(cudaDeviceSynchronize());
-        weight_bytes_ += (size_t)D * 588 * 2;
+        __half *padded = (__half *)cached("patch_embed.padded", (size_t)D * 640 * 2, [&](void *d) {
+            __half *raw; CUDA_CHECK(cudaMalloc((void **)&raw, (size_t)D * 588 * 2)); put16(pw, raw);
+            CUDA_CHECK(cudaMemset(d, 0, (size_t)D * 640 * 2));
+            pad_rows_f16_kernel<<<(unsigned)(((size_t)D * 640 + 255) / 256), 256>>>(raw, D, 588, (__half *)d, 640);
+            CUDA_CHECK(cudaDeviceSynchronize()); cudaFree(raw);
+        });
         patch_ = add_plan(make_plan(padded, D, 640, patches_, 256, GE_PATCH));
         patch_->a.bias = w32(f, VE, "patch_embed.proj.bias", D); patch_->a.out_f32 = x_; patch_->a.ld_out = D; patch_->a.pos = pos_;
     }
@@ -217,11 +225,13 @@ Error VisionDevice::load(const VisionFile &f) {
         b.n1w = w32(f, VE, p + "norm1.weight", D); b.n1b = w32(f, VE, p + "norm1.bias", D);
         b.n2w = w32(f, VE, p + "norm2.weight", D); b.n2b = w32(f, VE, p + "norm2.bias", D);
         {   // qkv_bias = [q_bias, 0, v_bias] (reference minigpt4.cpp:1259-1262)
-            float *qb = (float *)dalloc((size_t)3 * D * 4);
             const HostTensor &q = f.get(VE, p + "attn.q_bias"), &vb = f.get(VE, p + "attn.v_bias");
-            CUDA_CHECK(cudaMemcpy(qb, q.data, (size_t)D * 4, cudaMemcpyHostToDevice));
-            CUDA_CHECK(cudaMemcpy(qb + 2 * D, vb.data, (size_t)D * 4, cudaMemcpyHostToDevice));
-            b.qkv_bias = qb;
+            b.qkv_bias = (const float *)cached("qkv_bias:" + p, (size_t)3 * D * 4, [&](void *d) {
+                float *qb = (float *)d;
+                CUDA_CHECK(cudaMemset(qb, 0, (size_t)3 * D * 4));
+                CUDA_CHECK(cudaMemcpy(qb, q.data, (size_t)D * 4, cudaMemcpyHostToDevice));
+                CUDA_CHECK(cudaMemcpy(qb + 2 * D, vb.data, (size_t)D * 4, cudaMemcpyHostToDevice));
+            });
         }
         b.qkv = add_plan(make_plan(w16(f, VE, p + "attn.qkv.weight", 3 * D, D), 3 * D, D, ln16_, T, GE_QSCALE));
         b.qkv->a.bias = b.qkv_bias; b.qkv->a.qscale = 1.0f / sqrtf((float)d_.dh); b.qkv->a.qscale_rows = D; b.qkv->a.out_f32 = qkv_; b.qkv->a.ld_out = 3 * D;
@@ -240,17 +250,20 @@ Error VisionDevice::load(const VisionFile &f) {
     const std::string QF = "Qformer";
     qln_w_ = w32(f, QF, "bert.embeddings.LayerNorm.weight", QH); qln_b_ = w32(f, QF, "bert.embeddings.LayerNorm.bias", QH);
     auto cat16 = [&](std::initializer_list<const HostTensor *> ts, int cols) {  // row-concatenate matrices as F16
-        size_t total = 0; for (auto t : ts) { if (t->ne[0] != cols) MG4_PANIC("Q-Former matrix %s must have %d columns", t->name.c_str(), cols); total += (size_t)t->nelements() * 2; }
-        unsigned char *d = (unsigned char *)dalloc(total); size_t off = 0;
-        for (auto t : ts) { put16(*t, (__half *)(d + off)); off += (size_t)t->nelements() * 2; }
-        weight_bytes_ += total;
-        return (const __half *)d;
+        size_t total = 0; std::string key = "cat16";
+        for (auto t : ts) { if (t->ne[0] != cols) MG4_PANIC("Q-Former matrix %s must have %d columns", t->name.c_str(), cols); total += (size_t)t->nelements() * 2; key += ":" + t->name; }
+        return (const __half *)cached(key, total, [&](void *dv) {
+            unsigned char *d = (unsigned char *)dv; size_t off = 0;
+            for (auto t : ts) { put16(*t, (__half *)(d + off)); off += (size_t)t->nelements() * 2; }
+        });
     };
     auto cat32 = [&](std::initializer_list<const HostTensor *> ts) {
-        size_t total = 0; for (auto t : ts) total += t->nbytes;
-        unsigned char *d = (unsigned char *)dalloc(total); size_t off = 0;
-        for (auto t : ts) { CUDA_CHECK(cudaMemcpy(d + off, t->data, t->nbytes, cudaMemcpyHostToDevice)); off += t->nbytes; }
-        return (const float *)d;
+        size_t total = 0; std::string key = "cat32";
+        for (auto t : ts) { total += t->nbytes; key += ":" + t->name; }
+        return (const float *)cached(key, total, [&](void *dv) {
+            unsigned char *d = (unsigned char *)dv; size_t off = 0;
+            for (auto t : ts) { CUDA_CHECK(cudaMemcpy(d + off, t->data, t->nbytes, cudaMemcpyHostToDevice)); off += t->nbytes; }
+        });
     };
     qlayers_.resize((size_t)d_.q_layers);
     for (int i = 0; i < d_.q_layers; ++i) {
@@ -367,7 +380,7 @@ void VisionDevice::record() {
     CUDA_CHECK(cudaGetLastError());
 }
 
-float VisionDevice::encode(const float *image_host, float *out_host) {
+void VisionDevice::encode_begin(const float *image_host) {   // asynchronous: image H2D, the graph, embedding D2H on this lane's stream
     const size_t ib = (size_t)3 * 224 * 224 * 4, ob = (size_t)32 * d_.n_embd_llm * 4;
     memcpy(h_img_, image_host, ib);
     CUDA_CHECK(cudaMemcpyAsync(img_, h_img_, ib, cudaMemcpyHostToDevice, stream_));
@@ -375,12 +388,15 @@ float VisionDevice::encode(const float *image_host, float *out_host) {
     CUDA_CHECK(cudaGraphLaunch(graph_, stream_));
     CUDA_CHECK(cudaEventRecord(ev1_, stream_));
     CUDA_CHECK(cudaMemcpyAsync(h_out_, proj_out_, ob, cudaMemcpyDeviceToHost, stream_));
-    CUDA_CHECK(cudaStreamSynchronize(stream_));
     launches_ += (unsigned long long)graph_kernels_;
-    memcpy(out_host, h_out_, ob);
+}
+float VisionDevice::encode_end(float *out_host) {
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    memcpy(out_host, h_out_, (size_t)32 * d_.n_embd_llm * 4);
     float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
     return ms;
 }
+float VisionDevice::encode(const float *image_host, float *out_host) { encode_begin(image_host); return encode_end(out_host); }
 void VisionDevice::tap_residual(float *dst) { CUDA_CHECK(cudaMemcpy(dst, x_, (size_t)d_.T * d_.D * 4, cudaMemcpyDeviceToHost)); }
 void VisionDevice::tap_ln_vision(float *dst) {
     std::vector<__half> h((size_t)d_.T * d_.D);

@@ -9,6 +9,9 @@
 #pragma once
 #include "formats.h"
 #include <cuda.h>
+#include <functional>
+#include <map>
+#include <memory>
 
 namespace mg4 {
 
@@ -20,10 +23,13 @@ class VisionDevice {
 public:
     VisionDevice();
     ~VisionDevice();
-    Error load(const VisionFile &f);
+    // share != null: a further LANE of the same model (batched encoding): weights are shared with `share`, activations / plans / graph / stream are this lane's own
+    Error load(const VisionFile &f, const VisionDevice *share = nullptr);
     const VisionDims &dims() const { return d_; }
     // image: host F32 CHW [3][224][224]; out: host F32 [32][n_embd_llm].  Synchronous.  Returns device ms of the graph.
     float encode(const float *image_host, float *out_host);
+    void encode_begin(const float *image_host);   // asynchronous half of encode() (several lanes run concurrently) ...
+    float encode_end(float *out_host);            // ... and its synchronising half
     const float *last_embedding_device() const { return proj_out_; }
     // test taps (after encode): 1 = embeddings+pos [T][D] is not kept; 3 = ln_vision out (F16 -> F32) ; 5 = final
     void tap_ln_vision(float *dst);       // [T][D]
@@ -45,6 +51,8 @@ private:
     std::vector<GemmPlan *> plans_;
     std::vector<void *> allocs_;
     void *dalloc(size_t n);
+    std::shared_ptr<std::map<std::string, void *>> wcache_;   // key -> device pointer of a weight (owned by the lane that uploaded it)
+    void *cached(const std::string &key, size_t bytes, const std::function<void(void *)> &fill);
     static void put16(const HostTensor &t, __half *dst);  // any supported matrix type -> F16 on the device
     const __half *w16(const VisionFile &f, const std::string &model, const std::string &name, int rows, int cols);
     const float *w32(const VisionFile &f, const std::string &model, const std::string &name, int n);

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float *__restrict_
     }
 }
 
-// LayerNorm that first folds split-K partial sums into the residual stream (EXPERIMENTAL, with GE_PARTIAL): t = ((x + p0) + p1) + ... in
+// LayerNorm that first folds split-K partial sums into the residual stream (GE_PARTIAL): t = ((x + p0) + p1) + ... in
 // slice order (deterministic), written back to x, then normalised exactly like layernorm_kernel.  One CTA of 128 threads per row.
 __global__ void __launch_bounds__(128) layernorm_fold_kernel(float *__restrict__ x, int rows, int n, const float *__restrict__ w, const float *__restrict__ b,
                                                              __half *__restrict__ out16, const float *__restrict__ parts, int n_parts, long long part_stride) {

@@ -327,6 +327,24 @@ class B200:
         self.base.minigpt4_free_embedding(emb)
         return out
 
+    def encode_batch(self, ctx, images: list) -> tuple[list, float]:
+        """encode float32 CHW [3,224,224] arrays through minigpt4_b200_encode_images (concurrent lanes over shared weights);
+        returns ([32, n_embd] arrays, wall ms of the call) and frees the C buffers"""
+        import time
+        imgs = [np.ascontiguousarray(im, np.float32) for im in images]
+        arr = (MiniGPT4Image * len(imgs))(*[MiniGPT4Image(im.ctypes.data_as(C.c_void_p), 224, 224, 3, ImageFormat.F32) for im in imgs])
+        embs = (MiniGPT4Embedding * len(imgs))()
+        ins, outs = MiniGPT4Images(arr, len(imgs)), MiniGPT4Embeddings(embs, len(imgs))
+        t0 = time.perf_counter()
+        self._chk(self.L.minigpt4_b200_encode_images(ctx.ptr, C.byref(ins), C.byref(outs)))
+        ms = (time.perf_counter() - t0) * 1e3
+        res = []
+        for e in embs:
+            n = e.n_embeddings
+            res.append(np.ctypeslib.as_array(e.data, shape=(n,)).copy().reshape(32, n // 32))
+            self.base.minigpt4_free_embedding(e)
+        return res, ms
+
     # host-only seams (no GPU)
     def host_tokenize(self, llm_path: str, text: str | bytes, add_bos: bool = True) -> list[int]:
         b = text.encode() if isinstance(text, str) else text

@@ -1,20 +1,17 @@
-"""Prepared-but-unmeasured variants (round-2 work).  Skipped unless MG4_EXPERIMENTAL=1:
-
-    MG4_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -m gpu -x -q
-
-* Q4_K / Q5_0 / Q5_1 / Q8_0 LLaMA tensors (device paths behind MINIGPT4_B200_EXPERIMENTAL_TYPES)."""
+"""Device paths of the remaining ggjt block types - Q4_K (dot2_q4k) and Q5_0 / Q5_1 / Q8_0 (dot2_b32), their repack and token-embedding kernels:
+bit-identical to the CPU oracle (first run on hardware in round 2: 68 cases green, profiles/r2_call_block_types.txt)."""
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("MG4_EXPERIMENTAL"), reason="experimental variants: set MG4_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("shape", [(64, 512), (130, 4096), (48, 11008 - 11008 % 256), (33, 256)])
 @pytest.mark.parametrize("n", [1, 3, 8, 11])
 def test_q4_k_matvec_is_bit_identical(ext, orc, mg, shape, n):
-    """Q4_K device path (dot2_q4k, repack_q4k): prepared from the Q5_K kernel minus the fifth bits, never run when it was committed."""
+    """Q4_K device path (dot2_q4k, repack_q4k): the Q5_K kernel minus the fifth bits."""
     rows, cols = shape
     rng = np.random.default_rng(rows * 7 + cols + n)
     raw = mg.synth_quant(rng, 12, rows, cols, 0.02)
@@ -42,7 +39,7 @@ def test_q4_k_llama_file_matches_oracle(ext, orc, mg, tmp_path):
 @pytest.mark.parametrize("shape", [(64, 512), (130, 4096), (48, 11008), (34, 32)])
 @pytest.mark.parametrize("n", [1, 3, 8, 11])
 def test_b32_family_matvec_is_bit_identical(ext, orc, mg, name, gt, shape, n):
-    """Q5_0 / Q5_1 / Q8_0 device path (dot2_b32, repack_b32): prepared against the oracle's canonical order, never run when committed
+    """Q5_0 / Q5_1 / Q8_0 device path (dot2_b32, repack_b32) against the oracle's canonical order
     (the fifth-bit reconstruction was checked by a CPU emulation of the dp4a arithmetic)."""
     rows, cols = shape
     rng = np.random.default_rng(rows * 7 + cols + n + gt)

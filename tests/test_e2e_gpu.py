@@ -127,9 +127,23 @@ def test_vision_gemm_grid_variants(lib, ext, mg, tiny, big_llm, monkeypatch):
     monkeypatch.delenv("MINIGPT4_B200_VISION_TSPLIT"); monkeypatch.delenv("MINIGPT4_B200_VISION_SPLITK")
     a, b, c = ext.encode_array(c_plain, img), ext.encode_array(c_ts, img), ext.encode_array(c_def, img)
     assert np.array_equal(a, b), float(np.abs(a - b).max())
-    assert rel_err(c, a) < 1e-4, rel_err(c, a)
+    assert rel_err(c, a) < 2e-3, rel_err(c, a)   # (F32 sums differ in the last bits; a few LayerNorm outputs then round to the other F16 neighbour)
     assert np.array_equal(c, ext.encode_array(c_def, img))   # no atomics: the same bits every time
     for x in (c_def, c_ts, c_plain): lib.minigpt4_free(x)
+
+
+def test_batched_encode_equals_single_encodes(lib, ext, mg, tiny, big_llm):
+    """minigpt4_b200_encode_images runs the images concurrently on lanes (own activations / graph / stream, shared weights): every embedding must be
+    the bits minigpt4_encode_image produces for that image, for batches smaller than, equal to and larger than the lane count."""
+    c = lib.minigpt4_model_load(tiny["vision"], big_llm, 1, 1, 64, 8, 0)
+    imgs = [mg.synth_image(s) for s in range(11)]
+    single = [ext.encode_array(c, im) for im in imgs]
+    for n in (1, 3, 8, 11):
+        got, _ = ext.encode_batch(c, imgs[:n])
+        assert len(got) == n
+        for a, b in zip(got, single): assert np.array_equal(a, b)
+    assert np.array_equal(ext.encode_array(c, imgs[2]), single[2])   # lane 0 still serves minigpt4_encode_image
+    lib.minigpt4_free(c)
 
 
 def test_queued_prompt_pieces_equal_piecewise_evaluation(ext, tiny):
