@@ -4,7 +4,7 @@
 // Data layout in HBM (owned by this engine; algorithmic bytes == file bytes):
 //   * every quantised matrix is repacked at load into SoA planes so that each warp-level access is a
 //     128-bit aligned vector (Q4_1/Q4_0: row-packed [nb x 16 B nibbles][nb x half2{d,m} | half d] so a run of rows is ONE contiguous range for cp.async.bulk;
-//     Q5_K: qs 128 B + qh 32 B + {scales[12],d,dmin} 16 B; Q6_K: ql 128 B + qh 64 B + scales 16 B + half d)
+//     Q5_K: row-packed [nsb x 128 B qs][nsb x 32 B qh][nsb x 16 B {scales[12],d,dmin}]; Q6_K: ql 128 B + qh 64 B + scales 16 B + half d)
 //   * wq|wk|wv are concatenated row-wise (one launch), w1/w3 are row-interleaved (gate r, up r adjacent)
 //   * KV cache: F16 [layer][n_ctx][n_embd_local] for K and V (token-major; values as in ggml's cache)
 //   * activations between kernels are F32 vectors; each consumer re-quantises them to the weight type's
@@ -21,7 +21,7 @@ struct QMat {          // one repacked weight matrix (or a fused group of matric
     int rows = 0, cols = 0;
     void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
     size_t bytes = 0;  // algorithmic bytes (rows * row_bytes)
-    int row_bytes = 0; // Q4_0/Q4_1 row-packed layout: p0 holds rows of [nb x 16 B nibbles][nb x scales], row_bytes each
+    int row_bytes = 0; // row-packed layouts (p0 holds rows of row_bytes each): Q4_0 / Q4_1 [nb x 16 B nibbles][nb x scales]; Q5_K [nsb x 128 B qs][nsb x 32 B qh][nsb x 16 B {scales, d, dmin}]
 };
 
 struct PQMat {         // prefill operand cache of one Q4_0 / Q4_1 matrix (llama_prefill.cuh): int8, class-major, + {d, m} in the same order

@@ -286,11 +286,11 @@ __device__ __forceinline__ void dot2_q5k(const QMat &w, int r0, const unsigned c
         if (sb < nsb) {
             uint4 qs[2], qh[2], sc[2];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const size_t o = (size_t)(r0 + r) * nsb + sb;
-                qs[r] = ldg_stream((const uint4 *)w.p0 + o * 8 + j * 2 + hf);
-                qh[r] = ldg_stream((const uint4 *)w.p1 + o * 2 + hf);
-                sc[r] = ldg_stream((const uint4 *)w.p2 + o);
+            for (int r = 0; r < 2; ++r) {   // row-packed: [nsb x 128 B qs][nsb x 32 B qh][nsb x 16 B {scales[12], d, dmin}]
+                const unsigned char *row = (const unsigned char *)w.p0 + (size_t)(r0 + r) * (size_t)w.row_bytes;
+                qs[r] = ldg_stream((const uint4 *)row + sb * 8 + j * 2 + hf);
+                qh[r] = ldg_stream((const uint4 *)(row + (size_t)nsb * 128) + sb * 2 + hf);
+                sc[r] = ldg_stream((const uint4 *)(row + (size_t)nsb * 160) + sb);
             }
             int lo[2][4], hi[2][4]; float dd[2], dmin[2]; int sca[2], scb[2], mna[2], mnb[2];
 #pragma unroll
@@ -883,16 +883,17 @@ __global__ void repack_q4(const unsigned char *src, int src_nb, int blk0, int nb
     if (q41) ((unsigned *)sc)[dst_blk0 + b] = p[0] | (p[1] << 8) | (p[2] << 16) | ((unsigned)p[3] << 24);
     else ((unsigned short *)sc)[dst_blk0 + b] = (unsigned short)(p[0] | (p[1] << 8));
 }
-__global__ void repack_q5k(const unsigned char *src, int src_nb, int blk0, int nblk, int rows, unsigned char *qs, unsigned char *qh, unsigned char *sc, int dst_nb, int row_mul, int row_off, int dst_blk0) {
+__global__ void repack_q5k(const unsigned char *src, int src_nb, int blk0, int nblk, int rows, unsigned char *dst, int dst_nb, int dst_row_bytes, int row_mul, int row_off, int dst_blk0) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * nblk) return;
     const int r = (int)(i / nblk), b = (int)(i % nblk);
-    const unsigned char *p = src + ((size_t)r * src_nb + blk0 + b) * 176;
-    const size_t o = (size_t)(r * row_mul + row_off) * dst_nb + dst_blk0 + b;
-    for (int j = 0; j < 128; ++j) qs[o * 128 + j] = p[48 + j];
-    for (int j = 0; j < 32; ++j) qh[o * 32 + j] = p[16 + j];
-    for (int j = 0; j < 12; ++j) sc[o * 16 + j] = p[4 + j];
-    for (int j = 0; j < 4; ++j) sc[o * 16 + 12 + j] = p[j];
+    const unsigned char *p = src + ((size_t)r * src_nb + blk0 + b) * 176;   // block_q5_K: d, dmin, scales[12], qh[32], qs[128]
+    unsigned char *row = dst + (size_t)(r * row_mul + row_off) * (size_t)dst_row_bytes;   // row-packed: [nb x qs][nb x qh][nb x {scales, d, dmin}]
+    unsigned char *qs = row + (size_t)(dst_blk0 + b) * 128, *qh = row + (size_t)dst_nb * 128 + (size_t)(dst_blk0 + b) * 32, *sc = row + (size_t)dst_nb * 160 + (size_t)(dst_blk0 + b) * 16;
+    for (int j = 0; j < 128; ++j) qs[j] = p[48 + j];
+    for (int j = 0; j < 32; ++j) qh[j] = p[16 + j];
+    for (int j = 0; j < 12; ++j) sc[j] = p[4 + j];
+    for (int j = 0; j < 4; ++j) sc[12 + j] = p[j];
 }
 __global__ void repack_b32(int type, const unsigned char *src, int src_nb, int blk0, int nblk, int rows, unsigned char *p0, unsigned char *p1, unsigned char *p2, int dst_nb, int row_mul, int row_off, int dst_blk0) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -309,6 +309,127 @@ __device__ __forceinline__ Acc4 dot2_q4_reg(const unsigned char *row0, const uns
     return r;
 }
 
+// ---- K-quant weights (Q5_K): Q8_K activations -------------------------------------------------------------------------------------------
+// Staged layout = k::stage_act<ACT_Q8_K>: [int8 q: cols][float d: cols / 256][int16 bsums: cols / 16].  Per 256-element super-block (ggml
+// quantize_row_q8_K): max = the element of largest |x| (first index on ties), iscale = -128 / max, q = min(127, rint(iscale x)), d = 1 / iscale,
+// bsums = sums of 16 q.  One warp per super-block (lane l: elements 8 l .. 8 l + 7), all 15 warps; RMS-normed inputs: warps 0-7 first form the
+// canonical sum of squares (stage_norm_k), every warp folds the 16 warp sums.  Identical bytes to k::stage_act.
+constexpr int kQ8kRounds = 4;   // super-blocks per warp: cols <= 15 x 4 x 256 = 15360
+__device__ __forceinline__ void stage_q8k(const float *__restrict__ x, const float *__restrict__ nw, int cols, unsigned char *sm, double *red, bool pow2, double inv_cols, long long *tr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nsb = cols >> 8;  // tid < 480
+    constexpr int kNormRounds = 2;   // RMS-normed inputs are n_embd wide: <= 15 x 2 x 256 = 7680
+    float4 xa[kQ8kRounds], xb[kQ8kRounds], wa[kNormRounds], wb[kNormRounds];
+#pragma unroll
+    for (int k = 0; k < kQ8kRounds; ++k) {   // this warp's super-blocks warp, warp + 15, ...: all loads in flight at once
+        const int sb = warp + kConsumerWarps * k;
+        const bool on = sb < nsb;
+        const int i = sb * 256 + lane * 8;
+        xa[k] = on ? __ldcg((const float4 *)(x + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xb[k] = on ? __ldcg((const float4 *)(x + i + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < kNormRounds) { if (nw) { wa[k] = on ? __ldg((const float4 *)(nw + i)) : make_float4(0.f, 0.f, 0.f, 0.f); wb[k] = on ? __ldg((const float4 *)(nw + i + 4)) : make_float4(0.f, 0.f, 0.f, 0.f); } }
+    }
+    float scale = 1.0f;
+    if (nw) {
+        if (warp < 8) {
+            double ssa = 0.0, ssb = 0.0;
+#pragma unroll
+            for (int it = 0; it < kNormItems; ++it) {
+                const int i = 1024 * it + 4 * tid;
+                if (i < cols) {
+                    const float4 a = __ldcg((const float4 *)(x + i));
+                    if (it & 1) { ssb += (double)(a.x * a.x); ssb += (double)(a.y * a.y); ssb += (double)(a.z * a.z); ssb += (double)(a.w * a.w); }
+                    else        { ssa += (double)(a.x * a.x); ssa += (double)(a.y * a.y); ssa += (double)(a.z * a.z); ssa += (double)(a.w * a.w); }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const double ta = __shfl_xor_sync(0xffffffffu, ssa, o), tb = __shfl_xor_sync(0xffffffffu, ssb, o); ssa += ta; ssb += tb; }
+            if (lane == 0) { red[warp] = ssa; red[warp + 8] = ssb; }
+        }
+        consumer_sync();
+        double t = lane < 16 ? red[lane] : 0.0;
+        t = warp_sum(t);
+        const float mean = pow2 ? (float)(t * inv_cols) : (float)(t / (double)cols);
+        scale = 1.0f / sqrtf(mean + 1e-6f);
+    }
+    if (tr) tr[8] = clock64();
+    int8_t *qs = (int8_t *)sm; float *d = (float *)(sm + cols); int16_t *bs = (int16_t *)(sm + cols + nsb * 4);
+#pragma unroll
+    for (int k = 0; k < kQ8kRounds; ++k) {
+        const int sb = warp + kConsumerWarps * k;
+        if (sb < nsb) {   // (warp-uniform)
+            float v[8] = {xa[k].x, xa[k].y, xa[k].z, xa[k].w, xb[k].x, xb[k].y, xb[k].z, xb[k].w};
+            if (k < kNormRounds) {
+                if (nw) {
+                    const float w8[8] = {wa[k < kNormRounds ? k : 0].x, wa[k < kNormRounds ? k : 0].y, wa[k < kNormRounds ? k : 0].z, wa[k < kNormRounds ? k : 0].w,
+                                         wb[k < kNormRounds ? k : 0].x, wb[k < kNormRounds ? k : 0].y, wb[k < kNormRounds ? k : 0].z, wb[k < kNormRounds ? k : 0].w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = (v[j] * scale) * w8[j];
+                }
+            }
+            float amax = 0.f, mx = 0.f; int mi = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float a = fabsf(v[j]); if (a > amax) { amax = a; mx = v[j]; mi = lane * 8 + j; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {  // first-index arg-max of |x| (strict > in the sequential reference)
+                const float oa = __shfl_xor_sync(0xffffffffu, amax, o), om = __shfl_xor_sync(0xffffffffu, mx, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+                if (oa > amax || (oa == amax && oi < mi)) { amax = oa; mx = om; mi = oi; }
+            }
+            int q[8]; int sum = 0;
+            const float iscale = amax != 0.f ? -128.f / mx : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { int t = __float2int_rn(iscale * v[j]); t = t < 127 ? t : 127; q[j] = t; sum += t; }
+            if (amax == 0.f) sum = 0;
+            const unsigned w0 = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((unsigned)(q[3] & 0xff) << 24);
+            const unsigned w1 = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((unsigned)(q[7] & 0xff) << 24);
+            *(uint2 *)(qs + sb * 256 + lane * 8) = make_uint2(w0, w1);
+            const int s2 = sum + __shfl_xor_sync(0xffffffffu, sum, 1);
+            if ((lane & 1) == 0) bs[sb * 16 + (lane >> 1)] = (int16_t)s2;
+            if (lane == 0) d[sb] = amax != 0.f ? 1.0f / iscale : 0.f;
+        }
+    }
+}
+// Two Q5_K rows in shared memory (row = [nsb x 128 B qs][nsb x 32 B qh][nsb x 16 B {scales[12], d, dmin}]) against the staged Q8_K vector: the
+// lane mapping (8 lanes per super-block, 4 super-blocks per pass), integer arithmetic and float order of k::dot2_q5k.  Result = sum d - sum m.
+__device__ __forceinline__ Acc4 dot2_q5k_smem(const unsigned char *row0, const unsigned char *row1, int nsb, int cols, const unsigned char *act, int lane) {
+    const int sub = lane >> 3, j = (lane & 7) >> 1, hf = lane & 1;
+    const float *ad = (const float *)(act + cols);
+    const int16_t *abs_ = (const int16_t *)(act + cols + nsb * 4);
+    Acc4 r{0.f, 0.f, 0.f, 0.f};
+    for (int sb0 = 0; sb0 < nsb; sb0 += 4) {
+        const int sb = sb0 + sub;
+        if (sb < nsb) {
+            const int4 a0 = *(const int4 *)(act + sb * 256 + 64 * j + 16 * hf);
+            const int4 a1 = *(const int4 *)(act + sb * 256 + 64 * j + 32 + 16 * hf);
+            const float d8 = ad[sb];
+            const int b0 = abs_[sb * 16 + 4 * j + hf], b1 = abs_[sb * 16 + 4 * j + 2 + hf];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const unsigned char *row = rr ? row1 : row0;
+                const uint4 qs = *((const uint4 *)row + sb * 8 + j * 2 + hf);
+                const uint4 qh = *((const uint4 *)(row + (size_t)nsb * 128) + sb * 2 + hf);
+                const uint4 sc = *((const uint4 *)(row + (size_t)nsb * 160) + sb);
+                const unsigned qv[4] = {qs.x, qs.y, qs.z, qs.w}, hv[4] = {qh.x, qh.y, qh.z, qh.w};
+                int lo[4], hi[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    lo[i] = (int)((qv[i] & 0x0F0F0F0Fu) | (((hv[i] >> (2 * j)) & 0x01010101u) << 4));
+                    hi[i] = (int)(((qv[i] >> 4) & 0x0F0F0F0Fu) | (((hv[i] >> (2 * j + 1)) & 0x01010101u) << 4));
+                }
+                int sca, scb, mna, mnb;
+                const unsigned char *sp = (const unsigned char *)&sc;
+                scale_min_k4(sp, 2 * j, sca, mna); scale_min_k4(sp, 2 * j + 1, scb, mnb);
+                const float2 f = __half22float2(*(const __half2 *)&sc.w);
+                int s0 = __dp4a(lo[0], a0.x, 0); s0 = __dp4a(lo[1], a0.y, s0); s0 = __dp4a(lo[2], a0.z, s0); s0 = __dp4a(lo[3], a0.w, s0);
+                int s1 = __dp4a(hi[0], a1.x, 0); s1 = __dp4a(hi[1], a1.y, s1); s1 = __dp4a(hi[2], a1.z, s1); s1 = __dp4a(hi[3], a1.w, s1);
+                const float dv = (f.x * d8) * (float)(sca * s0 + scb * s1), mv = (f.y * d8) * (float)(mna * b0 + mnb * b1);
+                if (rr) { r.d1 += dv; r.m1 += mv; } else { r.d0 += dv; r.m0 += mv; }
+            }
+        }
+    }
+    return r;
+}
+
 // shared memory carve-up (dynamic): [2 W slots][act][2 W "full" mbarriers]
 struct Smem6 { unsigned char *slots, *actb; uint64_t *full; };
 __device__ __forceinline__ Smem6 carve6(const Params6 &P) {
@@ -352,8 +473,9 @@ __device__ __forceinline__ void fill_one(const Params6 &P, const Smem6 &m, const
 
 // The matvec phase of one op for one stream warp: for each of its row pairs wait for the slot(s), dot, re-arm the slot(s), reduce, epilogue.
 //   cc = slot-loads this warp has consumed so far: load n sits in slot n & 1 and completes phase (n >> 1) & 1 of that slot's barrier.
-template <bool Q41, int KIND, int NBL, bool TRACE>
+template <int WT, int KIND, int NBL, bool TRACE>
 __device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const int2 *share, int oi, Fill &f, unsigned &cc, int pos, long long *tr) {
+    constexpr bool Q41 = WT == GG_Q4_1, Q5K = WT == GG_Q5_K;
     const Op6 &op = P.ops[oi];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int W = P.W;
@@ -364,7 +486,7 @@ __device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const
     const unsigned rb = (unsigned)op.row_bytes;
     // n_embd-wide RMS-normed inputs (qkv, gate/up, output) are held in registers; wo (8 % of the bytes; El wide under tensor parallelism) and
     // down read the staged vector from shared memory
-    constexpr bool REG = NBL > 0 && KIND != OP_DOWN && KIND != OP_WO;
+    constexpr bool REG = !Q5K && NBL > 0 && KIND != OP_DOWN && KIND != OP_WO;
     ActRegs<REG ? NBL : 1> ar;
     if (REG) load_act_regs<REG ? NBL : 1>(m.actb, cols, lane, ar);
     unsigned char *const slot0 = m.slots + (size_t)(2 * warp) * P.slot_bytes;
@@ -391,7 +513,8 @@ __device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const
         cc += (unsigned)parts;
         if (TRACE && tr) tw1 = clock64();
         Acc4 a;
-        if (REG) a = dot2_q4_reg<Q41, REG ? NBL : 1>(row0, row1, ar, lane);
+        if (Q5K) a = dot2_q5k_smem(row0, row1, cols >> 8, cols, m.actb, lane);
+        else if (REG) a = dot2_q4_reg<Q41, REG ? NBL : 1>(row0, row1, ar, lane);
         else a = dot2_q4_smem<Q41>(row0, row1, nb, cols, m.actb, lane);
         // Butterfly reductions of the four partial sums, PACKED: stage 16 leaves (d, m) of row 0 in lanes 0-15 and of row 1 in lanes 16-31,
         // stage 8 leaves one quantity per lane (d in lanes with bit 3 clear, m in the others), stages 4-2-1 are plain.  Every surviving lane
@@ -408,7 +531,7 @@ __device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const
         z += __shfl_xor_sync(0xffffffffu, z, 4); z += __shfl_xor_sync(0xffffffffu, z, 2); z += __shfl_xor_sync(0xffffffffu, z, 1);
         // lanes 0-7: sum d of row 0, 8-15: sum m of row 0, 16-23: sum d of row 1, 24-31: sum m of row 1
         const float zz = __shfl_xor_sync(0xffffffffu, z, 8);
-        const float v = z + zz;                              // lane 0: row 0 = warp_sum(d0) + warp_sum(m0); lane 16: row 1
+        const float v = Q5K ? z - zz : z + zz;              // lane 0: row 0 = warp_sum(d0) + warp_sum(m0) (Q5_K: minus, the mins term); lane 16: row 1
         const float v1 = __shfl_xor_sync(0xffffffffu, v, 16), v0 = v;
         if (lane == 0) {
             if (KIND == OP_QKV) {
@@ -570,7 +693,6 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel6(const __grid_c
     __shared__ float part[16 * 128];
     __shared__ int2 share[8];   // this CTA's contiguous share [lo, hi) of the row pairs of each op kind
     constexpr int ACT = act_of(WT);
-    constexpr bool Q41 = WT == GG_Q4_1;
     const Smem6 m = carve6(P);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
@@ -672,8 +794,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel6(const __grid_c
             grid_barrier(P.barrier, bar_target);
             if (TRACE && tr) tr[1] = clock64();
             const float *src = kind == OP_WO ? P.att : kind == OP_DOWN ? P.act : P.x;
-            if (nw) { if (tid < 256) stage_norm<ACT>(src, nw, cols, m.actb, red, P.E_pow2 != 0, P.inv_E, TRACE ? tr : nullptr); }
-            else stage_plain<ACT>(src, cols, m.actb);
+            if (ACT == ACT_Q8_K) stage_q8k(src, nw, cols, m.actb, red, P.E_pow2 != 0, P.inv_E, TRACE ? tr : nullptr);
+            else if (nw) { if (tid < 256) stage_norm<ACT == ACT_Q8_K ? ACT_Q8_1 : ACT>(src, nw, cols, m.actb, red, P.E_pow2 != 0, P.inv_E, TRACE ? tr : nullptr); }
+            else stage_plain<ACT == ACT_Q8_K ? ACT_Q8_1 : ACT>(src, cols, m.actb);
             if (TRACE && tr) tr[9] = clock64();
             consumer_sync();
             if (TRACE && tr) tr[2] = clock64();
@@ -683,11 +806,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel6(const __grid_c
             touch_kv_head(P.kcache + lo, P.vcache + lo, P.tab_exp, pos, cta, P.El);
         }
         switch (kind) {
-            case OP_QKV:    consume6<Q41, OP_QKV, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
-            case OP_WO:     consume6<Q41, OP_WO, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
-            case OP_GATEUP: consume6<Q41, OP_GATEUP, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
-            case OP_DOWN:   consume6<Q41, OP_DOWN, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
-            default:        consume6<Q41, OP_OUTPUT, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
+            case OP_QKV:    consume6<WT, OP_QKV, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
+            case OP_WO:     consume6<WT, OP_WO, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
+            case OP_GATEUP: consume6<WT, OP_GATEUP, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
+            case OP_DOWN:   consume6<WT, OP_DOWN, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
+            default:        consume6<WT, OP_OUTPUT, NBL, TRACE>(P, m, share, oi, f, cc, pos, tr); break;
         }
         if (TRACE && tr) tr[3] = clock64();  // (thread 0 = warp 0 only; other warps may still be consuming)
     }

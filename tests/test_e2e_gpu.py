@@ -91,14 +91,14 @@ def test_batch_invariance_and_chain(ext, tiny):
 
 
 def test_megakernel_equals_per_op_path(ext, orc, tiny, monkeypatch):
-    """The persistent one-launch-per-token megakernel (homogeneous Q4_0/Q4_1) and the per-op graph are the same function."""
-    import os
-    for wt in ("q4_1", "q4_0"):
+    """The persistent one-launch-per-token megakernel (homogeneous Q4_0 / Q4_1 / Q5_K) and the per-op graph are the same function."""
+    for wt in ("q4_1", "q4_0", "q5_k"):
         ids = list(range(7, 19))
         monkeypatch.setenv("MINIGPT4_B200_NO_MEGAKERNEL", "1")
         c1 = ext.llm_load(tiny[wt], n_ctx=128)
         monkeypatch.delenv("MINIGPT4_B200_NO_MEGAKERNEL")
         c2 = ext.llm_load(tiny[wt], n_ctx=128)
+        assert ext.stats(c1).decode_megakernel == 0 and ext.stats(c2).decode_megakernel >= 6
         e = orc.OracleEngine(None, tiny[wt], n_ctx=128)
         ext.eval_tokens(c1, ids); ext.eval_tokens(c2, ids); e.eval_tokens(ids)
         for _ in range(24):  # single-token steps go through the decode graph: per-op kernels (c1) vs megakernel (c2)

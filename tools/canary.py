@@ -14,7 +14,9 @@ ok = True
 with tempfile.TemporaryDirectory() as d:
     cases = [("q4_1", dict(n_vocab=1024, n_embd=512, n_head=4, n_layer=2), 230, 12),
              ("q4_0", dict(n_vocab=1024, n_embd=512, n_head=4, n_layer=2), 40, 12),
-             ("q4_1", dict(n_vocab=2048, n_embd=4096, n_head=32, n_layer=2), 180, 20)]
+             ("q4_1", dict(n_vocab=2048, n_embd=4096, n_head=32, n_layer=2), 180, 20),
+             ("q5_k", dict(n_vocab=1024, n_embd=512, n_head=4, n_layer=2), 200, 12),
+             ("q5_k", dict(n_vocab=2048, n_embd=4096, n_head=32, n_layer=2), 60, 12)]
     for wt, dims, n_prompt, n_gen in cases:
         p = f"{d}/llama-{wt}-{dims['n_embd']}.bin"
         mg.write_llama_ggjt(p, mg.LlamaSpec(wtype=wt, **dims))
