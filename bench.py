@@ -406,7 +406,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "engine": {"decode_megakernel_generation": int(st.decode_megakernel), "prefill_gemm": int(getattr(st, "prefill_gemm", 0))}}
 
-    if world > 1:
+    if world > 1 and os.environ.get("MINIGPT4_BENCH_TP", "1") != "0":
         # the tensor-parallel LLaMA step of north_star on the same GPUs (strong scaling: ONE stream over all ranks), measured next to the
         # replica number: 32-row prefix + N_GEN chained greedy tokens, CUDA events, max over ranks; parity against this rank's own 1-GPU context
         import torch
@@ -422,7 +422,7 @@ def main():
         ext.eval_embd(c_tp, rows); lg_tp = ext.logits(c_tp)
         ids_tp, _ = ext.decode_chain(c_tp, N_GEN)                      # warm-up pass (also the parity ids)
         tp_ms = []
-        for _ in range(max(1, args.steps)):
+        for _ in range(max(1, min(3, args.steps))):
             lib.minigpt4_reset_chat(c_tp)
             ext.eval_embd(c_tp, rows); ext.flush(c_tp)
             torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -430,20 +430,22 @@ def main():
         ar_us, peer = ext.tp_time_allreduce(c_tp, 64)
         t = torch.tensor([sum(tp_ms), ar_us], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tp_total_ms, ar_us = t.tolist()
+        st_tp = ext.stats(c_tp)
+        fused = bool(st_tp.decode_megakernel)
         tp_rec = {"world": world, "value": len(tp_ms) * N_GEN / (tp_total_ms * 1e-3), "unit": "tokens/s", "scaling": "strong",
                   "ms_per_token": tp_total_ms / (len(tp_ms) * N_GEN),
-                  "collective": ("one-shot peer-memory all-reduce fused with the residual add (CUDA IPC mappings, loads over NVLink; 2 per layer)" if peer
-                                 else "ncclAllReduce + add kernel (2 per layer)"),
-                  "allreduce_us": ar_us, "allreduce_us_per_token": ar_us * 2 * st.n_layer,
-                  "weight_bytes_per_token_per_gpu": ext.stats(c_tp).llm_weight_bytes_per_token}
+                  "path": ("decode megakernel with the all-reduce INSIDE the kernel (OP_REDUCE: flag stores to the peers, partial sums read straight out of peer "
+                           "memory over NVLink, 2 per layer)" if fused else
+                           "per-op kernels + " + ("one-shot peer-memory all-reduce kernel fused with the residual add (CUDA IPC mappings, loads over NVLink)" if peer
+                                                  else "ncclAllReduce + add kernel") + ", 2 per layer"),
+                  "standalone_allreduce_us": ar_us, "allreduces_per_token": 2 * st.n_layer,
+                  "weight_bytes_per_token_per_gpu": st_tp.llm_weight_bytes_per_token,
+                  "hbm_roofline_frac_per_gpu": st_tp.llm_weight_bytes_per_token / (tp_total_ms / (len(tp_ms) * N_GEN) * 1e-3) * 1e-9 / peak}
         if c1 is not None:   # parity of TP against the 1-GPU engine on identical inputs (float order of the partial sums differs: tolerance, not bits)
             lib.minigpt4_reset_chat(c1)
             ext.eval_embd(c1, rows); lg1 = ext.logits(c1)
             ids1, _ = ext.decode_chain(c1, N_GEN)
-            n_same = 0
-            for a, b in zip(ids_tp.tolist(), ids1.tolist()):
-                if a != b: break
-                n_same += 1
+            n_same = next((i for i, (a, b) in enumerate(zip(ids_tp.tolist(), ids1.tolist())) if a != b), N_GEN)
             tp_rec["parity_vs_1gpu"] = {"logits_rel_err_after_prefix": float(np.abs(lg_tp - lg1).max() / np.abs(lg1).max()), "bar": 1e-2,
                                         "leading_greedy_ids_equal": n_same, "of": N_GEN}
             lib.minigpt4_free(c_tp)

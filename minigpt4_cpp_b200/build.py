@@ -2,6 +2,7 @@
 ctypes loader looks: reference minigpt4/minigpt4_library.py:539-566)."""
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import subprocess
@@ -34,31 +35,38 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and OUT.exists() and stamp.exists() and stamp.read_text() == dig:
         return OUT
     OUT.parent.mkdir(parents=True, exist_ok=True)
-    objs = []
-    procs = []
-    for s in SOURCES:
-        o = OUT.parent / (s + ".o")
-        cmd = [NVCC, *FLAGS, "-x", "cu", "-c", str(CSRC / s), "-o", str(o)]
-        if verbose:
-            print(" ".join(cmd))
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(str(o))
-    failed = False
-    for s, p in procs:
-        out, _ = p.communicate()
-        if p.returncode != 0:
-            failed = True
-            sys.stderr.write(f"--- nvcc failed on {s} ---\n{out}\n")
-        elif verbose and out.strip():
-            print(out)
-    if failed:
-        raise RuntimeError("libminigpt4.so: compilation failed")
-    link = [NVCC, "-ccbin", "/usr/bin/g++", "-shared", "-o", str(OUT), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-            "-Xlinker", "--no-undefined", "-ldl", "-lpthread", "-cudart", "static"]
-    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("libminigpt4.so: link failed\n" + r.stdout)
-    stamp.write_text(dig)
+    # several ranks of one torchrun may get here together: one builds (into private object names, the .so is renamed into place), the others wait
+    with open(OUT.parent / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and OUT.exists() and stamp.exists() and stamp.read_text() == dig:
+            return OUT
+        objs = []
+        procs = []
+        for s in SOURCES:
+            o = OUT.parent / (s + ".o")
+            cmd = [NVCC, *FLAGS, "-x", "cu", "-c", str(CSRC / s), "-o", str(o)]
+            if verbose:
+                print(" ".join(cmd))
+            procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            objs.append(str(o))
+        failed = False
+        for s, p in procs:
+            out, _ = p.communicate()
+            if p.returncode != 0:
+                failed = True
+                sys.stderr.write(f"--- nvcc failed on {s} ---\n{out}\n")
+            elif verbose and out.strip():
+                print(out)
+        if failed:
+            raise RuntimeError("libminigpt4.so: compilation failed")
+        tmp = OUT.with_suffix(f".so.tmp{os.getpid()}")
+        link = [NVCC, "-ccbin", "/usr/bin/g++", "-shared", "-o", str(tmp), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                "-Xlinker", "--no-undefined", "-ldl", "-lpthread", "-cudart", "static"]
+        r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("libminigpt4.so: link failed\n" + r.stdout)
+        os.replace(tmp, OUT)
+        stamp.write_text(dig)
     return OUT
 
 

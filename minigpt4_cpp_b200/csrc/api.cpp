@@ -140,7 +140,7 @@ int minigpt4_b200_tokenize(struct MiniGPT4Context *ctx, const char *text, int ad
     memcpy(out, t.data(), t.size() * sizeof(int32_t));
     return (int)t.size();
 }
-int minigpt4_b200_eval_tokens(struct MiniGPT4Context *ctx, const int32_t *ids, int n) { return E(ctx)->add_tokens(std::vector<int32_t>(ids, ids + n)); }
+int minigpt4_b200_eval_tokens(struct MiniGPT4Context *ctx, const int32_t *ids, int n) { return n <= 0 ? 0 : E(ctx)->add_tokens(std::vector<int32_t>(ids, ids + n)); }
 int minigpt4_b200_eval_embd(struct MiniGPT4Context *ctx, const float *rows, int n) { return E(ctx)->add_embedding(rows, n); }
 int minigpt4_b200_flush(struct MiniGPT4Context *ctx) { return E(ctx)->flush() ? 0 : ErrFailedToAddString; }
 int minigpt4_b200_get_logits(struct MiniGPT4Context *ctx, float *out) { E(ctx)->flush(); E(ctx)->llm().logits_to_host(out); return 0; }

@@ -74,7 +74,7 @@ bool MappedFile::open(const std::string &path) {
 // bounds-checked little-endian cursor
 struct Cursor {
     const uint8_t *b; size_t n; size_t pos = 0; bool ok = true;
-    bool need(size_t k) { if (pos + k > n) { ok = false; return false; } return true; }
+    bool need(size_t k) { if (pos > n || k > n - pos) { ok = false; return false; } return true; }   // (no pos + k: a damaged size must not wrap)
     int32_t s4() { int32_t v = 0; if (need(4)) { memcpy(&v, b + pos, 4); pos += 4; } return v; }
     uint32_t u4() { return (uint32_t)s4(); }
     float f4() { float v = 0; if (need(4)) { memcpy(&v, b + pos, 4); pos += 4; } return v; }
@@ -125,9 +125,10 @@ Error VisionFile::load(const std::string &path) {
             t.name = c.lstr();
             t.n_dims = c.s4();
             if (!c.ok || t.n_dims < 0 || t.n_dims > 4) return ErrLoadModelFileHeader;
-            for (int d = 0; d < t.n_dims; ++d) t.ne[d] = c.s4();
+            for (int d = 0; d < t.n_dims; ++d) { t.ne[d] = c.s4(); if (t.ne[d] <= 0) return ErrLoadModelFileHeader; }   // (a negative extent would wrap nbytes)
             t.gg = container_dtype_to_gg(c.s4());
             if (t.gg < 0) return ErrLoadModelMiniGPT4DataType;
+            if (t.n_dims > 0 && t.ne[0] % (int64_t)gg_block_elems(t.gg)) return ErrLoadModelFileHeader;
         }
         auto &dst = models[mname];
         model_order.push_back(mname);
@@ -168,7 +169,7 @@ bool LlamaFile::load(const std::string &path) {
         HostTensor t;
         t.n_dims = (int)c.u4(); uint32_t name_len = c.u4(); t.gg = (int)c.u4();
         if (!c.ok || t.n_dims < 1 || t.n_dims > 2 || gg_block_bytes(t.gg) == 0) return false;
-        for (int d = 0; d < t.n_dims; ++d) t.ne[d] = c.u4();
+        for (int d = 0; d < t.n_dims; ++d) { t.ne[d] = c.u4(); if (t.ne[d] <= 0 || t.ne[d] > (int64_t)1 << 31) return false; }
         t.name = c.str(name_len);
         c.pos = (c.pos + 31) & ~(size_t)31;
         if (t.ne[0] % (int64_t)gg_block_elems(t.gg)) return false;

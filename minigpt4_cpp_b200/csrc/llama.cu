@@ -1,6 +1,5 @@
 // llama.cu — host side of the device-resident LLaMA step (see llama.h, llama_kernels.cuh).
 #include "llama_kernels.cuh"
-#include "llama_mega.cuh"
 #include "llama_mega6.cuh"
 #include "llama_prefill.cuh"
 #include "tp.h"
@@ -16,10 +15,11 @@ static size_t g_max_dyn_smem = 0;
 
 template <int WT, int NT>
 static void launch_mv(const MatvecArgs &a, int grid, size_t smem, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};   // the attribute is per device (minigpt4_b200_set_device: several contexts of one process may sit on different GPUs)
+    int dev = 0; cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         CUDA_CHECK(cudaFuncSetAttribute(matvec_kernel<WT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_dyn_smem));
-        configured = true;
+        configured[dev & 63] = true;
     }
     matvec_kernel<WT, NT><<<grid, kThreads, smem, s>>>(a);
 }
@@ -152,10 +152,8 @@ LlamaDevice::~LlamaDevice() {
                     (void *)act_, (void *)logits_, (void *)partial_, (void *)qact_, (void *)embd_in_, (void *)state_}) if (p) cudaFree(p);
     for (auto &L : layers_) for (PQMat *m : {&L.pqkv, &L.pwo, &L.pw13, &L.pw2}) { if (m->q) cudaFree(m->q); if (m->sc) cudaFree(m->sc); }
     for (void *p : {(void *)pf_q8_, pf_sc_, (void *)tok_ids_, pf_part_}) if (p) cudaFree(p);
-    if (mega_ops_) cudaFree(mega_ops_);
     if (mega_barrier_) cudaFree(mega_barrier_);
     if (mega_trace_) cudaFree(mega_trace_);
-    delete (mk::MegaParams *)mega_params_;
     delete (mk6::Params6 *)mega6_params_;
     if (h_state_) cudaFreeHost(h_state_);
     if (h_argmax_) cudaFreeHost(h_argmax_);
@@ -173,6 +171,7 @@ bool LlamaDevice::load(const LlamaFile &f, int n_ctx, TPLink *tp) {
     d_.n_vocab = (int)f.n_vocab; d_.n_embd = (int)f.n_embd; d_.n_head = (int)f.n_head; d_.n_layer = (int)f.n_layer;
     d_.n_ff = (int)f.n_ff(); d_.n_ctx = n_ctx; d_.head_dim = d_.n_embd / d_.n_head;
     if (d_.head_dim != 128 || (int)f.n_rot != 128) { MG4_ERR("only head_dim 128 LLaMA models are supported (got %d)", d_.head_dim); return false; }
+    if (n_ctx < 8 || n_ctx > 32768) { MG4_ERR("n_ctx %d is outside the supported range 8 .. 32768 (attention scratch = 6 n_ctx bytes of shared memory)", n_ctx); return false; }
     if (d_.n_head % world || d_.n_ff % (32 * world)) { MG4_ERR("tensor-parallel degree %d does not divide the model", world); return false; }
     n_head_local_ = d_.n_head / world; n_embd_local_ = n_head_local_ * 128; n_ff_local_ = d_.n_ff / world;
     const int E = d_.n_embd, El = n_embd_local_, FF = d_.n_ff, FFl = n_ff_local_;
@@ -268,6 +267,7 @@ bool LlamaDevice::load(const LlamaFile &f, int n_ctx, TPLink *tp) {
     CUDA_CHECK(cudaHostAlloc((void **)&h_state_, sizeof(DeviceState), cudaHostAllocDefault)); memset(h_state_, 0, sizeof(DeviceState));
     CUDA_CHECK(cudaHostAlloc((void **)&h_argmax_, 64, cudaHostAllocDefault)); *h_argmax_ = 0;
     CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(49152, d_.n_ctx * 6)));
     if (tp_ && tp_->world > 1) tp_->setup_peers(E, stream_);
     pf_ready_ = build_prefill();
     build_graph();
@@ -492,7 +492,7 @@ bool LlamaDevice::build_prefill() {
     make_map_u8(pf_tmS_e_, pf_sc_, R, pitch_e / 4, 32, pf::kTok, false);
     make_map_u8(pf_tmB_ff_, pf_q8_, R, pitch_ff, 128, pf::kTok, true);
     make_map_u8(pf_tmS_ff_, pf_sc_, R, pitch_ff / 4, 32, pf::kTok, false);
-    pf_part_bytes_ = (size_t)48 << 20;   // roots of K-split slices: [slice][token][row] {d-tree, m-tree}
+    pf_part_bytes_ = (size_t)96 << 20;   // roots of K-split slices: [slice][token][row] {d-tree, m-tree}
     CUDA_CHECK(cudaMalloc(&pf_part_, pf_part_bytes_));
     const size_t smem = 1024 + (size_t)pf::kStages * pf::kStageBytes + pf::kStackBytes + 256;
     CUDA_CHECK(cudaFuncSetAttribute(pf::prefill_gemm_q4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -522,8 +522,15 @@ void LlamaDevice::prefill_chunk(int n, bool want_logits) {
         // K split over subtrees of the class butterfly so that matrices with few 128-row tiles (wo / down: 32) still fill the machine
         const int tiles = p.rows_pad / pf::kRows;
         int nz = 1;
-        if (!getenv("MINIGPT4_B200_PREFILL_NO_KSPLIT"))
-            while (nz < 8 && tiles * (int)ty * nz * 2 <= sm_count_ && (size_t)(nz * 2) * n * p.rows_pad * sizeof(float2) <= pf_part_bytes_) nz *= 2;
+        if (!getenv("MINIGPT4_B200_PREFILL_NO_KSPLIT")) {   // waves of CTAs x work per CTA (+ a little per-CTA overhead), smallest wins
+            double best = 1e30;
+            for (int c = 1; c <= 8; c *= 2) {
+                if ((size_t)c * n * p.rows_pad * sizeof(float2) > pf_part_bytes_ && c > 1) break;
+                const int ctas = tiles * (int)ty * c;
+                const double cost = (double)((ctas + sm_count_ - 1) / sm_count_) / c + 0.02 * c;
+                if (cost < best - 1e-9) { best = cost; nz = c; }
+            }
+        }
         a.jr_per_z = 32 / nz; a.partial = (float2 *)pf_part_; a.part_tok = n; a.part_rows = p.rows_pad;
         const dim3 grid((unsigned)tiles, ty, (unsigned)nz);
         if (p.q41) pf::prefill_gemm_q4<true><<<grid, pf::kThreads, smem, stream_>>>(*(const CUtensorMap *)p.tm, *tb, *ts, a);
@@ -561,7 +568,7 @@ void LlamaDevice::prefill_chunk(int n, bool want_logits) {
 // positions and the token come from *state_, so the same graph serves every step
 // ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
-// persistent megakernel program (llama_mega6.cuh; generation 4 = llama_mega.cuh kept for A/B runs behind MINIGPT4_B200_MEGA_GEN=4)
+// persistent megakernel program (llama_mega6.cuh)
 // ------------------------------------------------------------------------------------------------
 bool LlamaDevice::build_mega() {
     if (getenv("MINIGPT4_B200_NO_MEGAKERNEL")) return false;
@@ -580,9 +587,8 @@ bool LlamaDevice::build_mega() {
     CUDA_CHECK(cudaMalloc((void **)&mega_barrier_, 64)); CUDA_CHECK(cudaMemset(mega_barrier_, 0, 64));
     mega_n_ops_ = (tp ? 7 : 5) * d_.n_layer + 3;
     if (getenv("MINIGPT4_B200_MEGA_TRACE")) { CUDA_CHECK(cudaMalloc((void **)&mega_trace_, (size_t)(mega_n_ops_ + 1) * 32 * sizeof(long long))); CUDA_CHECK(cudaMemset(mega_trace_, 0, (size_t)(mega_n_ops_ + 1) * 32 * sizeof(long long))); }
-    mega_gen_ = !tp && wt != GG_Q5_K && getenv("MINIGPT4_B200_MEGA_GEN") && atoi(getenv("MINIGPT4_B200_MEGA_GEN")) == 4 ? 4 : 6;
-    const bool ok = mega_gen_ == 4 ? build_mega4() : build_mega6();
-    if (!ok) return false;
+    mega_gen_ = 6;
+    if (!build_mega6()) return false;
     const void *fn = mega_fn();
     CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem_));
     int occ = 0;
@@ -657,72 +663,8 @@ bool LlamaDevice::build_mega6() {
     return true;
 }
 
-// generation 4 (llama_mega.cuh): single producer warp + shared ring
-bool LlamaDevice::build_mega4() {
-    using namespace mk;
-    const int wt = mega_type_;
-    const int E = d_.n_embd, FF = d_.n_ff;
-    const int act = act_of(wt);
-    size_t act_b = std::max(act_bytes(act, FF), act_bytes(act, E));
-    act_b = std::max(act_b, (size_t)d_.n_ctx * 6);
-    act_b = (act_b + 127) & ~(size_t)127;
-    const int rb_e = layers_[0].qkv.row_bytes, rb_ff = layers_[0].w2.row_bytes;
-    int slot = std::max(2 * rb_e, rb_ff);
-    slot = (slot + 127) & ~127;
-    cudaDeviceProp prop; int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-    const size_t budget = prop.sharedMemPerBlockOptin - 2048;
-    const size_t ops_b = (size_t)(5 * d_.n_layer + 3) * sizeof(MegaOp);
-    const int n_slots = (int)std::min<long long>(48, ((long long)budget - 9216 - (long long)act_b - (long long)ops_b - 1024) / (long long)slot);
-    if (n_slots < 12) return false;
-    const int inflight = 10;
-    std::vector<MegaOp> ops;
-    auto add = [&](int kind, int layer, const QMat *m, const float *norm) {
-        MegaOp o{}; o.kind = kind; o.layer = layer; o.norm_w = norm;
-        if (m) {
-            o.rows = m->rows; o.cols = m->cols; o.row_bytes = m->row_bytes; o.w = (const unsigned char *)m->p0;
-            o.sps = 2 * m->row_bytes <= slot ? 1 : 2;
-            o.n_su = m->rows / 2;
-            o.n_warps = std::max(1, std::min(kConsumerWarps, (n_slots - (o.sps == 2 ? 0 : inflight)) / o.sps));
-        }
-        ops.push_back(o);
-    };
-    add(OP_EMBED, 0, nullptr, nullptr);
-    for (int il = 0; il < d_.n_layer; ++il) {
-        Layer &L = layers_[(size_t)il];
-        add(OP_QKV, il, &L.qkv, L.attn_norm);
-        add(OP_ATTN, il, nullptr, nullptr);
-        add(OP_WO, il, &L.wo, nullptr);
-        add(OP_GATEUP, il, &L.w13, L.ffn_norm);
-        add(OP_DOWN, il, &L.w2, nullptr);
-    }
-    add(OP_OUTPUT, 0, &output_, final_norm_);
-    add(OP_FINAL, 0, nullptr, nullptr);
-    CUDA_CHECK(cudaMalloc(&mega_ops_, ops.size() * sizeof(MegaOp)));
-    CUDA_CHECK(cudaMemcpy(mega_ops_, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
-    MegaParams *P = new MegaParams();
-    P->ops = (const MegaOp *)mega_ops_; P->n_ops = (int)ops.size();
-    P->n_slots = n_slots; P->slot_bytes = slot; P->act_bytes = (int)act_b; P->xs_bytes = 0;
-    P->E = E; P->FF = FF; P->n_head = d_.n_head; P->n_ctx = d_.n_ctx; P->n_vocab = d_.n_vocab;
-    P->kq_scale = 1.0f / sqrtf((float)d_.n_embd / (float)d_.n_head);
-    P->x = x_; P->q = q_; P->att = att_; P->act = act_; P->logits = logits_; P->kcache = kcache_; P->vcache = vcache_;
-    P->rope = rope_; P->tab_exp = tab_exp_; P->tab_silu = tab_silu_;
-    P->tok = (const unsigned char *)tok_raw_; P->tok_type = tok_type_; P->tok_row_bytes = gg_row_bytes(tok_type_, (size_t)E);
-    P->state = state_; P->barrier = mega_barrier_;
-    P->trace = mega_trace_;
-    P->l2_ahead = 0;
-    P->flags = getenv("MINIGPT4_B200_MEGA_FLAGS") ? atoi(getenv("MINIGPT4_B200_MEGA_FLAGS")) : 1;
-    mega_params_ = P;
-    mega_smem_ = (size_t)n_slots * slot + act_b + (size_t)n_slots * 16 + ops.size() * sizeof(MegaOp) + 64;
-    MG4_INFO("decode megakernel (generation 4): %d ops/token, ring %d x %d B, act %zu B, %zu B shared per CTA, grid %d", (int)ops.size(), n_slots, slot, act_b, mega_smem_, sm_count_);
-    return true;
-}
 const void *LlamaDevice::mega_fn() const {
     const bool t = mega_trace_ != nullptr, q41 = mega_type_ == GG_Q4_1;
-    if (mega_gen_ == 4) {
-        using namespace mk;
-        if (t) return q41 ? (const void *)decode_megakernel<GG_Q4_1, true> : (const void *)decode_megakernel<GG_Q4_0, true>;
-        return q41 ? (const void *)decode_megakernel<GG_Q4_1, false> : (const void *)decode_megakernel<GG_Q4_0, false>;
-    }
     using namespace mk6;
     if (mega_type_ == GG_Q5_K) return t ? (const void *)decode_megakernel6<GG_Q5_K, 0, true> : (const void *)decode_megakernel6<GG_Q5_K, 0, false>;
 #define MG4_M6(NBL) (q41 ? (t ? (const void *)decode_megakernel6<GG_Q4_1, NBL, true> : (const void *)decode_megakernel6<GG_Q4_1, NBL, false>) \
@@ -737,7 +679,7 @@ void LlamaDevice::launch_mega() {
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    void *args[1] = {mega_gen_ == 4 ? mega_params_ : mega6_params_};
+    void *args[1] = {mega6_params_};
     CUDA_CHECK(cudaLaunchKernelExC(&cfg, mega_fn(), args));
     ++launches_;
     CUDA_CHECK(cudaMemcpyAsync(h_argmax_, &state_->argmax_id, 4, cudaMemcpyDeviceToHost, stream_));
@@ -813,7 +755,7 @@ float LlamaDevice::time_allreduce(int reps) {
 }
 int LlamaDevice::mega_trace(long long *out, int max_values) {
     if (!mega_trace_) return 0;
-    const int n = std::min(max_values, mega_n_ops_ * (mega_gen_ == 4 ? 16 : 32));
+    const int n = std::min(max_values, mega_n_ops_ * 32);
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaMemcpy(out, mega_trace_, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
     return n;

@@ -95,7 +95,6 @@ private:
     void build_graph();
     bool build_mega();               // persistent one-launch-per-token decode (homogeneous Q4_0/Q4_1, single GPU)
     bool build_mega6();
-    bool build_mega4();
     void launch_mega();
     const void *mega_fn() const;
     LlamaDims d_{};
@@ -121,10 +120,9 @@ private:
     unsigned long long launches_ = 0;
     int graph_kernels_ = 0;
     long long *mega_trace_ = nullptr; int mega_n_ops_ = 0;
-    int mega_stk_ = 7;
     int mega_gen_ = 6; void *mega6_params_ = nullptr; int mega6_nbl_ = 0;  // generation 6 (llama_mega6.cuh)
     bool h_state_busy_ = false;
-    bool mega_ = false; void *mega_ops_ = nullptr; unsigned *mega_barrier_ = nullptr; void *mega_params_ = nullptr; size_t mega_smem_ = 0; int mega_type_ = -1;
+    bool mega_ = false; unsigned *mega_barrier_ = nullptr; size_t mega_smem_ = 0; int mega_type_ = -1;
     int sm_count_ = 148;
 };
 

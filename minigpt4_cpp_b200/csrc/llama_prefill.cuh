@@ -5,7 +5,7 @@
 // INTEGER block dot products, F32 scaling.  Here the integer dots run on the 5th-generation tensor cores:
 //   * one tcgen05.mma kind::i8 (M = 128 weight rows, N = 32 tokens, K = 32 = ONE quant block, accumulate = 0) per quant block puts the
 //     128 x 32 exact int32 block dots into TMEM; the per-block scales cannot be folded into the MMA, so
-//   * eight epilogue warps read each block's dots back (tcgen05.ld), apply  d_w * d_a * isum  and  m_w * s_a  on the CUDA cores and
+//   * sixteen epilogue warps (32 rows x 8 tokens each) read each block's dots back (tcgen05.ld), apply  d_w * d_a * isum  and  m_w * s_a  on the CUDA cores and
 //     accumulate in the CANONICAL FLOAT ORDER of oracle.cpp / k::dot2_q4: "lane" class l = b mod 32 accumulates its blocks l, l+32, ...
 //     in increasing order; the 32 class sums are then combined by the xor-butterfly tree (16, 8, 4, 2, 1).  The K loop therefore walks
 //     the classes in bit-reversed order (0, 16, 8, 24, ...), which turns the butterfly into a post-order tree walk with a 5-deep stack
@@ -29,8 +29,10 @@ constexpr int kRows = 128;        // weight rows per CTA (UMMA M)
 constexpr int kStages = 4;        // shared-memory pipeline depth (tiles of 4 blocks)
 constexpr int kStageBytes = 16384 + 4096 + 1024;  // A 128 x 128 B | B 32 x 128 B | activation scales 32 x 4 x {d, s}
 constexpr int kGroups = 4;        // TMEM tile groups (4 x 32-column block regions each) -> 512 columns
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;     // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue
+constexpr int kEpiWarps = 16;       // 4 per TMEM lane quarter: a warp owns 32 rows x kTpw tokens (twice the warps of the first cut: the epilogue is a latency chain)
+constexpr int kTpw = kTok * 4 / kEpiWarps;   // tokens per epilogue warp (8)
+constexpr int kThreads = 64 + 32 * kEpiWarps;     // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-17 = epilogue
+static_assert(kTpw == 8, "tmem_ld8i");
 constexpr int kStackBytes = 4 * kTok * kRows * 8; // stack levels 1-4: [level][token][row] {d-tree, m-tree}
 
 struct PrefillArgs {
@@ -80,11 +82,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 }
 // instruction descriptor, kind::i8: D = S32 (c_format 2), A = B = signed 8-bit (format 1), both K-major, M = 128, N = n
 __device__ __forceinline__ uint32_t umma_idesc_i8(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
-__device__ __forceinline__ void tmem_ld16i(uint32_t taddr, int (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr));
+__device__ __forceinline__ void tmem_ld8i(uint32_t taddr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint4 ldg_nc16(const void *p) {
@@ -202,13 +202,13 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
         }
     } else {
         // ---------------- epilogue: scale, accumulate in canonical order, butterfly tree, fused output ----------------
-        const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;   // TMEM lanes 32 * (warp % 4) .. + 31; tokens 16 * half .. + 15
-        const int row_in = quarter * 32 + lane, r = m_tile * kRows + row_in, c0 = half * 16;
+        const int ew = warp - 2, quarter = warp & 3, tq = ew >> 2;   // TMEM lanes 32 * (warp % 4) .. + 31; tokens kTpw * tq .. + kTpw - 1
+        const int row_in = quarter * 32 + lane, r = m_tile * kRows + row_in, c0 = tq * kTpw;
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
         const __half2 *wrow = g.wsc + (size_t)r * (32 * g.S);
-        float accd[16], accm[16], l0d[16], l0m[16];
+        float accd[kTpw], accm[kTpw], l0d[kTpw], l0m[kTpw];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) { accd[c] = 0.f; accm[c] = 0.f; l0d[c] = 0.f; l0m[c] = 0.f; }
+        for (int c = 0; c < kTpw; ++c) { accd[c] = 0.f; accm[c] = 0.f; l0d[c] = 0.f; l0m[c] = 0.f; }
         unsigned cnt = 0;
         for (int jr = jr0; jr < jr1; ++jr) {
             const int l = bitrev5(jr);
@@ -226,11 +226,11 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (i < v) {
-                        int isum[16];
-                        tmem_ld16i(tmem_base + tlane + (uint32_t)(gq * 128 + i * 32 + c0), isum);
+                        int isum[kTpw];
+                        tmem_ld8i(tmem_base + tlane + (uint32_t)(gq * 128 + i * 32 + c0), isum);
                         const float2 f = __half22float2(*(const __half2 *)&wv[i]);
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
+                        for (int c = 0; c < kTpw; ++c) {
                             const float2 ds = asc[(c0 + c) * 4 + i];
                             if (Q41) { accd[c] = fmaf(f.x * ds.x, (float)isum[c], accd[c]); accm[c] = fmaf(f.y, ds.y, accm[c]); }
                             else accd[c] += ((float)isum[c] * f.x) * ds.x;
@@ -245,11 +245,11 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
             const int jl = jr - jr0;   // leaf number inside this CTA's subtree (jr0 is a multiple of the subtree size)
             if ((jl & 1) == 0) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) { l0d[c] = accd[c]; l0m[c] = accm[c]; accd[c] = 0.f; accm[c] = 0.f; }
+                for (int c = 0; c < kTpw; ++c) { l0d[c] = accd[c]; l0m[c] = accm[c]; accd[c] = 0.f; accm[c] = 0.f; }
             } else {
                 int ones = 1; while (ones < 5 && ((jl >> ones) & 1)) ++ones;  // trailing ones of jl (>= 1)
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < kTpw; ++c) {
                     float vd = l0d[c] + accd[c], vm = l0m[c] + accm[c];
                     accd[c] = 0.f; accm[c] = 0.f;
                     for (int lev = 1; lev < ones; ++lev) {
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefill_gemm_q4(const __grid_cons
         // results: res[c] = d-tree + m-tree (k::dot2_q4: warp_sum(accd) + warp_sum(accm)); fused epilogues of k::matvec_kernel
         const int n_past = g.state->n_past;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < kTpw; ++c) {
             const int t = t_tile * kTok + c0 + c;
             if (gridDim.z > 1) {   // K split: the root of this CTA's subtree; prefill_combine finishes the tree
                 if (t < g.n_tok && r < g.rows) g.partial[((size_t)blockIdx.z * g.part_tok + t) * g.part_rows + r] = make_float2(l0d[c], l0m[c]);

@@ -67,8 +67,13 @@ __global__ void __launch_bounds__(256) tp_allreduce_resid_kernel(TPPeers P, unsi
         asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(P.flags[threadIdx.x] + P.rank), "r"(seq) : "memory");
     }
     if (threadIdx.x < (unsigned)P.world) {
-        unsigned v; const unsigned *f = P.flags[P.rank] + threadIdx.x;
-        do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while ((int)(v - seq) < 0);
+        unsigned v, spins = 0; const unsigned *f = P.flags[P.rank] + threadIdx.x;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - seq) >= 0) break;
+            if (++spins > (1u << 25)) asm volatile("trap;");   // a lost peer must end in a failed launch (an error the host reports), never in a hung GPU
+            __nanosleep(64);
+        }
     }
     __syncthreads();
     for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) * 4; i < count; i += (int)(gridDim.x * blockDim.x) * 4) {

@@ -73,10 +73,11 @@ static GemmPlan *make_plan(const __half *W, int M, int K, const __half *X, int T
     return p;
 }
 static void launch_plan(const GemmPlan *p, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};   // per device
+    int dev = 0; cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-        configured = true;
+        configured[dev & 63] = true;
     }
     gemm_f16_tcgen05<<<dim3((unsigned)p->grid, (unsigned)p->grid_y, (unsigned)p->grid_z), 192, p->smem, s>>>(p->tmW, p->tmX, p->a);
     CUDA_CHECK(cudaGetLastError());
@@ -319,11 +320,12 @@ Error VisionDevice::load(const VisionFile &f, const VisionDevice *share) {
 static size_t attn_smem(int nk, int dh) { const int nkp = (nk + 31) & ~31; return ((size_t)nk * (dh + 4) + (size_t)nk * dh + (size_t)8 * kAttnNQ * (nkp > dh ? nkp : dh)) * 4; }
 static void launch_attention(int dh, dim3 grid, cudaStream_t s, const float *q, int ldq, const float *k, const float *v, int ldkv, int nq, int nk, float div, int qpc,
                              __half *out, int ld_out, const __half *tab) {
-    static bool cfg = false;
-    if (!cfg) {
+    static bool cfg[64] = {};   // per device
+    int dev = 0; cudaGetDevice(&dev);
+    if (!cfg[dev & 63]) {
         CUDA_CHECK(cudaFuncSetAttribute(attention_f32_kernel<88>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
         CUDA_CHECK(cudaFuncSetAttribute(attention_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        cfg = true;
+        cfg[dev & 63] = true;
     }
     if (nk > 288) MG4_PANIC("attention: at most 288 keys (got %d)", nk);
     const size_t sm = attn_smem(nk, dh);
