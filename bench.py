@@ -43,7 +43,7 @@ def metric_name(size: str, wtype: str) -> str:
 
 
 def workload(size: str, wtype: str, blocks: int) -> str:
-    return (f"configs[{1 if (wtype, N_GEN) == ('q4_1', 128) else 2 if wtype == 'q5_k' else '-'}]: Vicuna-{size} {wtype} decode-only, {N_PREFIX}-row image prefix + {N_GEN} generated tokens; "
+    return (f"configs[{1 if (size, wtype, N_GEN) == ('7b', 'q4_1', 128) else 2 if (size, wtype) == ('7b', 'q5_k') else 3 if (size, wtype) == ('13b', 'q5_k') else '-'}]: Vicuna-{size} {wtype} decode-only, {N_PREFIX}-row image prefix + {N_GEN} generated tokens; "
             f"plus ViT-g f16 224x224 encode ({blocks} blocks) per step")
 
 
@@ -447,7 +447,10 @@ def main():
             ids1, _ = ext.decode_chain(c1, N_GEN)
             n_same = next((i for i, (a, b) in enumerate(zip(ids_tp.tolist(), ids1.tolist())) if a != b), N_GEN)
             tp_rec["parity_vs_1gpu"] = {"logits_rel_err_after_prefix": float(np.abs(lg_tp - lg1).max() / np.abs(lg1).max()), "bar": 1e-2,
-                                        "leading_greedy_ids_equal": n_same, "of": N_GEN}
+                                        "leading_greedy_ids_equal": n_same, "of": N_GEN,
+                                        "note": "all ranks are bit-identical to each other; against ONE GPU only the float order of the partial sums differs, and this random-weight "
+                                                "32-layer model turns a 1e-6 input perturbation into a 1.9e-2 logit change (DESIGN.md 2.1): tools/tp_check.py holds the 1e-2 bar on "
+                                                "2- and 4-layer models (32 of 32 ids)"}
             lib.minigpt4_free(c_tp)
         line["tp"] = tp_rec
 

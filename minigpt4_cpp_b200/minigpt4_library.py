@@ -177,6 +177,8 @@ class MiniGPT4SharedLibrary:
 def library_path() -> Path:
     """In-tree build output (build/libminigpt4.so), built on demand; the extension must exist — no fallback."""
     from . import build as _build
+    if os.environ.get("MINIGPT4_B200_LIB"):   # A/B of another build of the same ABI (tools/ab_lib.py, tools/mega_trace.py)
+        return Path(os.environ["MINIGPT4_B200_LIB"]).resolve()
     return _build.build()
 
 

@@ -28,7 +28,8 @@ d = "/dev/shm/tpcheck"; os.makedirs(d, exist_ok=True)
 out = {}
 cases = (("tiny_q4_1", mg.LlamaSpec(n_vocab=1024, n_embd=1024, n_head=8, n_layer=4, wtype="q4_1"), 21, 8),
          ("tiny_f16", mg.LlamaSpec(n_vocab=1024, n_embd=1024, n_head=8, n_layer=4, wtype="f16"), 21, 8),
-         ("wide_q4_1_megakernel", mg.LlamaSpec(n_vocab=2048, n_embd=4096, n_head=32, n_layer=2, wtype="q4_1"), 40, 32))
+         ("wide_q4_1_megakernel", mg.LlamaSpec(n_vocab=2048, n_embd=4096, n_head=32, n_layer=2, wtype="q4_1"), 40, 32),
+         ("wide_q5_k_megakernel", mg.LlamaSpec(n_vocab=2048, n_embd=4096, n_head=32, n_layer=2, n_mult=512, wtype="q5_k"), 40, 32))   # n_ff 11264: shards of whole super-blocks for 2 and 4 ranks
 for name, spec, n_prompt, n_gen in cases:
     p = f"{d}/{name}.bin"
     if rank == 0:
