@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -43,11 +44,18 @@ extern int g_verbosity;  // 0 none, 1 error, 2 info, 3 debug
 #define MG4_INFO(...) do { if (mg4::g_verbosity >= 2) { fprintf(stdout, "[minigpt4-b200][info] " __VA_ARGS__); fputc('\n', stdout); } } while (0)
 #define MG4_DBG(...)  do { if (mg4::g_verbosity >= 3) { fprintf(stdout, "[minigpt4-b200][debug] " __VA_ARGS__); fputc('\n', stdout); } } while (0)
 
-// Fatal: there is NO CPU fallback.  A CUDA failure aborts loudly (reference PANIC -> exit(-1), minigpt4.cpp:230-232).
-#define CUDA_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
-    fprintf(stderr, "[minigpt4-b200][fatal] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \
-    fflush(stderr); abort(); } } while (0)
-#define MG4_PANIC(...) do { fprintf(stderr, "[minigpt4-b200][fatal] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); abort(); } while (0)
+// There is NO CPU fallback, so a failure is either reported or fatal - never worked around:
+//  * while a model is being LOADED (a LoadScope is alive on this thread) a failed check - missing tensor, unsupported tensor type or shape,
+//    device memory exhausted, no usable driver - throws LoadFailure; Engine::init turns it into the ABI's error code and
+//    minigpt4_model_load returns NULL, like the reference (minigpt4.cpp:2476-2492);
+//  * anywhere else (a kernel launch that failed, a corrupted context) the process aborts loudly (reference PANIC -> exit(-1), minigpt4.cpp:230-232).
+struct LoadFailure { char msg[384]; };
+extern thread_local int g_load_depth;
+struct LoadScope { LoadScope() { ++g_load_depth; } ~LoadScope() { --g_load_depth; } };
+[[noreturn]] void fail(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+[[noreturn]] void fail_cuda(cudaError_t e, const char *file, int line);
+#define CUDA_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) mg4::fail_cuda(_e, __FILE__, __LINE__); } while (0)
+#define MG4_PANIC(...) mg4::fail(__VA_ARGS__)
 
 // ggml tensor type ids as stored in ggjt files (llama.cpp@master-31cfbb1 ggml.h)
 enum GGType : int { GG_F32 = 0, GG_F16 = 1, GG_Q4_0 = 2, GG_Q4_1 = 3, GG_Q5_0 = 6, GG_Q5_1 = 7, GG_Q8_0 = 8, GG_Q8_1 = 9,

@@ -20,30 +20,39 @@ Error Engine::init(const std::string &path, const std::string &llm_path, int ver
     n_batch_ = n_batch > 0 ? n_batch : 512;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        // No CPU fallback exists: the hot path is CUDA only.
-        fprintf(stderr, "[minigpt4-b200][fatal] no CUDA device available; this engine has no CPU path\n");
-        abort();
+        // No CPU fallback exists: the hot path is CUDA only.  Reported at every verbosity - a caller must never mistake this for a slow success.
+        cudaGetLastError();
+        fprintf(stderr, "[minigpt4-b200][error] no CUDA device available; this engine has no CPU path\n");
+        return ErrLoadLanguageModel;
     }
-    if (g_tp_config.set && g_tp_config.world > 1) tp.init(g_tp_config.rank, g_tp_config.world, g_tp_config.id);
-    {
-        const double t0 = now_ms();
-        LlamaFile lf;
-        if (!lf.load(llm_path)) { MG4_ERR("failed to read language model %s", llm_path.c_str()); return ErrLoadLanguageModel; }
-        tok_.init(lf.vocab);
-        llm_.reset(new LlamaDevice());
-        if (!llm_->load(lf, n_ctx > 0 ? n_ctx : 2048, tp.world > 1 ? &tp : nullptr)) return ErrLoadLanguageModel;
-        MG4_INFO("Load language model took %.0f ms", now_ms() - t0);
-    }
-    if (!path.empty()) {
-        const double t0 = now_ms();
-        vfile_.reset(new VisionFile());   // (kept mapped: further encode lanes are built from it on demand)
-        VisionFile &vf = *vfile_;
-        if (Error e = vf.load(path)) return e;
-        vis_.reset(new VisionDevice());
-        if (Error e = vis_->load(vf)) return e;
-        if (vis_->dims().n_embd_llm != llm_->dims().n_embd)
-            MG4_ERR("warning: llama_proj width %d != language model n_embd %d", vis_->dims().n_embd_llm, llm_->dims().n_embd);
-        MG4_INFO("Load model from file took %.0f ms", now_ms() - t0);
+    Error where = ErrLoadLanguageModel;
+    try {
+        LoadScope loading;   // failed checks below throw LoadFailure instead of aborting the host process (common.h)
+        if (g_tp_config.set && g_tp_config.world > 1) tp.init(g_tp_config.rank, g_tp_config.world, g_tp_config.id);
+        {
+            const double t0 = now_ms();
+            LlamaFile lf;
+            if (!lf.load(llm_path)) { MG4_ERR("failed to read language model %s", llm_path.c_str()); return ErrLoadLanguageModel; }
+            tok_.init(lf.vocab);
+            llm_.reset(new LlamaDevice());
+            if (!llm_->load(lf, n_ctx > 0 ? n_ctx : 2048, tp.world > 1 ? &tp : nullptr)) return ErrLoadLanguageModel;
+            MG4_INFO("Load language model took %.0f ms", now_ms() - t0);
+        }
+        if (!path.empty()) {
+            where = ErrLoadModelFileHeader;
+            const double t0 = now_ms();
+            vfile_.reset(new VisionFile());   // (kept mapped: further encode lanes are built from it on demand)
+            VisionFile &vf = *vfile_;
+            if (Error e = vf.load(path)) return e;
+            vis_.reset(new VisionDevice());
+            if (Error e = vis_->load(vf)) return e;
+            if (vis_->dims().n_embd_llm != llm_->dims().n_embd)
+                MG4_ERR("warning: llama_proj width %d != language model n_embd %d", vis_->dims().n_embd_llm, llm_->dims().n_embd);
+            MG4_INFO("Load model from file took %.0f ms", now_ms() - t0);
+        }
+    } catch (const LoadFailure &f) {
+        fprintf(stderr, "[minigpt4-b200][error] %s\n", f.msg);
+        return where;
     }
     sampler_.reset(new Sampler(seed));
     logits_.resize((size_t)llm_->dims().n_vocab);
@@ -76,7 +85,13 @@ Error Engine::encode_images(const ::MiniGPT4Image *images, size_t n, ::MiniGPT4E
     const size_t lanes = std::min<size_t>(n, (size_t)kEncodeLanes);
     while (vis_lanes_.size() + 1 < lanes) {
         std::unique_ptr<VisionDevice> l(new VisionDevice());
-        if (Error e = l->load(*vfile_, vis_.get())) return e;
+        try {
+            LoadScope loading;   // (a lane that does not fit in device memory is an error code, not an abort)
+            if (Error e = l->load(*vfile_, vis_.get())) return e;
+        } catch (const LoadFailure &f) {
+            fprintf(stderr, "[minigpt4-b200][error] encode lane %zu: %s\n", vis_lanes_.size() + 1, f.msg);
+            return ErrLoadModelFileHeader;
+        }
         vis_lanes_.push_back(std::move(l));
     }
     auto lane = [&](size_t k) { return k == 0 ? vis_.get() : vis_lanes_[k - 1].get(); };

@@ -10,6 +10,19 @@
 namespace mg4 {
 
 int g_verbosity = 1;
+thread_local int g_load_depth = 0;
+
+void fail(const char *fmt, ...) {
+    LoadFailure f;
+    va_list ap; va_start(ap, fmt); vsnprintf(f.msg, sizeof f.msg, fmt, ap); va_end(ap);
+    if (g_load_depth > 0) throw f;
+    fprintf(stderr, "[minigpt4-b200][fatal] %s\n", f.msg); fflush(stderr);
+    abort();
+}
+void fail_cuda(cudaError_t e, const char *file, int line) {
+    if (g_load_depth > 0) cudaGetLastError();   // (an allocation failure is not sticky: the device stays usable for the caller's next attempt)
+    fail("CUDA error %s at %s:%d: %s", cudaGetErrorName(e), file, line, cudaGetErrorString(e));
+}
 
 double now_ms() {
     using namespace std::chrono;

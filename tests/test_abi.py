@@ -99,3 +99,15 @@ def test_null_arguments_are_harmless(lib):
         assert fn(None) == 0
     L.minigpt4_quantize_model.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
     assert L.minigpt4_quantize_model(None, None, 5) == 17  # PathDoesNotExist
+
+
+def test_model_load_without_a_device_is_an_error_code_not_an_abort(lib, tmp_path):
+    """No CUDA device: the engine has no CPU path, says so on stderr and returns NULL (the ABI's failure value) - the host process survives."""
+    import minigpt4_cpp_b200 as m
+    from minigpt4_cpp_b200 import modelgen as mg
+    ext = m.B200(lib)
+    if ext.L.minigpt4_b200_device_count() > 0:
+        pytest.skip("this box has a CUDA device")
+    p = str(tmp_path / "llama.bin")
+    mg.write_llama_ggjt(p, mg.LlamaSpec(n_vocab=1024, n_embd=128, n_head=1, n_layer=1, wtype="q4_1"))
+    assert ext.L.minigpt4_b200_llm_load(p.encode(), 32, 1, 0) is None

@@ -176,6 +176,20 @@ def test_context_overflow_is_an_error(ext, tiny):
     ext.base.minigpt4_free(c)
 
 
+def test_damaged_model_is_an_error_not_an_abort(ext, tiny, tmp_path):
+    """A load-time failure (here: a tensor the graph needs is missing) returns NULL like the reference; the process and the device stay usable."""
+    raw = open(tiny["q4_1"], "rb").read()
+    name = b"layers.1.ffn_norm.weight"
+    assert raw.count(name) == 1
+    bad = tmp_path / "missing-tensor.bin"
+    bad.write_bytes(raw.replace(name, b"layers.1.ffn_norx.weight"))
+    assert ext.L.minigpt4_b200_llm_load(str(bad).encode(), 64, 1, 0) is None
+    c = ext.llm_load(tiny["q4_1"], n_ctx=64)
+    ext.eval_tokens(c, [3, 4, 5])
+    assert np.isfinite(ext.logits(c)).all()
+    ext.base.minigpt4_free(c)
+
+
 def test_chat_flow_through_reference_abi(lib, ext, orc, mg, tiny, big_llm):
     """system prompt -> begin_chat_image -> 32 x end_chat_image (greedy) == oracle engine, token for token."""
     c = lib.minigpt4_model_load(tiny["vision"], big_llm, 1, 1337, 512, 8, 0)

@@ -30,7 +30,10 @@ cases = (("tiny_q4_1", mg.LlamaSpec(n_vocab=1024, n_embd=1024, n_head=8, n_layer
          ("tiny_f16", mg.LlamaSpec(n_vocab=1024, n_embd=1024, n_head=8, n_layer=4, wtype="f16"), 21, 8),
          ("wide_q4_1_megakernel", mg.LlamaSpec(n_vocab=2048, n_embd=4096, n_head=32, n_layer=2, wtype="q4_1"), 40, 32),
          ("wide_q5_k_megakernel", mg.LlamaSpec(n_vocab=2048, n_embd=4096, n_head=32, n_layer=2, n_mult=512, wtype="q5_k"), 40, 32))   # n_ff 11264: shards of whole super-blocks for 2 and 4 ranks
+only = os.environ.get("TP_CHECK_ONLY")   # run one case by name
 for name, spec, n_prompt, n_gen in cases:
+    if only and name != only:
+        continue
     p = f"{d}/{name}.bin"
     if rank == 0:
         mg.write_llama_ggjt(p, spec)
