@@ -2,6 +2,7 @@
 // minigpt4.cpp:2543-2987) plus the B200 extensions (include/minigpt4_b200.h).
 #include "../../include/minigpt4_b200.h"
 #include "engine.h"
+#include "image.h"
 #include <string.h>
 #include <sys/stat.h>
 #include <string>
@@ -34,9 +35,36 @@ struct MiniGPT4Context *minigpt4_model_load(const char *path, const char *llm_mo
     return reinterpret_cast<struct MiniGPT4Context *>(e);
 }
 
-// OpenCV-only in the reference; its default build returns OpenCVNotLinked (minigpt4.cpp:2592-2594, :2648-2650)
-int minigpt4_image_load_from_file(struct MiniGPT4Context *, const char *, struct MiniGPT4Image *, int) { return ErrOpenCVNotLinked; }
-int minigpt4_preprocess_image(struct MiniGPT4Context *, const struct MiniGPT4Image *, struct MiniGPT4Image *, int) { return ErrOpenCVNotLinked; }
+// Image file -> 8-bit RGB (reference minigpt4.cpp:2576-2596: cv::imread(IMREAD_COLOR) + BGR2RGB, compiled only with OpenCV - its default build
+// returns OpenCVNotLinked).  Decoded here without third-party code: PNG and binary PPM / PGM (csrc/image.cpp); anything else is OpenImage.
+// Pixel buffers of MiniGPT4Image are float-array allocations whatever they hold, because minigpt4_free_image releases them as such (:2790-2798).
+int minigpt4_image_load_from_file(struct MiniGPT4Context *, const char *path, struct MiniGPT4Image *image, int) {
+    if (!image) return ErrOpenImage;
+    RgbImage im; std::string err;
+    if (!decode_image_file(path, im, err)) { MG4_ERR("%s: %s", path ? path : "(null)", err.c_str()); return ErrOpenImage; }
+    const size_t bytes = im.px.size();
+    float *buf = new float[(bytes + 3) / 4];
+    memcpy(buf, im.px.data(), bytes);
+    image->data = buf; image->width = im.w; image->height = im.h; image->channels = 3; image->format = MINIGPT4_IMAGE_FORMAT_U8;
+    return ErrNone;
+}
+
+// 8-bit RGB of any size -> the encoder's input (reference :2598-2651): Pillow-bicubic resize to 224 x 224, / 255, CLIP mean / std, planar CHW.
+// The reference describes the result as a 1 x 150528 single-channel image (it reports the shape of its concatenated planes, :2639-2641);
+// minigpt4_encode_image only checks the element count (:2130), and the same description is returned here.
+int minigpt4_preprocess_image(struct MiniGPT4Context *, const struct MiniGPT4Image *image, struct MiniGPT4Image *preprocessed_image, int) {
+    if (!image || !preprocessed_image || !image->data) return ErrOpenImage;
+    if (image->channels != 3) { MG4_ERR("Image must have 3 channels"); return ErrImageChannelsExpectedRGB; }
+    if (image->format != MINIGPT4_IMAGE_FORMAT_U8) { MG4_ERR("Image must be in U8 format"); return ErrImageFormatExpectedU8; }
+    if (image->width <= 0 || image->height <= 0 || image->width > 32768 || image->height > 32768) return ErrImageSize;
+    std::vector<uint8_t> small((size_t)224 * 224 * 3);
+    resize_bicubic_u8((const uint8_t *)image->data, image->width, image->height, small.data(), 224, 224);
+    float *out = new float[(size_t)3 * 224 * 224];
+    normalize_to_chw(small.data(), 224, 224, out);
+    preprocessed_image->data = out; preprocessed_image->width = 1; preprocessed_image->height = 3 * 224 * 224; preprocessed_image->channels = 1;
+    preprocessed_image->format = MINIGPT4_IMAGE_FORMAT_F32;
+    return ErrNone;
+}
 
 int minigpt4_encode_image(struct MiniGPT4Context *ctx, struct MiniGPT4Image *image, struct MiniGPT4Embedding *embedding, size_t /*n_threads: CPU notion, ignored*/) {
     return E(ctx)->encode_image(image, embedding);

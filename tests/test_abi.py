@@ -1,5 +1,5 @@
 """C-ABI surface: the library loads and exports every symbol include/*.h declares; GPU-free entry points behave like
-the reference (error strings minigpt4.cpp:97-119, EOS helpers :2764-2782, OpenCV stubs :2592-2594)."""
+the reference (error strings minigpt4.cpp:97-119, EOS helpers :2764-2782, image entry points :2576-2651)."""
 import ctypes
 import re
 from pathlib import Path
@@ -49,11 +49,12 @@ def test_eos_helpers(lib):
     assert lib.minigpt4_is_eos("a ###") and not lib.minigpt4_is_eos("### a")
 
 
-def test_opencv_entry_points_report_not_linked(lib):
+def test_image_entry_points_validate_like_the_reference(lib):
+    """minigpt4.cpp:2598-2615: 3 channels and U8 or an error code; a file that cannot be read is OpenImage (tests/test_image_cpu.py has the rest)."""
     import minigpt4_cpp_b200 as m
-    with pytest.raises(RuntimeError, match="OpenCVNotLinked"):
-        lib.minigpt4_image_load_from_file(m.MiniGPT4Context(None), "x.png", 0)
-    with pytest.raises(RuntimeError, match="OpenCVNotLinked"):
+    with pytest.raises(RuntimeError, match="OpenImage"):
+        lib.minigpt4_image_load_from_file(m.MiniGPT4Context(None), "/nonexistent/x.png", 0)
+    with pytest.raises(RuntimeError, match="OpenImage"):
         lib.minigpt4_preprocess_image(m.MiniGPT4Context(None), m.MiniGPT4Image())
 
 

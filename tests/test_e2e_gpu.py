@@ -190,6 +190,31 @@ def test_damaged_model_is_an_error_not_an_abort(ext, tiny, tmp_path):
     ext.base.minigpt4_free(c)
 
 
+def test_image_file_to_embedding_through_the_abi(lib, ext, tiny, big_llm, tmp_path):
+    """examples/main.cpp's flow (reference :207-240): minigpt4_image_load_from_file -> minigpt4_preprocess_image -> minigpt4_encode_image on a PNG of
+    arbitrary size == encoding the Pillow-resized, CLIP-normalised tensor directly."""
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:300, 0:420]
+    rgb = ((np.stack([xx * 2 + yy, xx + yy * 3, 255 - xx], -1) % 256) + rng.integers(-20, 20, (300, 420, 3))).clip(0, 255).astype(np.uint8)
+    path = tmp_path / "photo.png"
+    Image.fromarray(rgb).save(path)
+    c = lib.minigpt4_model_load(tiny["vision"], big_llm, 1, 1337, 256, 8, 0)
+    img = lib.minigpt4_image_load_from_file(c, str(path), 0)
+    pre = lib.minigpt4_preprocess_image(c, img, 0)
+    emb = lib.minigpt4_encode_image(c, pre, 0)
+    got = np.ctypeslib.as_array(emb.data, shape=(32 * 4096,)).copy()
+    small = np.asarray(Image.fromarray(rgb).resize((224, 224), Image.BICUBIC))
+    f = small.astype(np.float32) * np.float32(1.0 / 255.0)
+    d = (f.astype(np.float64) - np.array([0.48145466, 0.4578275, 0.40821073])).astype(np.float32)
+    chw = np.ascontiguousarray((d.astype(np.float64) / np.array([0.26862954, 0.26130258, 0.27577711])).astype(np.float32).transpose(2, 0, 1))
+    want = ext.encode_array(c, chw).reshape(-1)
+    assert np.array_equal(got, want)
+    lib.minigpt4_free_embedding(emb)
+    lib.minigpt4_free_image(img); lib.minigpt4_free_image(pre)
+    lib.minigpt4_free(c)
+
+
 def test_chat_flow_through_reference_abi(lib, ext, orc, mg, tiny, big_llm):
     """system prompt -> begin_chat_image -> 32 x end_chat_image (greedy) == oracle engine, token for token."""
     c = lib.minigpt4_model_load(tiny["vision"], big_llm, 1, 1337, 512, 8, 0)
