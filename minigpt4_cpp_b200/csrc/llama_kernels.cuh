@@ -86,33 +86,29 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-// Two execution contexts share these helpers: stand-alone kernels (all 256 threads of the CTA, __syncthreads, plain loads)
-// and the persistent decode megakernel (MEGA: 256 consumer threads + a producer warp, named barrier 1, and L2-only
-// loads because inputs were written by OTHER CTAs earlier in the same launch and L1 may hold stale lines).
+// CTA-wide sync of 256 threads: the stand-alone kernels below use the whole CTA (__syncthreads); the persistent decode megakernel
+// (llama_mega6.cuh) syncs its first eight warps on named barrier 1 while the other warps keep streaming.
 template <bool MEGA> __device__ __forceinline__ void cta_sync() {
     if (MEGA) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads();
 }
-template <bool MEGA> __device__ __forceinline__ float ld_act(const float *p) { return MEGA ? __ldcg(p) : *p; }
-template <bool MEGA>
 __device__ __forceinline__ double block_sum(double v, double *red) {  // red: >= 33 doubles of shared memory; 256 threads
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = warp_sum(v);
-    cta_sync<MEGA>();
+    cta_sync<false>();
     if (lane == 0) red[warp] = v;
-    cta_sync<MEGA>();
+    cta_sync<false>();
     if (warp == 0) { double t = lane < 8 ? red[lane] : 0.0; t = warp_sum(t); if (lane == 0) red[32] = t; }
-    cta_sync<MEGA>();
+    cta_sync<false>();
     return red[32];
 }
-template <bool MEGA>
 __device__ __forceinline__ float block_max(float v, float *red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = warp_max(v);
-    cta_sync<MEGA>();
+    cta_sync<false>();
     if (lane == 0) red[warp] = v;
-    cta_sync<MEGA>();
+    cta_sync<false>();
     if (warp == 0) { float t = lane < 8 ? red[lane] : -INFINITY; t = warp_max(t); if (lane == 0) red[32] = t; }
-    cta_sync<MEGA>();
+    cta_sync<false>();
     return red[32];
 }
 __device__ __forceinline__ float lut_f16(const __half *tab, float x) {  // ggml fp16 LUT op: in rounded to F16, out F16
@@ -123,7 +119,7 @@ __device__ __forceinline__ float lut_f16(const __half *tab, float x) {  // ggml 
 // activation staging: F32 row (optionally RMS-normalised, eps 1e-6, double accumulation like ggml_rms_norm)
 // -> shared memory in the weight type's vec_dot format (quantize_row_q8_0 / q8_1 AVX2 semantics, q8_K)
 // ---------------------------------------------------------------------------------------------
-template <int ACT, bool MEGA>
+template <int ACT>
 __device__ void stage_act(const float *__restrict__ x, const float *__restrict__ nw, int cols, unsigned char *sm, double *red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5; constexpr int nwarps = 8, nthreads = 256;
     float scale = 1.0f;
@@ -135,30 +131,30 @@ __device__ void stage_act(const float *__restrict__ x, const float *__restrict__
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int ia = 2048 * k + 4 * tid + e, ib = ia + 1024;
-                if (ia < cols) { const float v = ld_act<MEGA>(x + ia); ssa += (double)(v * v); }
-                if (ib < cols) { const float v = ld_act<MEGA>(x + ib); ssb += (double)(v * v); }
+                if (ia < cols) { const float v = x[ia]; ssa += (double)(v * v); }
+                if (ib < cols) { const float v = x[ib]; ssb += (double)(v * v); }
             }
         }
         ssa = warp_sum(ssa); ssb = warp_sum(ssb);
-        cta_sync<MEGA>();
+        cta_sync<false>();
         if (lane == 0) { red[warp] = ssa; red[warp + 8] = ssb; }
-        cta_sync<MEGA>();
+        cta_sync<false>();
         if (warp == 0) { double t = lane < 16 ? red[lane] : 0.0; t = warp_sum(t); if (lane == 0) red[32] = t; }
-        cta_sync<MEGA>();
+        cta_sync<false>();
         const double tot = red[32];
         const float mean = (float)(tot / (double)cols);
         scale = 1.0f / sqrtf(mean + 1e-6f);
     }
     if (ACT == ACT_F16) {
         __half *h = (__half *)sm;
-        for (int i = tid; i < cols; i += nthreads) { float v = ld_act<MEGA>(x + i); if (nw) v = (v * scale) * nw[i]; h[i] = __float2half_rn(v); }
+        for (int i = tid; i < cols; i += nthreads) { float v = x[i]; if (nw) v = (v * scale) * nw[i]; h[i] = __float2half_rn(v); }
     } else if (ACT == ACT_Q8_K) {
         int8_t *qs = (int8_t *)sm; float *d = (float *)(sm + cols); int16_t *bs = (int16_t *)(sm + cols + cols / 256 * 4);
         for (int sb = warp; sb < cols / 256; sb += nwarps) {
             float v[8]; float amax = 0.f, mx = 0.f; int mi = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int i = sb * 256 + lane * 8 + j; float t = ld_act<MEGA>(x + i); if (nw) t = (t * scale) * nw[i]; v[j] = t;
+                const int i = sb * 256 + lane * 8 + j; float t = x[i]; if (nw) t = (t * scale) * nw[i]; v[j] = t;
                 const float a = fabsf(t); if (a > amax) { amax = a; mx = t; mi = lane * 8 + j; }
             }
 #pragma unroll
@@ -183,7 +179,7 @@ __device__ void stage_act(const float *__restrict__ x, const float *__restrict__
         int8_t *qs = (int8_t *)sm; float *d = (float *)(sm + cols); float *s = d + cols / 32;
         for (int b = warp; b < cols / 32; b += nwarps) {
             const int i = b * 32 + lane;
-            float v = ld_act<MEGA>(x + i); if (nw) v = (v * scale) * nw[i];
+            float v = x[i]; if (nw) v = (v * scale) * nw[i];
             const float amax = warp_max(fabsf(v));
             const float dd = amax / 127.f;
             const float id = amax != 0.0f ? 127.f / amax : 0.0f;
@@ -557,7 +553,7 @@ __device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {  //
 template <int ACT>
 __global__ void __launch_bounds__(kThreads) stage_kernel(const float *x, int x_stride, const float *norm_w, int cols, unsigned char *out, size_t astride) {
     __shared__ double red[34];
-    stage_act<ACT, false>(x + (size_t)blockIdx.x * x_stride, norm_w, cols, out + (size_t)blockIdx.x * astride, red);
+    stage_act<ACT>(x + (size_t)blockIdx.x * x_stride, norm_w, cols, out + (size_t)blockIdx.x * astride, red);
 }
 
 template <int WT, int NT>
@@ -636,13 +632,8 @@ __global__ void __launch_bounds__(kThreads, 2) matvec_kernel(const MatvecArgs a)
 // rounded to F16, dots accumulate in F32, exp through the fp16 LUT, soft-max sum in double
 // grid (n_head_local, ntok), block 256, dynamic smem = n_ctx * 6 bytes
 // ---------------------------------------------------------------------------------------------
-template <bool MEGA> __device__ __forceinline__ uint4 ld_kv16(const __half *p) { return MEGA ? __ldcg((const uint4 *)p) : *(const uint4 *)p; }
-template <bool MEGA> __device__ __forceinline__ __half2 ld_kv4(const __half *p) {
-    if (MEGA) { const unsigned u = __ldcg((const unsigned *)p); return *(const __half2 *)&u; }
-    return *(const __half2 *)p;
-}
+__device__ __forceinline__ uint4 ld_kv16(const __half *p) { return *(const uint4 *)p; }
 // one (head h, token t) of decode/prefill attention; 256 threads; dyn = n_ctx * 6 bytes of shared scratch
-template <bool MEGA, int EARLY_V = 12>
 __device__ __forceinline__ void attention_head(const float *__restrict__ q, const __half *__restrict__ kc, const __half *__restrict__ vc, float *__restrict__ out,
                                                int pos, int h, int t, int E, int n_ctx, float kq_scale, const __half *__restrict__ tab_exp,
                                                unsigned char *dyn, double *red, float *redf, __half *qh, float *part /*[16*128]*/) {
@@ -661,13 +652,13 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
 #pragma unroll
             for (int u = 0; u < B; ++u) {
                 const int key = min(kb0 + u * 16 + sub, nkv - 1);  // clamped, unconditional: a predicated load would demote kv[] to local memory
-                kv[u] = ld_kv16<MEGA>(kc + (size_t)key * E + h * 128 + l16 * 8);
+                kv[u] = ld_kv16(kc + (size_t)key * E + h * 128 + l16 * 8);
             }
             if (!have_q) {
                 const float *qp = q + (size_t)t * E + h * 128 + l16 * 8;
                 float qf[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) qf[e] = ld_act<MEGA>(qp + e);
+                for (int e = 0; e < 8; ++e) qf[e] = qp[e];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) q2[j] = __floats2half2_rn(qf[2 * j], qf[2 * j + 1]);
                 have_q = true;
@@ -688,24 +679,16 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
             }
         }
     }
-    // megakernel: the first batch of V rows does not depend on the scores - request it now, so its HBM round trip runs under the
-    // soft-max (three block reductions and a table lookup) instead of after it
-    constexpr int BV = MEGA ? EARLY_V : 1;
-    uint4 vv0[BV];
-    if (MEGA) {
-#pragma unroll
-        for (int u = 0; u < BV; ++u) { const int key = min((tid >> 4) + 16 * u, nkv - 1); vv0[u] = ld_kv16<MEGA>(vc + (size_t)key * E + h * 128 + (tid & 15) * 8); }
-    }
-    cta_sync<MEGA>();
+    cta_sync<false>();
     float mx = -INFINITY;
     for (int i = tid; i < nkv; i += 256) mx = fmaxf(mx, sc[i]);
-    mx = block_max<MEGA>(mx, redf);
+    mx = block_max(mx, redf);
     double sum = 0.0;
     for (int i = tid; i < nkv; i += 256) { const float v = lut_f16(tab_exp, sc[i] - mx); sc[i] = v; sum += (double)v; }
-    const double tot = block_sum<MEGA>(sum, red);
+    const double tot = block_sum(sum, red);
     const float inv = (float)(1.0 / tot);
     for (int i = tid; i < nkv; i += 256) ph[i] = __float2half_rn(sc[i] * inv);
-    cta_sync<MEGA>();
+    cta_sync<false>();
     // P.V : thread = (key group g of 16, dim octet o of 16); groups are combined by a pairwise tree (canonical order)
     {
         const int g = tid >> 4, o = tid & 15;
@@ -714,23 +697,10 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
         constexpr int B = 12;
         int key0 = g;
-        if (MEGA) {  // the batch requested before the soft-max (keys g, g+16, ...: same sequential FMA order)
-#pragma unroll
-            for (int u = 0; u < BV; ++u) {
-                const int key = g + 16 * u;
-                if (key < nkv) {
-                    const float p = __half2float(ph[key]);
-                    const __half2 *v2 = (const __half2 *)&vv0[u];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { const float2 v = __half22float2(v2[j]); acc[2 * j] = fmaf(v.x, p, acc[2 * j]); acc[2 * j + 1] = fmaf(v.y, p, acc[2 * j + 1]); }
-                }
-            }
-            key0 += 16 * BV;
-        }
         for (; key0 < nkv; key0 += 16 * B) {  // batch the V loads (192 keys per pass); the FMA order over keys stays sequential
             uint4 vv[B];
 #pragma unroll
-            for (int u = 0; u < B; ++u) { const int key = min(key0 + 16 * u, nkv - 1); vv[u] = ld_kv16<MEGA>(vc + (size_t)key * E + h * 128 + o * 8); }
+            for (int u = 0; u < B; ++u) { const int key = min(key0 + 16 * u, nkv - 1); vv[u] = ld_kv16(vc + (size_t)key * E + h * 128 + o * 8); }
 #pragma unroll
             for (int u = 0; u < B; ++u) {
                 const int key = key0 + 16 * u;
@@ -745,7 +715,7 @@ __device__ __forceinline__ void attention_head(const float *__restrict__ q, cons
 #pragma unroll
         for (int e = 0; e < 8; ++e) part[g * 128 + o * 8 + e] = acc[e];
     }
-    cta_sync<MEGA>();
+    cta_sync<false>();
     if (tid < 128) {
         float v[16];
 #pragma unroll
@@ -765,7 +735,7 @@ __global__ void __launch_bounds__(256) attn_kernel(const float *__restrict__ q, 
     __shared__ float redf[34];
     __shared__ __align__(16) __half qh[128];
     __shared__ float part[16 * 128];
-    attention_head<false>(q, kc, vc, out, st->n_past + (int)blockIdx.y, (int)blockIdx.x, (int)blockIdx.y, E, n_ctx, kq_scale, tab_exp, smem, red, redf, qh, part);
+    attention_head(q, kc, vc, out, st->n_past + (int)blockIdx.y, (int)blockIdx.x, (int)blockIdx.y, E, n_ctx, kq_scale, tab_exp, smem, red, redf, qh, part);
 }
 
 // ---------------------------------------------------------------------------------------------

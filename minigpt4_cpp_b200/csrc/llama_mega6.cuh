@@ -310,7 +310,7 @@ __device__ __forceinline__ Acc4 dot2_q4_reg(const unsigned char *row0, const uns
 }
 
 // ---- K-quant weights (Q5_K): Q8_K activations -------------------------------------------------------------------------------------------
-// Staged layout = k::stage_act<ACT_Q8_K>: [int8 q: cols][float d: cols / 256][int16 bsums: cols / 16].  Per 256-element super-block (ggml
+// Staged layout = k::stage_act: [int8 q: cols][float d: cols / 256][int16 bsums: cols / 16].  Per 256-element super-block (ggml
 // quantize_row_q8_K): max = the element of largest |x| (first index on ties), iscale = -128 / max, q = min(127, rint(iscale x)), d = 1 / iscale,
 // bsums = sums of 16 q.  One warp per super-block (lane l: elements 8 l .. 8 l + 7), all 15 warps; RMS-normed inputs: warps 0-7 first form the
 // canonical sum of squares (stage_norm_k), every warp folds the 16 warp sums.  Identical bytes to k::stage_act.
@@ -563,7 +563,7 @@ __device__ __forceinline__ void consume6(const Params6 &P, const Smem6 &m, const
     if (TRACE && tr) { tr[4] = t_wait; tr[5] = t_dot; tr[6] = n_units; tr[7] = t_epi; }
 }
 
-// ---- attention of one head (256 threads = warps 0-7 of CTA h): k::attention_head<true> with the CTA-wide reductions restructured for latency
+// ---- attention of one head (256 threads = warps 0-7 of CTA h): k::attention_head with the CTA-wide reductions restructured for latency
 // (4 named-barrier syncs instead of 10: the max comes out of the score loop, the second level of the soft-max sum is done redundantly by every
 // warp).  Every float / double operation and its order are those of k::attention_head (max is order-free), so the output is bit-identical.
 // out-of-line so that the attention code gets its own register allocation (it runs on n_head CTAs only)

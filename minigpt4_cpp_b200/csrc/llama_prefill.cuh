@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256) stage_rows_classmajor(const float *x, int
     extern __shared__ __align__(16) unsigned char sm[];
     __shared__ double red[34];
     const int t = blockIdx.x, nb = cols >> 5;
-    stage_act<ACT, false>(x + (size_t)t * x_stride, norm_w, cols, sm, red);
+    stage_act<ACT>(x + (size_t)t * x_stride, norm_w, cols, sm, red);
     __syncthreads();
     const float *d = (const float *)(sm + cols), *s = d + nb;
     for (int i = threadIdx.x; i < nb * 2; i += 256) {  // 16-byte halves of the blocks: lo plane [b], hi plane [b]

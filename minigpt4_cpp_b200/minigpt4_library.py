@@ -308,7 +308,7 @@ class B200:
         return ms.value, nb.value
 
     def mega_trace(self, ctx) -> np.ndarray:
-        """per-op clock stamps [2 CTAs][n_ops][16] (generation 4: [8]) of the last megakernel launch (needs MINIGPT4_B200_MEGA_TRACE=1 at load)"""
+        """per-op clock stamps [2 CTAs][n_ops][16] of the last megakernel launch (needs MINIGPT4_B200_MEGA_TRACE=1 at load)"""
         buf = np.zeros(2 * 403 * 16, np.int64)
         n = self.L.minigpt4_b200_mega_trace(ctx.ptr, _ptr(buf), buf.size)
         slots = 16 if self.stats(ctx).decode_megakernel >= 6 else 8
