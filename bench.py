@@ -401,7 +401,7 @@ def main():
                     "region": "wall clock of one whole chat turn through the reference C ABI (ctypes, host buffers): minigpt4_encode_image (image H2D, encode, embedding D2H) + "
                               "minigpt4_system_prompt + minigpt4_begin_chat_image (embedding H2D, 32-row prefix, prompt) + 128 x minigpt4_end_chat_image(temp=0) (graph launch, sync, 4-byte D2H each); "
                               "value = 128 tokens / that time",
-                    "decode_calls_only": e2e_decode, "ttft_ms": ttft_ms, "prefill_ms": prefill_ms, "prompt_tokens_incl_system": n_prompt},
+                    "decode_calls_only": e2e_decode, "decode_calls_note": "the first end_chat call also evaluates the queued prompt rows (deferred, merged prefill): per-token host overhead = this minus prefix_ms", "ttft_ms": ttft_ms, "prefill_ms": prefill_ms, "prompt_tokens_incl_system": n_prompt},
             "encode_batch8": encode_batch8(ext, ctx, mg),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "engine": {"decode_megakernel_generation": int(st.decode_megakernel), "prefill_gemm": int(getattr(st, "prefill_gemm", 0))}}
