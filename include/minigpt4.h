@@ -95,7 +95,7 @@ MINIGPT4_API struct MiniGPT4Context *minigpt4_model_load(const char *path, const
                                                          int verbosity, int seed, int n_ctx,
                                                          int n_batch, bool numa);
 /* minigpt4.h:98-99 — OpenCV-only in the reference (minigpt4.cpp:2576-2651; its default build returns OpenCVNotLinked).
- * Here: PNG / PPM / PGM file -> 8-bit RGB (OpenImage (5) for anything else), then Pillow-bicubic resize to 224x224,
+ * Here: PNG / JPEG / PPM / PGM file -> 8-bit RGB (OpenImage (5) for anything else), then Pillow-bicubic resize to 224x224,
  * /255, CLIP mean/std, planar CHW F32 - the tensor minigpt4_encode_image takes. Release both with minigpt4_free_image. */
 MINIGPT4_API int minigpt4_image_load_from_file(struct MiniGPT4Context *ctx, const char *path,
                                                IN struct MiniGPT4Image *image, int flags);

@@ -36,7 +36,7 @@ struct MiniGPT4Context *minigpt4_model_load(const char *path, const char *llm_mo
 }
 
 // Image file -> 8-bit RGB (reference minigpt4.cpp:2576-2596: cv::imread(IMREAD_COLOR) + BGR2RGB, compiled only with OpenCV - its default build
-// returns OpenCVNotLinked).  Decoded here without third-party code: PNG and binary PPM / PGM (csrc/image.cpp); anything else is OpenImage.
+// returns OpenCVNotLinked).  Decoded here without third-party code: PNG, JPEG and binary PPM / PGM (csrc/image.cpp, csrc/jpeg.cpp); anything else is OpenImage.
 // Pixel buffers of MiniGPT4Image are float-array allocations whatever they hold, because minigpt4_free_image releases them as such (:2790-2798).
 int minigpt4_image_load_from_file(struct MiniGPT4Context *, const char *path, struct MiniGPT4Image *image, int) {
     if (!image) return ErrOpenImage;

@@ -6,7 +6,6 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
-#include <thread>
 
 namespace mg4 {
 
@@ -309,8 +308,8 @@ bool decode_image_file(const char *path, RgbImage &out, std::string &err) {
     fclose(f);
     if (buf.size() >= 8 && buf[0] == 0x89 && buf[1] == 'P') return decode_png(buf.data(), buf.size(), out, err);
     if (buf.size() >= 8 && buf[0] == 'P' && (buf[1] == '6' || buf[1] == '5')) return decode_pnm(buf.data(), buf.size(), out, err);
-    if (buf.size() >= 3 && buf[0] == 0xFF && buf[1] == 0xD8) { err = "JPEG is not decoded by this library (PNG, PPM, PGM are): convert the image, or pass pixels to minigpt4_preprocess_image"; return false; }
-    err = "unrecognised image format (PNG, PPM, PGM are decoded)";
+    if (buf.size() >= 3 && buf[0] == 0xFF && buf[1] == 0xD8) return decode_jpeg(buf.data(), buf.size(), out, err);
+    err = "unrecognised image format (PNG, JPEG, PPM, PGM are decoded)";
     return false;
 }
 
@@ -361,15 +360,6 @@ Coeffs precompute(int in_size, int out_size) {
     return c;
 }
 inline uint8_t clip8(int32_t v) { v >>= kPrecisionBits; return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
-
-template <class F> void parallel_rows(int rows, size_t work_per_row, F f) {
-    unsigned nt = std::thread::hardware_concurrency();
-    if (nt > 16) nt = 16;
-    if (nt < 2 || (size_t)rows * work_per_row < (1u << 22)) { f(0, rows); return; }
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t) { const int a = (int)((size_t)rows * t / nt), b = (int)((size_t)rows * (t + 1) / nt); if (b > a) th.emplace_back(f, a, b); }
-    for (auto &x : th) x.join();
-}
 
 }  // namespace
 

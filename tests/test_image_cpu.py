@@ -273,3 +273,208 @@ def test_damaged_png_files_are_rejected_not_crashed_on(tmp_path):
         assert r.returncode == 0, (r.returncode, r.stdout[-200:], r.stderr[-600:])
         ok, bad = int(r.stdout.split()[1]), int(r.stdout.split()[3])
         assert bad > 200, (ok, bad)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# JPEG (csrc/jpeg.cpp).  Pillow decodes with libjpeg-turbo's defaults - the library and settings behind cv::imread in the reference -
+# so equality with Pillow is equality with the reference's pixels.
+# ---------------------------------------------------------------------------------------------------------------------------------------
+def photo(rng, h, w):
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([128 + 100 * np.sin(xx / 17.0) * np.cos(yy / 23.0), 128 + 90 * np.cos(xx / 11.0 + yy / 31.0), (xx * 2 + yy * 3) % 256], -1)
+    return (base + rng.normal(0, 12, (h, w, 3))).clip(0, 255).astype(np.uint8)
+
+
+def load_pixels(lib, path):
+    img, a = load(lib, path)
+    lib.minigpt4_free_image(img)
+    return a
+
+
+@pytest.mark.parametrize("size", [(64, 48), (65, 49), (17, 9), (1, 1), (8, 8), (257, 131), (640, 427)])
+def test_jpeg_written_by_pillow(lib, tmp_path, size):
+    w, h = size
+    a = photo(np.random.default_rng(w * 31 + h), h, w)
+    p = tmp_path / "t.jpg"
+    for kw in (dict(quality=90, subsampling=0), dict(quality=75, subsampling=1), dict(quality=75, subsampling=2), dict(quality=30, subsampling=2, optimize=True),
+               dict(quality=85, subsampling=2, progressive=True), dict(quality=95, subsampling=0, progressive=True),
+               dict(quality=60, subsampling=1, progressive=True, optimize=True), dict(quality=80, subsampling=2, restart_marker_blocks=2),
+               dict(quality=80, subsampling=1, progressive=True, restart_marker_rows=1), dict(quality=90, subsampling=0, keep_rgb=True)):
+        Image.fromarray(a).save(p, "JPEG", **kw)
+        if "restart_marker_blocks" in kw and w * h > 256:
+            assert b"\xff\xd0" in p.read_bytes()
+        assert np.array_equal(load_pixels(lib, p), np.asarray(Image.open(p).convert("RGB"))), (size, kw)
+    Image.fromarray(a[..., 0]).save(p, "JPEG", quality=80)
+    assert np.array_equal(load_pixels(lib, p), np.asarray(Image.open(p).convert("RGB")))
+
+
+def test_jpeg_exif_orientation_is_applied_like_imread(lib, tmp_path):
+    from PIL import ImageOps
+    a = photo(np.random.default_rng(8), 75, 103)
+    p = tmp_path / "o.jpg"
+    for o in range(1, 9):
+        ex = Image.Exif(); ex[0x0112] = o
+        Image.fromarray(a).save(p, "JPEG", quality=85, exif=ex.tobytes())
+        want = np.asarray(ImageOps.exif_transpose(Image.open(p)).convert("RGB"))
+        got = load_pixels(lib, p)
+        assert got.shape == want.shape and np.array_equal(got, want), o
+
+
+ZZ = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+      35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63]
+AC_SYMS = [0x00, 0xF0] + [(r << 4) | s for r in range(16) for s in range(1, 11)]
+
+
+def write_jpeg(path, rgb, samp, interleaved=True, restart=0, q16=False, ids=(1, 2, 3), jfif=True):
+    """A minimal baseline JPEG writer (flat Huffman codes: 4-bit DC categories, 8-bit AC symbols) for the layouts Pillow cannot write:
+    4:4:0, 4:1:1, 4:1:0, chroma at 2x1 under 2x2 luma, one scan per component, 16-bit quantisation tables, fill bytes, odd component ids."""
+    import struct
+    from scipy.fft import dctn
+
+    class BitW:
+        def __init__(s): s.out = bytearray(); s.acc = 0; s.n = 0
+
+        def put(s, v, k):
+            for i in range(k - 1, -1, -1):
+                s.acc = (s.acc << 1) | ((v >> i) & 1); s.n += 1
+                if s.n == 8:
+                    s.out.append(s.acc)
+                    if s.acc == 0xFF: s.out.append(0)
+                    s.acc = 0; s.n = 0
+
+        def flush(s):
+            while s.n: s.put(1, 1)
+
+    def cat(v): return 0 if v == 0 else abs(v).bit_length()
+
+    def enc_block(bw, q, pred):
+        d = int(q[0]) - pred; c = cat(d); bw.put(c, 4)
+        if c: bw.put(d if d > 0 else d + (1 << c) - 1, c)
+        run = 0
+        last = max([k for k in range(1, 64) if q[ZZ[k]] != 0], default=0)
+        for k in range(1, last + 1):
+            v = int(q[ZZ[k]])
+            if v == 0: run += 1; continue
+            while run > 15: bw.put(AC_SYMS.index(0xF0), 8); run -= 16
+            c = cat(v); bw.put(AC_SYMS.index((run << 4) | c), 8); bw.put(v if v > 0 else v + (1 << c) - 1, c); run = 0
+        if last < 63: bw.put(AC_SYMS.index(0x00), 8)
+        return int(q[0])
+
+    H, W, _ = rgb.shape; f = rgb.astype(np.float64)
+    ycc = np.stack([0.299 * f[..., 0] + 0.587 * f[..., 1] + 0.114 * f[..., 2], -0.168736 * f[..., 0] - 0.331264 * f[..., 1] + 0.5 * f[..., 2] + 128,
+                    0.5 * f[..., 0] - 0.418688 * f[..., 1] - 0.081312 * f[..., 2] + 128], -1)
+    hmax = max(s[0] for s in samp); vmax = max(s[1] for s in samp)
+    mcux = -(-W // (8 * hmax)); mcuy = -(-H // (8 * vmax))
+    qt = (np.arange(64).reshape(8, 8) // 4 + 3).astype(np.int64) + (260 if q16 else 0)
+    comps = []
+    for i, (h, v) in enumerate(samp):
+        fx, fy = hmax // h, vmax // v
+        dw, dh = -(-W * h // hmax), -(-H * v // vmax)
+        pl = np.pad(ycc[..., i], ((0, dh * fy - H), (0, dw * fx - W)), mode="edge").reshape(dh, fy, dw, fx).mean((1, 3))
+        bw_, bh_ = mcux * h, mcuy * v
+        pl = np.pad(pl, ((0, bh_ * 8 - dh), (0, bw_ * 8 - dw)), mode="edge")
+        blocks = np.zeros((bh_, bw_, 64), np.int64)
+        for by in range(bh_):
+            for bx in range(bw_):
+                blocks[by, bx] = np.rint(dctn(pl[by * 8:by * 8 + 8, bx * 8:bx * 8 + 8] - 128, norm="ortho") / qt).astype(np.int64).reshape(64)
+        comps.append(dict(h=h, v=v, blocks=blocks, cw=-(-dw // 8), ch=-(-dh // 8)))
+    out = bytearray(b"\xff\xd8")
+    if jfif: out += b"\xff\xe0" + struct.pack(">H", 16) + b"JFIF\0\1\1\0\0\1\0\1\0\0"
+    qz = [int(qt.reshape(64)[ZZ[i]]) for i in range(64)]
+    if q16: out += b"\xff\xdb" + struct.pack(">H", 2 + 1 + 128) + bytes([0x10]) + b"".join(struct.pack(">H", x) for x in qz)
+    else: out += b"\xff\xdb" + struct.pack(">H", 2 + 1 + 64) + bytes([0]) + bytes(qz)
+    out += b"\xff\xc0" + struct.pack(">HBHHB", 8 + 3 * 3, 8, H, W, 3) + b"".join(bytes([ids[i], (samp[i][0] << 4) | samp[i][1], 0]) for i in range(3))
+    out += b"\xff\xc4" + struct.pack(">H", 2 + 17 + 12) + bytes([0x00]) + bytes([0, 0, 0, 12] + [0] * 12) + bytes(range(12))
+    out += b"\xff\xc4" + struct.pack(">H", 2 + 17 + 162) + bytes([0x10]) + bytes([0] * 7 + [162] + [0] * 8) + bytes(AC_SYMS)
+    if restart: out += b"\xff\xdd" + struct.pack(">HH", 4, restart)
+
+    def scan(cis):
+        nonlocal out
+        out += b"\xff\xff\xda" + struct.pack(">HB", 6 + 2 * len(cis), len(cis)) + b"".join(bytes([ids[c], 0x00]) for c in cis) + bytes([0, 63, 0])
+        bw = BitW(); st = dict(pred=[0, 0, 0], cnt=0, rst=0)
+
+        def maybe_restart():
+            if restart and st["cnt"] == restart:
+                bw.flush(); bw.out += bytes([0xFF, 0xD0 + st["rst"]]); st["rst"] = (st["rst"] + 1) & 7; st["pred"] = [0, 0, 0]; st["cnt"] = 0
+        if len(cis) == 1:
+            c = comps[cis[0]]
+            for by in range(c["ch"]):
+                for bx in range(c["cw"]):
+                    maybe_restart(); st["pred"][cis[0]] = enc_block(bw, c["blocks"][by, bx], st["pred"][cis[0]]); st["cnt"] += 1
+        else:
+            for my in range(mcuy):
+                for mx in range(mcux):
+                    maybe_restart()
+                    for ci in cis:
+                        c = comps[ci]
+                        for v in range(c["v"]):
+                            for h in range(c["h"]):
+                                st["pred"][ci] = enc_block(bw, c["blocks"][my * c["v"] + v, mx * c["h"] + h], st["pred"][ci])
+                    st["cnt"] += 1
+        bw.flush(); out += bw.out
+    if interleaved: scan([0, 1, 2])
+    else:
+        for c in (0, 1, 2): scan([c])
+    out += b"\xff\xd9"
+    Path(path).write_bytes(bytes(out))
+
+
+JPEG_LAYOUTS = [("444", [(1, 1)] * 3, {}), ("420", [(2, 2), (1, 1), (1, 1)], {}), ("422", [(2, 1), (1, 1), (1, 1)], {}), ("440", [(1, 2), (1, 1), (1, 1)], {}),
+                ("411", [(4, 1), (1, 1), (1, 1)], {}), ("410", [(4, 2), (1, 1), (1, 1)], {}), ("420_scan_per_component", [(2, 2), (1, 1), (1, 1)], dict(interleaved=False)),
+                ("440_restart2", [(1, 2), (1, 1), (1, 1)], dict(restart=2)), ("420_scan_per_component_restart3", [(2, 2), (1, 1), (1, 1)], dict(interleaved=False, restart=3)),
+                ("422_q16", [(2, 1), (1, 1), (1, 1)], dict(q16=True)), ("chroma2x1_luma2x2", [(2, 2), (2, 1), (2, 1)], {}),
+                ("ids_10_20_30_no_jfif", [(2, 2), (1, 1), (1, 1)], dict(ids=(10, 20, 30), jfif=False))]
+
+
+@pytest.mark.parametrize("name,samp,kw", JPEG_LAYOUTS, ids=[c[0] for c in JPEG_LAYOUTS])
+def test_jpeg_layouts_pillow_cannot_write(lib, tmp_path, name, samp, kw):
+    pytest.importorskip("scipy")
+    for (w, h) in [(61, 45), (16, 16), (33, 7)]:
+        a = photo(np.random.default_rng(w + h), h, w)
+        p = tmp_path / f"{name}.jpg"
+        write_jpeg(p, a, samp, **kw)
+        want = np.asarray(Image.open(p).convert("RGB"))
+        assert np.abs(want.astype(int) - a.astype(int)).mean() < (25 if kw.get("q16") else 12)   # (the writer produced the picture it was given)
+        got = load_pixels(lib, p)
+        assert got.shape == want.shape and np.array_equal(got, want), (name, w, h)
+
+
+JPEG_FUZZ_CHILD = r'''
+import ctypes, io, sys
+import numpy as np
+sys.path.insert(0, sys.argv[2])
+import minigpt4_cpp_b200 as m
+from PIL import Image
+lib = m.load_library()
+rng = np.random.default_rng(int(sys.argv[1]))
+yy, xx = np.mgrid[0:48, 0:64]
+arr = (np.stack([128 + 100 * np.sin(xx / 7.0), 128 + 90 * np.cos(yy / 5.0), (xx * 3 + yy * 5) % 256], -1) + rng.normal(0, 10, (48, 64, 3))).clip(0, 255).astype(np.uint8)
+goods = []
+for kw in (dict(subsampling=2), dict(subsampling=1, progressive=True), dict(subsampling=2, restart_marker_blocks=2)):
+    b = io.BytesIO(); Image.fromarray(arr).save(b, "JPEG", quality=80, **kw); goods.append(b.getvalue())
+img = m.MiniGPT4Image(); ok = bad = 0
+for it in range(900):
+    b = bytearray(goods[it % 3])
+    for _ in range(int(rng.integers(1, 5))):
+        i = int(rng.integers(2, min(len(b), 700) if it & 1 else len(b)))
+        b[i] = int(rng.integers(0, 256)) if rng.integers(0, 3) == 0 else b[i] ^ (1 << int(rng.integers(0, 8)))
+    if it % 7 == 0: b = b[:int(rng.integers(2, len(b)))]
+    open(sys.argv[3], "wb").write(bytes(b))
+    rc = lib.library.minigpt4_image_load_from_file(None, sys.argv[3].encode(), ctypes.pointer(img), 0)
+    assert rc in (0, 5), rc
+    if rc == 0: ok += 1; lib.library.minigpt4_free_image(ctypes.pointer(img))
+    else: bad += 1
+print("ok", ok, "bad", bad)
+'''
+
+
+def test_damaged_jpeg_files_do_not_crash_the_process(tmp_path):
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    child = tmp_path / "child.py"; child.write_text(JPEG_FUZZ_CHILD)
+    for seed in (0, 1):
+        r = subprocess.run([sys.executable, str(child), str(seed), str(root), str(tmp_path / "f.jpg")], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (r.returncode, r.stdout[-200:], r.stderr[-600:])
+        ok, bad = int(r.stdout.split()[1]), int(r.stdout.split()[3])
+        assert ok > 50 and bad > 50, (ok, bad)   # (a damaged scan still decodes to some picture, as with libjpeg; damaged headers are errors)
