@@ -406,7 +406,13 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "engine": {"decode_megakernel_generation": int(st.decode_megakernel), "prefill_gemm": int(getattr(st, "prefill_gemm", 0))}}
 
-    if world > 1 and os.environ.get("MINIGPT4_BENCH_TP", "1") != "0":
+    # tensor-parallel leg: on by default for the degrees that ran on hardware (2 and 4); MINIGPT4_BENCH_TP=1 forces it for any N, =0 disables it
+    tp_env = os.environ.get("MINIGPT4_BENCH_TP")
+    tp_leg = world > 1 and (tp_env == "1" or (tp_env != "0" and world in (2, 4)) or args.mode == "tp")
+    if world > 1 and not tp_leg and tp_env != "0":
+        line["tp"] = {"world": world, "skipped": "tensor parallelism over %d GPUs has not run on hardware yet (2 and 4 have: profiles/r2_bench_*gpu_dp_and_tp.json); "
+                                                "MINIGPT4_BENCH_TP=1 measures it" % world}
+    if tp_leg:
         # the tensor-parallel LLaMA step of north_star on the same GPUs (strong scaling: ONE stream over all ranks), measured next to the
         # replica number: 32-row prefix + N_GEN chained greedy tokens, CUDA events, max over ranks; parity against this rank's own 1-GPU context
         import torch
