@@ -407,7 +407,8 @@ class B200:
 
 class MiniGPT4ChatBot:
     """Chat driver with the reference's surface (reference minigpt4_library.py:568-689): generate() streams tokens,
-    upload_image() encodes an image (PIL image -> torchvision transform, or a ready float32 CHW array)."""
+    upload_image() encodes an image (PIL image -> torchvision transform like the reference, a file path -> the library's own decoder and
+    Pillow-exact preprocess, or a ready float32 CHW array)."""
 
     def __init__(self, model_path: str, llm_model_path: str, verbosity: Verbosity = Verbosity.SILENT, n_threads: int = 0):
         self.library = load_library()
@@ -426,6 +427,12 @@ class MiniGPT4ChatBot:
     def _preprocess(self, image) -> np.ndarray:
         if isinstance(image, np.ndarray):
             return np.ascontiguousarray(image, np.float32).reshape(1, 3, 224, 224)
+        if isinstance(image, (str, os.PathLike)):   # a file: the library's own decode + deterministic preprocess (examples/main.cpp's path)
+            raw = self.library.minigpt4_image_load_from_file(self.ctx, os.fspath(image), 0)
+            pre = self.library.minigpt4_preprocess_image(self.ctx, raw, 0)
+            arr = np.ctypeslib.as_array(C.cast(pre.data, C.POINTER(C.c_float)), shape=(1, 3, 224, 224)).copy()
+            self.library.minigpt4_free_image(raw); self.library.minigpt4_free_image(pre)
+            return arr
         from torchvision import transforms
         from torchvision.transforms.functional import InterpolationMode
         tf = transforms.Compose([transforms.RandomResizedCrop(self.image_size, interpolation=InterpolationMode.BICUBIC), transforms.ToTensor(),

@@ -478,3 +478,15 @@ def test_damaged_jpeg_files_do_not_crash_the_process(tmp_path):
         assert r.returncode == 0, (r.returncode, r.stdout[-200:], r.stderr[-600:])
         ok, bad = int(r.stdout.split()[1]), int(r.stdout.split()[3])
         assert ok > 50 and bad > 50, (ok, bad)   # (a damaged scan still decodes to some picture, as with libjpeg; damaged headers are errors)
+
+
+def test_chatbot_preprocess_accepts_a_file_path(lib, tmp_path):
+    """MiniGPT4ChatBot.upload_image(path) goes through the C ABI's decode + preprocess (no model needed for this half)."""
+    a = photo(np.random.default_rng(4), 120, 200)
+    p = tmp_path / "x.jpg"
+    Image.fromarray(a).save(p, "JPEG", quality=90)
+    bot = m.MiniGPT4ChatBot.__new__(m.MiniGPT4ChatBot)
+    bot.library = lib; bot.ctx = NULL
+    got = bot._preprocess(str(p))
+    _, want = expected_preprocess(np.asarray(Image.open(p).convert("RGB")))
+    assert got.shape == (1, 3, 224, 224) and np.array_equal(got[0], want)
