@@ -5,6 +5,7 @@
 #include "image.h"
 #include <string.h>
 #include <sys/stat.h>
+#include <exception>
 #include <string>
 
 using namespace mg4;
@@ -40,13 +41,18 @@ struct MiniGPT4Context *minigpt4_model_load(const char *path, const char *llm_mo
 // Pixel buffers of MiniGPT4Image are float-array allocations whatever they hold, because minigpt4_free_image releases them as such (:2790-2798).
 int minigpt4_image_load_from_file(struct MiniGPT4Context *, const char *path, struct MiniGPT4Image *image, int) {
     if (!image) return ErrOpenImage;
-    RgbImage im; std::string err;
-    if (!decode_image_file(path, im, err)) { MG4_ERR("%s: %s", path ? path : "(null)", err.c_str()); return ErrOpenImage; }
-    const size_t bytes = im.px.size();
-    float *buf = new float[(bytes + 3) / 4];
-    memcpy(buf, im.px.data(), bytes);
-    image->data = buf; image->width = im.w; image->height = im.h; image->channels = 3; image->format = MINIGPT4_IMAGE_FORMAT_U8;
-    return ErrNone;
+    try {
+        RgbImage im; std::string err;
+        if (!decode_image_file(path, im, err)) { MG4_ERR("%s: %s", path ? path : "(null)", err.c_str()); return ErrOpenImage; }
+        const size_t bytes = im.px.size();
+        float *buf = new float[(bytes + 3) / 4];
+        memcpy(buf, im.px.data(), bytes);
+        image->data = buf; image->width = im.w; image->height = im.h; image->channels = 3; image->format = MINIGPT4_IMAGE_FORMAT_U8;
+        return ErrNone;
+    } catch (const std::exception &e) {   // (an image that does not fit in host memory must not unwind through the C ABI)
+        MG4_ERR("%s: %s", path ? path : "(null)", e.what());
+        return ErrOpenImage;
+    }
 }
 
 // 8-bit RGB of any size -> the encoder's input (reference :2598-2651): Pillow-bicubic resize to 224 x 224, / 255, CLIP mean / std, planar CHW.
@@ -57,10 +63,17 @@ int minigpt4_preprocess_image(struct MiniGPT4Context *, const struct MiniGPT4Ima
     if (image->channels != 3) { MG4_ERR("Image must have 3 channels"); return ErrImageChannelsExpectedRGB; }
     if (image->format != MINIGPT4_IMAGE_FORMAT_U8) { MG4_ERR("Image must be in U8 format"); return ErrImageFormatExpectedU8; }
     if (image->width <= 0 || image->height <= 0 || image->width > 32768 || image->height > 32768) return ErrImageSize;
-    std::vector<uint8_t> small((size_t)224 * 224 * 3);
-    resize_bicubic_u8((const uint8_t *)image->data, image->width, image->height, small.data(), 224, 224);
-    float *out = new float[(size_t)3 * 224 * 224];
-    normalize_to_chw(small.data(), 224, 224, out);
+    float *out = nullptr;
+    try {
+        std::vector<uint8_t> small((size_t)224 * 224 * 3);
+        resize_bicubic_u8((const uint8_t *)image->data, image->width, image->height, small.data(), 224, 224);
+        out = new float[(size_t)3 * 224 * 224];
+        normalize_to_chw(small.data(), 224, 224, out);
+    } catch (const std::exception &e) {
+        MG4_ERR("preprocess: %s", e.what());
+        delete[] out;
+        return ErrImageSize;
+    }
     preprocessed_image->data = out; preprocessed_image->width = 1; preprocessed_image->height = 3 * 224 * 224; preprocessed_image->channels = 1;
     preprocessed_image->format = MINIGPT4_IMAGE_FORMAT_F32;
     return ErrNone;

@@ -3,6 +3,7 @@
 #include "../../include/minigpt4.h"
 #include <string.h>
 #include <algorithm>
+#include <exception>
 
 namespace mg4 {
 
@@ -52,6 +53,9 @@ Error Engine::init(const std::string &path, const std::string &llm_path, int ver
         }
     } catch (const LoadFailure &f) {
         fprintf(stderr, "[minigpt4-b200][error] %s\n", f.msg);
+        return where;
+    } catch (const std::exception &e) {   // (host memory exhausted while reading a file, ...)
+        fprintf(stderr, "[minigpt4-b200][error] %s\n", e.what());
         return where;
     }
     sampler_.reset(new Sampler(seed));

@@ -132,7 +132,7 @@ Error VisionFile::load(const std::string &path) {
     while (c.ok && c.pos < c.n) {
         std::string mname = c.lstr();
         int32_t nt = c.s4();
-        if (!c.ok || nt < 0) return ErrLoadModelFileHeader;
+        if (!c.ok || nt < 0 || (size_t)nt > (c.n - c.pos) / 12) return ErrLoadModelFileHeader;   // (a tensor record is at least 12 bytes: a wild count must not become an allocation)
         std::vector<HostTensor> metas((size_t)nt);
         for (auto &t : metas) {
             t.name = c.lstr();
@@ -175,7 +175,7 @@ bool LlamaFile::load(const std::string &path) {
     if (c.u4() != 0x67676a74u) { MG4_ERR("llama file: bad magic (need ggjt)"); return false; }
     if (c.u4() != 3) { MG4_ERR("llama file: need ggjt version 3"); return false; }
     n_vocab = c.u4(); n_embd = c.u4(); n_mult = c.u4(); n_head = c.u4(); n_layer = c.u4(); n_rot = c.u4(); ftype = c.u4();
-    if (!c.ok || n_vocab == 0 || n_vocab > (1u << 24) || n_head == 0) return false;
+    if (!c.ok || n_vocab == 0 || n_vocab > (1u << 24) || (size_t)n_vocab > (c.n - c.pos) / 8 || n_head == 0) return false;   // (a vocabulary entry is at least 8 bytes)
     vocab.resize(n_vocab);
     for (auto &v : vocab) { uint32_t len = c.u4(); v.text = c.str(len); v.score = c.f4(); if (!c.ok) return false; }
     while (c.ok && c.pos < c.n) {
