@@ -167,14 +167,14 @@ bool inflate_zlib(const uint8_t *src, size_t n, std::vector<uint8_t> &dst, size_
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+struct CrcTable {
+    uint32_t t[256];
+    CrcTable() { for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; t[i] = c; } }
+};
 uint32_t crc32_png(const uint8_t *d, size_t n) {
-    static uint32_t table[256]; static bool ready = false;
-    if (!ready) {
-        for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
-        ready = true;
-    }
+    static const CrcTable table;   // (initialised once, thread-safe)
     uint32_t c = 0xFFFFFFFFu;
-    for (size_t i = 0; i < n; ++i) c = table[(c ^ d[i]) & 255] ^ (c >> 8);
+    for (size_t i = 0; i < n; ++i) c = table.t[(c ^ d[i]) & 255] ^ (c >> 8);
     return c ^ 0xFFFFFFFFu;
 }
 inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
