@@ -13,8 +13,11 @@ pytestmark = pytest.mark.gpu
 def test_full_depth_vision_graph_matches_oracle(lib, ext, orc, mg, tmp_path):
     import bench
     vis = bench.model_dir() / "minigpt4-7b-f16-b39.bin"
-    if not vis.exists():
-        mg.write_minigpt4(vis, mg.VisionSpec(n_blocks=39, n_embd_llm=4096, fast=True))
+    if not vis.exists():   # (written under another name and renamed: an interrupted run must not leave a truncated file where bench.py looks)
+        import os
+        part = vis.with_name(vis.name + f".part{os.getpid()}")
+        mg.write_minigpt4(part, mg.VisionSpec(n_blocks=39, n_embd_llm=4096, fast=True))
+        os.replace(part, vis)
     llm = tmp_path / "llama-4096.bin"
     mg.write_llama_ggjt(llm, mg.LlamaSpec(n_vocab=2048, n_embd=4096, n_head=32, n_layer=2, wtype="q4_1"))
     c = lib.minigpt4_model_load(str(vis), str(llm), 1, 1, 256, 8, 0)
