@@ -76,11 +76,15 @@ def ensure_models(size: str, wtype: str, blocks: int):
     llm = d / f"llama-{size}-{wtype}.bin"
     vis = d / f"minigpt4-{size}-f16-b{blocks}.bin"
     info = d / f"llama-{size}-{wtype}.json"
+    def part(p):   # (files appear under their final name only when complete)
+        return p.with_name(p.name + f".part{os.getpid()}")
     if not (llm.exists() and info.exists()):
-        st = mg.write_llama_ggjt(llm, mg.LlamaSpec(wtype=wtype, **dims))
+        st = mg.write_llama_ggjt(part(llm), mg.LlamaSpec(wtype=wtype, **dims))
+        os.replace(part(llm), llm)
         info.write_text(json.dumps(st))
     if not vis.exists():
-        mg.write_minigpt4(vis, mg.VisionSpec(n_blocks=blocks, n_embd_llm=dims["n_embd"], fast=True))
+        mg.write_minigpt4(part(vis), mg.VisionSpec(n_blocks=blocks, n_embd_llm=dims["n_embd"], fast=True))
+        os.replace(part(vis), vis)
     return str(vis), str(llm), json.loads(info.read_text())
 
 
